@@ -1,0 +1,460 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 hot path (see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload NAME]
+
+Workload (default, BASELINE.json configs[1]): batched 4096-point radix-4 complex FFT, fp32, 65536 frames
+per GPU, in place, frame-major interleaved complex.  One step = one pass of the transform over the whole
+batch (4 GiB of algorithmic HBM traffic).  Steps alternate forward / reverse (the reverse carries the
+1/N scale, same kernel, same bytes) so the data stays bounded and the run checks itself: after an even
+number of steps the batch must equal the input again.
+
+Prints ONE JSON line.  `value` = whole-job Msamples/s with the batch resident in HBM; `e2e` = the same
+through the public host-buffer API (pinned host memory, H2D + D2H inside the timed region);
+`roofline` = algorithmic bytes / CUDA-event kernel time against the measured HBM copy peak;
+`cpu_baseline` = the reference's own CPU implementation (oracle/_ref) on this box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, used only when MEASURED_PEAKS.json is absent
+
+WORKLOADS = {
+    # name: (kind, params)
+    "fft4096_f32": dict(kind="fft", n=4096, frames=65536, precision="f32", bytes_per_sample=16),
+    "fft4096_f64": dict(kind="fft", n=4096, frames=65536, precision="f64", bytes_per_sample=32),
+    "fft1024_f32": dict(kind="fft", n=1024, frames=262144, precision="f32", bytes_per_sample=16),
+    "iir16384_f32": dict(kind="iir", channels=16384, samples=1 << 20, precision="f32", sections=4, bytes_per_sample=8),
+    "iir4096_f32": dict(kind="iir", channels=4096, samples=1 << 22, precision="f32", sections=4, bytes_per_sample=8),
+    "iirscan_f64": dict(kind="iir", channels=1, samples=1 << 30, precision="f64", sections=4, bytes_per_sample=16, path="scan"),
+}
+
+
+def hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    REASONS = {
+        0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x10: "sync_boost",
+        0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown",
+        0x100: "display_clock_setting",
+    }
+
+    def __init__(self, index: int):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.004)
+
+    def start(self):
+        if self.nv:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thread:
+            self._thread.join()
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------------------------------
+def dist_setup(n_gpus: int):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(local)
+    if n_gpus != world:
+        if rank == 0:
+            print(f"warning: --gpus {n_gpus} but WORLD_SIZE={world}; using {world}", file=sys.stderr)
+    return rank, local, world
+
+
+def barrier(world):
+    import torch
+    import torch.distributed as dist
+
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(value: float, world: int) -> float:
+    import torch
+    import torch.distributed as dist
+
+    if world == 1:
+        return value
+    t = torch.tensor([value], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+# --------------------------------------------------------------------------------------------------
+class FftWorkload:
+    def __init__(self, spec, device):
+        import torch
+
+        import simpledsp_b200 as S
+        from simpledsp_b200 import _capi as K
+
+        self.spec, self.S, self.K, self.torch = spec, S, K, torch
+        self.n, self.frames = spec["n"], spec["frames"]
+        self.prec = K.F32 if spec["precision"] == "f32" else K.F64
+        self.rdtype = torch.float32 if self.prec == K.F32 else torch.float64
+        self.radix = 4 if (self.n.bit_length() - 1) % 2 == 0 else 2
+        self.fwd = S.FftPlan(self.n, self.radix, self.prec, K.FORWARD, device)
+        self.inv = S.FftPlan(self.n, self.radix, self.prec, K.REVERSE, device)
+        g = torch.Generator(device="cuda").manual_seed(1234 + device)
+        self.data = torch.randn(self.frames, self.n, 2, device="cuda", generator=g, dtype=self.rdtype)
+        self.check_idx = torch.linspace(0, self.frames - 1, 32).long().cuda()
+        self.orig = self.data[self.check_idx].clone()
+        self.samples_per_step = self.frames * self.n
+        self.step_no = 0
+        self.stream = torch.cuda.current_stream().cuda_stream
+
+    def describe(self):
+        return self.fwd.describe()
+
+    def launches_per_step(self):
+        return self.fwd.launches(self.frames)
+
+    def step(self):
+        plan = self.fwd if self.step_no % 2 == 0 else self.inv
+        plan.exec_ptr(self.data.data_ptr(), self.frames, self.K.PTR_DEVICE, self.stream)
+        self.step_no += 1
+
+    def self_check(self):
+        """After an even number of steps the batch is the input again (forward then reverse)."""
+        if self.step_no % 2:
+            self.step()
+        self.torch.cuda.synchronize()
+        now = self.data[self.check_idx]
+        err = (now - self.orig).pow(2).sum(dim=(1, 2)).sqrt() / self.orig.pow(2).sum(dim=(1, 2)).sqrt()
+        return float(err.max())
+
+    # ---- end to end through the host-buffer API
+    def e2e_prepare(self):
+        import simpledsp_b200._capi as K
+
+        nbytes = self.frames * self.n * 2 * (4 if self.prec == K.F32 else 8)
+        ptr = C.c_void_p()
+        K.check(K.lib().sdsp_b200_host_alloc(C.byref(ptr), nbytes))
+        self._pinned = ptr
+        cdt = np.complex64 if self.prec == K.F32 else np.complex128
+        buf = (C.c_char * nbytes).from_address(ptr.value)
+        self.host = np.frombuffer(buf, dtype=cdt).reshape(self.frames, self.n)
+        rng = np.random.default_rng(99)
+        blk = (rng.standard_normal((1024, self.n)) + 1j * rng.standard_normal((1024, self.n))).astype(cdt)
+        for i in range(0, self.frames, 1024):
+            self.host[i:i + 1024] = blk[: min(1024, self.frames - i)]
+        self.host_first = self.host[:4].copy()
+        self.e2e_steps_done = 0
+        return nbytes, nbytes
+
+    def e2e_step(self):
+        plan = self.fwd if self.e2e_steps_done % 2 == 0 else self.inv
+        plan(self.host)  # public API on a host array: H2D, transform, D2H, synchronous
+        self.e2e_steps_done += 1
+
+    def e2e_check(self):
+        if self.e2e_steps_done % 2:
+            self.e2e_step()
+        err = np.linalg.norm(self.host[:4] - self.host_first) / np.linalg.norm(self.host_first)
+        return float(err)
+
+    def e2e_release(self):
+        import simpledsp_b200._capi as K
+
+        self.host = None
+        K.lib().sdsp_b200_host_free(self._pinned)
+
+
+class IirWorkload:
+    def __init__(self, spec, device):
+        import torch
+
+        import simpledsp_b200 as S
+        from simpledsp_b200 import _capi as K
+
+        self.spec, self.S, self.K, self.torch = spec, S, K, torch
+        self.ch, self.n, self.m = spec["channels"], spec["samples"], spec["sections"]
+        self.prec = K.F32 if spec["precision"] == "f32" else K.F64
+        self.rdtype = torch.float32 if self.prec == K.F32 else torch.float64
+        self.path = K.IIR_SCAN if spec.get("path") == "scan" else K.IIR_AUTO
+        self.bank = S.IirBank(self.m, self.ch, self.prec, K.NUM_GENERIC, device)
+        fs = 100e3
+        ftype = np.where(np.arange(self.ch) % 2 == 0, K.LOW_PASS, K.HIGH_PASS)
+        f0 = np.geomspace(1e3, 20e3, self.ch) if self.ch > 1 else np.array([10e3])
+        uniq = {}
+        gains, bs, as_ = np.zeros(self.ch), np.zeros((self.ch, self.m, 3)), np.zeros((self.ch, self.m, 3))
+        for c in range(self.ch):
+            key = (int(ftype[c]), float(f0[c]))
+            if key not in uniq:
+                uniq[key] = S.design(key[0], self.m, key[1], fs)
+            gains[c], bs[c], as_[c] = uniq[key]
+        self.bank.set_coeffs(gains, bs, as_)
+        g = torch.Generator(device="cuda").manual_seed(1234 + device)
+        self.data = torch.empty(self.ch, self.n, device="cuda", dtype=self.rdtype)
+        rows = max(1, (1 << 28) // self.n)
+        for lo in range(0, self.ch, rows):
+            self.data[lo:lo + rows].normal_(generator=g)
+        self.samples_per_step = self.ch * self.n
+        self.stream = torch.cuda.current_stream().cuda_stream
+
+    def describe(self):
+        return self.bank.describe(self.n, self.n, self.path)
+
+    def launches_per_step(self):
+        return 1
+
+    def step(self):
+        self.bank.process_ptr(self.data.data_ptr(), self.n, self.n, self.K.PTR_DEVICE, self.path, self.stream)
+
+    def self_check(self):
+        self.torch.cuda.synchronize()
+        return float(self.torch.isfinite(self.data[:: max(1, self.ch // 64), :4096]).all().item() == 0)
+
+    def e2e_prepare(self):
+        return None
+
+    def e2e_release(self):
+        pass
+
+
+# --------------------------------------------------------------------------------------------------
+def cpu_reference_rate(spec, threads: int, target_seconds: float = 6.0):
+    """The reference's own CPU implementation on a bounded sample of the workload.
+    -> (Msamples/s, kind, cores, sample description, single-thread Msamples/s)"""
+    from oracle import oracle as O
+
+    kind = "reference" if O.have_ref() else "port"
+    rng = np.random.default_rng(1234)
+    if spec["kind"] == "fft":
+        n = spec["n"]
+        radix = 4 if (n.bit_length() - 1) % 2 == 0 else 2
+        impl = "reference" if kind == "reference" and n <= 4096 else "port"
+        kind = "reference" if impl == "reference" else "port"
+        probe = rng.standard_normal((64, n)) + 1j * rng.standard_normal((64, n))
+        O.fft(probe[:2], radix, False, impl)  # builds the tables
+        t0 = time.perf_counter()
+        O.fft(probe, radix, False, impl, threads=1)
+        one = (time.perf_counter() - t0) / 64
+        frames = int(min(65536, max(threads * 16, target_seconds * threads / one)))
+        x = np.ascontiguousarray(np.tile(probe, (frames // 64 + 1, 1))[:frames])
+        use_threads = threads if impl == "reference" else 1
+        t0 = time.perf_counter()
+        O.fft(x, radix, False, impl, threads=use_threads)
+        dt = time.perf_counter() - t0
+        return (frames * n / dt / 1e6, kind, use_threads,
+                f"{frames} frames x {n}-pt fft_radix{radix} fp64 (the reference is fp64-only), g++ -O3 -DNDEBUG, {use_threads} threads, {dt:.2f} s",
+                n / one / 1e6)
+    ch_total, n_total, m = spec["channels"], spec["samples"], spec["sections"]
+    n = min(n_total, 1 << 18)
+    ch = min(ch_total, max(threads * 2, 16))
+    x = rng.standard_normal((ch, n))
+    ftype = np.where(np.arange(ch) % 2 == 0, 1, 2)
+    f0 = np.geomspace(1e3, 20e3, ch)
+    if kind == "reference":
+        t0 = time.perf_counter()
+        O.iir_bank_reference(x[:1], ftype[:1], f0[:1], 100e3, sections=m, threads=1)
+        one = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        O.iir_bank_reference(x, ftype, f0, 100e3, sections=m, threads=threads)
+        dt = time.perf_counter() - t0
+        use_threads = threads
+    else:
+        t0 = time.perf_counter()
+        O.iir_bank_port(x[:1], ftype[:1], f0[:1], 100e3, sections=m)
+        one = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        O.iir_bank_port(x, ftype, f0, 100e3, sections=m)
+        dt = time.perf_counter() - t0
+        use_threads = 1
+    return (ch * n / dt / 1e6, kind, use_threads,
+            f"{ch} channels x {n} samples casc_2o_iir<{m}> fp64, one object per channel, {use_threads} threads, {dt:.2f} s",
+            n / one / 1e6)
+
+
+def run_reference(args, spec, workload_name):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    for _ in range(max(1, min(args.warmup, 1))):
+        cpu_reference_rate(spec, threads, target_seconds=1.0)
+    rates = []
+    t0 = time.perf_counter()
+    steps = max(1, min(args.steps, 5))
+    last = None
+    for _ in range(steps):
+        last = cpu_reference_rate(spec, threads, target_seconds=4.0)
+        rates.append(last[0])
+    wall = time.perf_counter() - t0
+    value = float(np.mean(rates))
+    out = {
+        "impl": "reference", "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": wall / steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name, **{k: v for k, v in spec.items() if k != "kind"}},
+        "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": last[2], "kind": last[1], "sample": last[3],
+                         "single_thread": last[4]},
+        "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out))
+
+
+# --------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="fft4096_f32", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--frames", type=int, default=0, help="override frames (fft) for quick runs")
+    args = ap.parse_args()
+    spec = dict(WORKLOADS[args.workload])
+    if args.frames and spec["kind"] == "fft":
+        spec["frames"] = args.frames
+
+    if args.impl == "reference":
+        run_reference(args, spec, args.workload)
+        return
+
+    import torch
+
+    warmup = max(args.warmup, 3)
+    steps = max(args.steps, 1)
+    rank, local, world = dist_setup(args.gpus)
+    wl = (FftWorkload if spec["kind"] == "fft" else IirWorkload)(spec, local)
+
+    for _ in range(warmup):
+        wl.step()
+    barrier(world)
+
+    sampler = ClockSampler(local)
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    sampler.start()
+    barrier(world)
+    evs[0].record()
+    for i in range(steps):
+        wl.step()
+        evs[i + 1].record()
+    barrier(world)
+    clocks = sampler.stop()
+    total_ms = evs[0].elapsed_time(evs[-1])
+    per_step = np.array([evs[i].elapsed_time(evs[i + 1]) for i in range(steps)])
+    total_ms_max = max_over_ranks(total_ms, world)
+    check = wl.self_check()
+
+    samples = wl.samples_per_step * steps * world
+    value = samples / (total_ms_max * 1e-3) / 1e6
+    peak, peak_src = hbm_peak()
+    launches = wl.launches_per_step()
+    kernel_ms = float(per_step.mean()) / max(1, launches)
+    alg_bytes = wl.samples_per_step * spec["bytes_per_sample"] / max(1, launches)
+    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+
+    # ---- end to end (host buffers through the public API), rank-local, max over ranks
+    e2e = None
+    if not args.no_e2e and spec["kind"] == "fft":
+        h2d, d2h = wl.e2e_prepare()
+        e2e_steps = max(2, min(steps, 6))
+        wl.e2e_step()  # warm-up (allocates staging)
+        wl.e2e_step()
+        barrier(world)
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            wl.e2e_step()
+        barrier(world)
+        e2e_s = max_over_ranks(time.perf_counter() - t0, world)
+        e2e_err = wl.e2e_check()
+        wl.e2e_release()
+        e2e = {"value": wl.samples_per_step * e2e_steps * world / e2e_s / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3, "roundtrip_rel_err": e2e_err,
+               "api": "simpledsp_b200.FftPlan.__call__(numpy view of pinned host memory) -> sdsp_b200_fft_exec(PTR_HOST)"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        r = cpu_reference_rate(spec, os.cpu_count() or 1)
+        cpu = {"value": r[0], "unit": "Msamples/s", "cores": r[2], "kind": r[1], "sample": r[3], "single_thread": r[4]}
+
+    if rank == 0:
+        out = {
+            "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": total_ms_max / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": spec["precision"], "data": "synthetic",
+            "config": {"workload": args.workload, **{k: v for k, v in spec.items() if k != "kind"},
+                       "per_gpu": True, "in_place": True, "l2": "working set per step is far larger than the 126 MB L2",
+                       "steps_alternate": "forward/reverse" if spec["kind"] == "fft" else "n/a", "plan": wl.describe()},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0,
+                         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kernel_ms},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches * steps), "clocks": clocks,
+            "self_check": {"roundtrip_rel_err" if spec["kind"] == "fft" else "nonfinite": check},
+            "step_ms": {"min": float(per_step.min()), "median": float(np.median(per_step)), "max": float(per_step.max())},
+        }
+        print(json.dumps(out))
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,167 @@
+/*
+ * sdsp_b200.h -- C ABI of libsdsp_b200.so: the B200 (sm_100a) implementation of simpledsp's two
+ * data-parallel hot paths, batched.
+ *
+ * simpledsp itself has no FFI: its hot path is a header-only C++ template API
+ * (namespace sdsp, include/sdsp/fft.h and include/sdsp/casc_2o_iir.h in the reference).  This file is
+ * the one process/device boundary the B200 build introduces.  The drop-in headers shipped beside it
+ * (include/sdsp/fft.h, include/sdsp/casc_2o_iir.h, include/sdsp/filter_type.h) keep the reference's
+ * names and signatures and forward to the entry points below; any other language binds the same
+ * symbols (see INTEGRATION.md for the ctypes / cgo / JNI stubs).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every function returns an int status (0 = ok) and records a
+ *     message retrievable with sdsp_b200_last_error() (thread local).
+ *   - complex data is interleaved (re, im), exactly std::complex<T>[n] / sdsp::complex_array<N>
+ *     (reference include/sdsp/fft.h:51-52); frames are contiguous: data[frame][n].
+ *   - IIR data is planar channel-major: data[channel * channel_stride + sample]; one contiguous
+ *     range per filter object, as in reference casc_2o_iir.h:36-80 (process(begin, end)).
+ *   - all transforms and filters run IN PLACE (reference fft.h:290-291, 342-345; casc_2o_iir.h:71).
+ *   - ptr_kind says whether `data` is a host pointer (the library stages it through device memory,
+ *     synchronously) or a device pointer on the handle's device (asynchronous on `stream`).
+ *   - `stream` is a cudaStream_t passed as void*; NULL = the legacy default stream.
+ *   - there is NO CPU fallback: without a usable CUDA device every compute entry point fails with
+ *     SDSP_B200_ERR_NO_DEVICE / SDSP_B200_ERR_CUDA.
+ */
+#ifndef SDSP_B200_H
+#define SDSP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDSP_B200_VERSION 100 /* 0.1.0 */
+
+enum sdsp_b200_status {
+    SDSP_B200_OK = 0,
+    SDSP_B200_ERR_INVALID_ARG = 1,
+    SDSP_B200_ERR_UNSUPPORTED = 2, /* size / radix / section count outside what is built */
+    SDSP_B200_ERR_CUDA = 3,
+    SDSP_B200_ERR_OOM = 4,
+    SDSP_B200_ERR_NO_DEVICE = 5
+};
+
+enum sdsp_b200_precision { SDSP_B200_F32 = 0, SDSP_B200_F64 = 1 };
+/* reference fft.h:121-146: forward_fft (Sign +1, no scaling) / reverse_fft (Sign -1, times 1.0/N) */
+enum sdsp_b200_direction { SDSP_B200_FORWARD = 0, SDSP_B200_REVERSE = 1 };
+enum sdsp_b200_ptr_kind { SDSP_B200_PTR_HOST = 0, SDSP_B200_PTR_DEVICE = 1 };
+/* reference filter_type.h:6 -- same values */
+enum sdsp_b200_filter_type { SDSP_B200_FILTER_NONE = 0, SDSP_B200_LOW_PASS = 1, SDSP_B200_HIGH_PASS = 2, SDSP_B200_BAND_PASS = 3 };
+/* which class of the reference a bank mirrors: casc_2o_iir (runtime numerator, casc_2o_iir.h:8-215)
+ * or casc_2o_iir_lp / _hp / _bp (numerators {1,2,1} {1,-2,1} {1,0,-1} hard-wired, :266-468) */
+enum sdsp_b200_numerator { SDSP_B200_NUM_GENERIC = 0, SDSP_B200_NUM_LP = 1, SDSP_B200_NUM_HP = 2, SDSP_B200_NUM_BP = 3 };
+/* how a bank walks the time axis */
+enum sdsp_b200_iir_path {
+    SDSP_B200_IIR_AUTO = 0,       /* pure function of the bank configuration, never of call length alone */
+    SDSP_B200_IIR_SEQUENTIAL = 1, /* lane per channel, samples in order; bit-identical however a stream is cut into calls */
+    SDSP_B200_IIR_SCAN = 2        /* chunked state-space scan along time (reassociates; fp64 error ~1e-13 of peak) */
+};
+
+typedef struct sdsp_b200_fft_plan_s *sdsp_b200_fft_plan;
+typedef struct sdsp_b200_iir_bank_s *sdsp_b200_iir_bank;
+
+/* ---------------------------------------------------------------- runtime */
+int sdsp_b200_version(void);
+const char *sdsp_b200_last_error(void);
+int sdsp_b200_device_count(int *count);
+/* creates the context on `device` and checks it is sm_100; optional (plans do it lazily) */
+int sdsp_b200_init(int device);
+int sdsp_b200_shutdown(void);
+/* pinned host buffers for callers that want full-speed staging of host data */
+int sdsp_b200_host_alloc(void **ptr, size_t bytes);
+int sdsp_b200_host_free(void *ptr);
+int sdsp_b200_device_alloc(void **ptr, size_t bytes, int device);
+int sdsp_b200_device_free(void *ptr, int device);
+int sdsp_b200_memcpy(void *dst, const void *src, size_t bytes, int device); /* any direction, synchronous */
+int sdsp_b200_device_synchronize(int device);
+
+/* ---------------------------------------------------------------- FFT
+ * Replaces sdsp::fft_radix2<T,N>(complex_array<N>&) (reference include/sdsp/fft.h:258-299) and
+ * sdsp::fft_radix4<T,N>(complex_array<N>&) (:301-360), batched over n_frames frames.
+ *   radix 2: n must be a power of 2 (static_assert at fft.h:261)
+ *   radix 4: n must be a power of 4 (static_assert at fft.h:304)
+ * Both produce the same transform: natural-order in, natural-order out, unnormalised forward,
+ * 1/N-scaled reverse.  radix selects the argument check, not the arithmetic: on the device the
+ * frame is factored into register-resident radix-16/8/4/2 passes. */
+int sdsp_b200_fft_plan_create(sdsp_b200_fft_plan *plan, uint32_t n, int radix, int precision, int direction, int device);
+int sdsp_b200_fft_plan_destroy(sdsp_b200_fft_plan plan);
+int sdsp_b200_fft_exec(sdsp_b200_fft_plan plan, void *data, size_t n_frames, int ptr_kind, void *stream);
+/* human-readable description of the factorisation / launch geometry the plan chose */
+int sdsp_b200_fft_plan_describe(sdsp_b200_fft_plan plan, char *buf, size_t buf_len);
+/* number of kernel launches one exec of n_frames device-resident frames issues */
+int sdsp_b200_fft_plan_launches(sdsp_b200_fft_plan plan, size_t n_frames, int *launches);
+
+/* Digit-reversal tables, computed on the device (reference fft.h:217-236 digit_reverse<N,base>,
+ * :238-256 calc_swap_lookup<N,base>).  base 2 or 4.  half_table = 0: out[i] = rev(i);
+ * half_table = 1: the reference's swap table (the higher index of every pair maps to itself).
+ * `out` is a host array of n uint32.  Parity requirement: bit-exact. */
+int sdsp_b200_digit_reverse_table(uint32_t n, uint32_t base, int half_table, uint32_t *out, int device);
+/* Apply out[rev(i)] = in[i] to n_frames frames in place on the device (the permutation stage of
+ * fft.h:269-273 / 351-355 as a stand-alone operator). */
+int sdsp_b200_digit_reverse_permute(void *data, uint32_t n, uint32_t base, int precision, size_t n_frames,
+                                    int ptr_kind, int device, void *stream);
+
+/* ---------------------------------------------------------------- cascaded biquad IIR
+ * A bank is n_channels independent filter objects of one class and one section count
+ * (reference casc_2o_iir<m_t>, casc_2o_iir.h:8-215).  Coefficients and history live on the device.
+ * sections = m_t (1..8; the reference insists on even m_t, casc_2o_iir.h:25 -- the drop-in header keeps
+ * that static_assert, the ABI does not need it). */
+int sdsp_b200_iir_bank_create(sdsp_b200_iir_bank *bank, int sections, size_t n_channels, int precision,
+                              int numerator, int device);
+int sdsp_b200_iir_bank_destroy(sdsp_b200_iir_bank bank);
+/* Upload coefficients for channels [first, first+count).  Host arrays of doubles laid out like the
+ * reference's members: gain[count] (m_gain), b[count][sections][3] (m_b_coeff), a[count][sections][3]
+ * (m_a_coeff).  b[..][0] and a[..][0] are ignored (b0 == 1 implicitly, a0 never read:
+ * casc_2o_iir.h:64-69).  b may be NULL for the fixed-numerator banks.  Does not touch history
+ * (= copy_coeff_from, casc_2o_iir.h:28-34). */
+int sdsp_b200_iir_bank_set_coeffs(sdsp_b200_iir_bank bank, size_t first, size_t count, const double *gain,
+                                  const double *b, const double *a);
+/* History for channels [first, first+count): mem[count][sections+1][2] = for every row of the
+ * reference's m_mem (row 0 = scaled input, row j = output of section j-1) the two most recent
+ * values {x[n-1], x[n-2]}.  (The reference's 3-slot ring + m_pos, casc_2o_iir.h:11,15, is private;
+ * only this information is observable.) */
+int sdsp_b200_iir_bank_set_state(sdsp_b200_iir_bank bank, size_t first, size_t count, const double *mem);
+int sdsp_b200_iir_bank_get_state(sdsp_b200_iir_bank bank, size_t first, size_t count, double *mem);
+int sdsp_b200_iir_bank_reset_state(sdsp_b200_iir_bank bank);
+/* casc_2o_iir<m_t>::process(begin, end) (casc_2o_iir.h:36-80) over every channel of the bank:
+ * data[c * channel_stride + i], i < n_samples, filtered in place; history carries to the next call.
+ * path: sdsp_b200_iir_path. */
+int sdsp_b200_iir_bank_process(sdsp_b200_iir_bank bank, void *data, size_t n_samples, size_t channel_stride,
+                               int ptr_kind, int path, void *stream);
+int sdsp_b200_iir_bank_describe(sdsp_b200_iir_bank bank, size_t n_samples, size_t channel_stride, int path,
+                                char *buf, size_t buf_len);
+
+/* Butterworth designers, host scalar code (reference casc_2o_iir.h:168-194 set_lp_coeff,
+ * :140-166 set_hp_coeff, :82-138 set_bp_coeff).  Outputs: *gain, b[sections][3], a[sections][3]. */
+int sdsp_b200_iir_design_lp(int sections, double f0, double fs, double gain_in, double *gain, double *b, double *a);
+int sdsp_b200_iir_design_hp(int sections, double f0, double fs, double gain_in, double *gain, double *b, double *a);
+int sdsp_b200_iir_design_bp(int sections, double f0, double fs, double q, double gain_in, double *gain, double *b,
+                            double *a);
+/* preload_filter(value) (casc_2o_iir.h:196-214): steady-state history mem[sections+1][2] */
+int sdsp_b200_iir_preload_state(int sections, int filter_type, double gain, const double *b, const double *a,
+                                double value, double *mem);
+
+/* One-shot convenience used by the drop-in header for a single filter object held on the host:
+ * uploads {gain,b,a,mem}, filters data[0..n) in place on the device (sequential path), downloads the
+ * new history.  precision is that of `data`. */
+int sdsp_b200_iir_process_once(int sections, int numerator, int precision, double gain, const double *b,
+                               const double *a, double *mem, void *data, size_t n_samples, int device);
+
+/* ---------------------------------------------------------------- debugging / verification aids
+ * Host-side execution of the very code the kernels run per thread (same templates, compiled for the
+ * host), so index arithmetic and rounding behaviour can be checked where no GPU exists.  NOT a
+ * fallback: nothing in the library calls these. */
+int sdsp_b200_debug_emulate_fft(uint32_t n, int precision, int direction, void *data, size_t n_frames);
+int sdsp_b200_debug_emulate_iir(int sections, int numerator, int precision, double gain, const double *b,
+                                const double *a, double *mem, void *data, size_t n_samples);
+int sdsp_b200_debug_emulate_iir_scan(int sections, int numerator, int precision, double gain, const double *b,
+                                     const double *a, double *mem, void *data, size_t n_samples,
+                                     int chunk, int tile_chunks);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDSP_B200_H */

@@ -1,0 +1,608 @@
+// fft.cu -- batched complex FFT for sm_100a: kernels, plans and the C-ABI entry points.
+//
+// Replaces sdsp::fft_radix2 / sdsp::fft_radix4 (reference include/sdsp/fft.h:258-299, :301-360) and the
+// compile-time tables behind them (calc_wCoeffs :197-214, calc_swap_lookup :238-256), for batches of
+// frames resident in HBM.  See fft_core.cuh for the factorisation and DESIGN.md for the roofline.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "fft_core.cuh"
+
+namespace sdsp_b200
+{
+// =================================================================================================
+// twiddles.  exp(-2*pi*i*num/den) for den a power of two, evaluated in long double on the first
+// octant only and mirrored, so the table has the exact symmetries (and exact 0 / +-1 / equal
+// cos = sin at 45 degrees) that the reference's quarter-wave construction has (fft.h:148-194).
+static void unit_root(uint64_t num, uint64_t den, long double &re, long double &im)
+{
+    num %= den;
+    if (den < 8) { // den in {1,2,4}: all roots are exact
+        const int q = (int)(num * 4 / den);
+        static const int cr[4] = { 1, 0, -1, 0 }, ci[4] = { 0, -1, 0, 1 };
+        re = cr[q];
+        im = ci[q];
+        return;
+    }
+    const uint64_t oct = den / 8;
+    const uint64_t o = num / oct; // octant 0..7
+    const uint64_t r = num % oct;
+    // angle inside the octant, folded to [0, pi/4]
+    const bool fold = (o & 1) != 0;
+    const uint64_t rr = fold ? (oct - r) : r;
+    const long double ang = 2.0L * 3.14159265358979323846264338327950288L * (long double)rr / (long double)den;
+    long double c = cosl(ang), s = sinl(ang);
+    if (rr == 0) {
+        c = 1.0L;
+        s = 0.0L;
+    } else if (rr == oct) {
+        c = s = 0.70710678118654752440084436210484903928L;
+    }
+    if (fold) {
+        const long double t = c;
+        c = s;
+        s = t;
+    }
+    // now (c, s) = (cos, sin) of the angle reduced into the first quadrant position within quadrant o/2
+    long double cq, sq; // cos/sin of full angle theta = 2*pi*num/den
+    switch (o / 2) {
+    case 0: cq = c; sq = s; break;
+    case 1: cq = -s; sq = c; break;
+    case 2: cq = -c; sq = -s; break;
+    default: cq = s; sq = -c; break;
+    }
+    re = cq;
+    im = -sq;
+}
+
+template <typename T>
+static void build_twiddles(int n, const int *radix, int npass, std::vector<cplx<T>> &out)
+{
+    out.clear();
+    int pp = 1;
+    for (int p = 0; p + 1 < npass; p++) {
+        const int r = radix[p];
+        const int np = n / pp;
+        const int m_range = np / r;
+        for (int k = 1; k < r; k++)
+            for (int m = 0; m < m_range; m++) {
+                long double re, im;
+                unit_root((uint64_t)m * (uint64_t)k, (uint64_t)np, re, im);
+                out.push_back(cplx<T>{ (T)re, (T)im });
+            }
+        pp *= r;
+    }
+}
+
+// =================================================================================================
+// the single-CTA kernel: FPC frames per CTA, TPF threads per frame, E points per thread
+template <typename T>
+__device__ __forceinline__ cplx<T> ld_stream(const cplx<T> *p)
+{
+    return *p;
+}
+template <typename T>
+__device__ __forceinline__ void st_stream(cplx<T> *p, cplx<T> v)
+{
+    *p = v;
+}
+
+template <class Cfg, typename T, int THREADS, int MINB, int P>
+__device__ __forceinline__ void fft_kernel_passes(cplx<T> (&v)[Cfg::E], cplx<T> *fs, const cplx<T> *__restrict__ tw, int t)
+{
+    if constexpr (P < Cfg::NPASS) {
+        if constexpr (P > 0) {
+#pragma unroll
+            for (int e = 0; e < Cfg::E; e++)
+                v[e] = fs[Cfg::pad(t + Cfg::S * e)];
+            if constexpr (P + 1 < Cfg::NPASS)
+                __syncthreads(); // everyone has read before this pass overwrites the exchange buffer
+        }
+        fft_pass<Cfg, P, T>(v, t, tw);
+        if constexpr (P + 1 < Cfg::NPASS) {
+#pragma unroll
+            for (int e = 0; e < Cfg::E; e++)
+                fs[Cfg::pad(fft_out_pos<Cfg, P>(t, e))] = v[e];
+            __syncthreads();
+            fft_kernel_passes<Cfg, T, THREADS, MINB, P + 1>(v, fs, tw, t);
+        }
+    }
+}
+
+template <class Cfg, typename T, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+    fft_cta_kernel(cplx<T> *__restrict__ data, const cplx<T> *__restrict__ tw, size_t n_frames, int inverse, T scale)
+{
+    constexpr int FPC = THREADS / Cfg::TPF;
+    static_assert(THREADS % Cfg::TPF == 0 && FPC >= 1, "block must hold whole frames");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx<T> *smem = reinterpret_cast<cplx<T> *>(smem_raw);
+    const int fl = threadIdx.x / Cfg::TPF;
+    const int t = threadIdx.x % Cfg::TPF;
+    cplx<T> *fs = smem + (size_t)fl * Cfg::PADDED_N;
+    const size_t groups = (n_frames + FPC - 1) / FPC;
+
+    for (size_t g = blockIdx.x; g < groups; g += gridDim.x) {
+        const size_t frame = g * FPC + fl;
+        const bool active = frame < n_frames;
+        cplx<T> *gp = data + frame * (size_t)Cfg::N + t;
+        cplx<T> v[Cfg::E];
+        if (active) {
+#pragma unroll
+            for (int e = 0; e < Cfg::E; e++)
+                v[e] = ld_stream(gp + Cfg::S * e);
+        } else {
+#pragma unroll
+            for (int e = 0; e < Cfg::E; e++)
+                v[e] = cplx<T>{ 0, 0 };
+        }
+        if (inverse) { // IDFT(x) = swap(DFT(swap(x))) / N
+#pragma unroll
+            for (int e = 0; e < Cfg::E; e++)
+                v[e] = cplx<T>{ v[e].y, v[e].x };
+        }
+        fft_kernel_passes<Cfg, T, THREADS, MINB, 0>(v, fs, tw, t);
+        if (inverse) {
+#pragma unroll
+            for (int e = 0; e < Cfg::E; e++)
+                v[e] = cplx<T>{ v[e].y * scale, v[e].x * scale };
+        }
+        if (active) {
+#pragma unroll
+            for (int e = 0; e < Cfg::E; e++)
+                st_stream(gp + Cfg::S * e, v[e]);
+        }
+        if constexpr (Cfg::NPASS > 1)
+            __syncthreads(); // last pass has read the exchange buffer before the next group writes it
+    }
+}
+
+// =================================================================================================
+// digit reversal on the device (reference fft.h:217-236).  Base 2: bit reversal of the log2(n) low
+// bits; base 4: the same with the two bits of every digit kept in order.
+__device__ __forceinline__ uint32_t digit_reverse_dev(uint32_t i, int log2n, uint32_t base)
+{
+    uint32_t r = __brev(i) >> (32 - log2n);
+    if (base == 4)
+        r = ((r & 0xAAAAAAAAu) >> 1) | ((r & 0x55555555u) << 1);
+    return r;
+}
+
+__global__ void digit_reverse_table_kernel(uint32_t *out, uint32_t n, int log2n, uint32_t base, int half_table)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    uint32_t r = digit_reverse_dev(i, log2n, base);
+    // calc_swap_lookup (fft.h:249-254): of every pair only the lower index keeps its partner, so a
+    // linear sweep swaps once.  Entries 0 and n-1 are fixed points anyway.
+    if (half_table && r < i)
+        r = i;
+    out[i] = r;
+}
+
+template <typename T>
+__global__ void digit_reverse_permute_kernel(cplx<T> *data, uint32_t n, int log2n, uint32_t base, size_t n_frames)
+{
+    // one thread per pair (i, rev(i)) with i < rev(i): an in-place swap touches every element once
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = n_frames * (size_t)n;
+    if (gid >= total)
+        return;
+    const size_t frame = gid / n;
+    const uint32_t i = (uint32_t)(gid % n);
+    const uint32_t r = digit_reverse_dev(i, log2n, base);
+    if (r > i) {
+        cplx<T> *f = data + frame * n;
+        const cplx<T> a = f[i], b = f[r];
+        f[i] = b;
+        f[r] = a;
+    }
+}
+
+// =================================================================================================
+// plans
+struct FftPlan;
+typedef int (*fft_launch_fn)(const FftPlan &, void *data, size_t n_frames, cudaStream_t stream);
+typedef void (*fft_emulate_fn)(void *frame, const void *tw, bool inverse);
+
+struct FftPlan {
+    uint32_t n = 0;
+    int radix = 2, precision = 0, direction = 0, device = 0;
+    int npass = 0, radices[4] = { 1, 1, 1, 1 }, e = 0, threads = 0, frames_per_cta = 0, min_blocks = 0;
+    size_t smem_bytes = 0;
+    int ctas_per_sm = 0, sm_count = 0;
+    void *d_tw = nullptr;
+    size_t tw_bytes = 0;
+    fft_launch_fn launch = nullptr;
+    // host staging (ptr_kind == HOST)
+    void *d_stage = nullptr;
+    size_t stage_bytes = 0;
+    std::mutex mu;
+};
+
+template <class Cfg, typename T, int THREADS, int MINB>
+static int launch_cta(const FftPlan &p, void *data, size_t n_frames, cudaStream_t stream)
+{
+    constexpr int FPC = THREADS / Cfg::TPF;
+    const size_t groups = (n_frames + FPC - 1) / FPC;
+    if (groups == 0)
+        return SDSP_B200_OK;
+    const size_t resident = (size_t)p.sm_count * (size_t)p.ctas_per_sm;
+    // persistent-style grid: a whole number of waves, each CTA strides over frame groups
+    size_t grid = groups < resident * 4 ? groups : resident * 4;
+    const T scale = (T)(1.0 / (double)Cfg::N);
+    fft_cta_kernel<Cfg, T, THREADS, MINB><<<(unsigned)grid, THREADS, p.smem_bytes, stream>>>(
+        reinterpret_cast<cplx<T> *>(data), reinterpret_cast<const cplx<T> *>(p.d_tw), n_frames,
+        p.direction == SDSP_B200_REVERSE ? 1 : 0, scale);
+    SDSP_CUDA(cudaGetLastError());
+    return SDSP_B200_OK;
+}
+
+template <class Cfg, typename T, int THREADS, int MINB>
+static int setup_cta(FftPlan &p)
+{
+    constexpr int FPC = THREADS / Cfg::TPF;
+    p.npass = Cfg::NPASS;
+    p.radices[0] = Cfg::R0;
+    p.radices[1] = Cfg::R1;
+    p.radices[2] = Cfg::R2;
+    p.radices[3] = Cfg::R3;
+    p.e = Cfg::E;
+    p.threads = THREADS;
+    p.frames_per_cta = FPC;
+    p.min_blocks = MINB;
+    p.smem_bytes = Cfg::NPASS > 1 ? (size_t)FPC * Cfg::PADDED_N * sizeof(cplx<T>) : 0;
+    auto kern = fft_cta_kernel<Cfg, T, THREADS, MINB>;
+    if (p.smem_bytes > 48 * 1024)
+        SDSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
+    int occ = 0;
+    SDSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, p.smem_bytes));
+    if (occ < 1)
+        return set_error(SDSP_B200_ERR_UNSUPPORTED, "fft kernel for n=%u does not fit on an SM", p.n);
+    p.ctas_per_sm = occ;
+    p.launch = &launch_cta<Cfg, T, THREADS, MINB>;
+    std::vector<cplx<T>> tw;
+    build_twiddles<T>(Cfg::N, p.radices, Cfg::NPASS, tw);
+    p.tw_bytes = tw.size() * sizeof(cplx<T>);
+    if (p.tw_bytes) {
+        SDSP_CUDA(cudaMalloc(&p.d_tw, p.tw_bytes));
+        SDSP_CUDA(cudaMemcpy(p.d_tw, tw.data(), p.tw_bytes, cudaMemcpyHostToDevice));
+    }
+    return SDSP_B200_OK;
+}
+
+template <class Cfg, typename T>
+static void emulate_cfg(void *frame, bool inverse)
+{
+    int radices[4] = { Cfg::R0, Cfg::R1, Cfg::R2, Cfg::R3 };
+    std::vector<cplx<T>> tw;
+    build_twiddles<T>(Cfg::N, radices, Cfg::NPASS, tw);
+    tw.push_back(cplx<T>{ 1, 0 });
+    fft_emulate_frame<Cfg, T>(reinterpret_cast<cplx<T> *>(frame), tw.data(), inverse, (T)(1.0 / (double)Cfg::N));
+}
+
+// the factorisation table: log2(n) -> configuration.  16 points per thread wherever the frame has them.
+template <int LG>
+struct CfgFor;
+#define SDSP_FFT_CFG(LG, THREADS_, MINB_, ...)   \
+    template <>                                  \
+    struct CfgFor<LG> {                          \
+        using type = FftCfg<__VA_ARGS__>;        \
+        static constexpr int THREADS = THREADS_; \
+        static constexpr int MINB = MINB_;       \
+    };
+SDSP_FFT_CFG(1, 256, 4, 2, 2, 2)
+SDSP_FFT_CFG(2, 256, 4, 4, 4, 4)
+SDSP_FFT_CFG(3, 256, 4, 8, 8, 8)
+SDSP_FFT_CFG(4, 256, 3, 16, 16, 16)
+SDSP_FFT_CFG(5, 256, 3, 32, 16, 16, 2)
+SDSP_FFT_CFG(6, 256, 3, 64, 16, 16, 4)
+SDSP_FFT_CFG(7, 256, 3, 128, 16, 16, 8)
+SDSP_FFT_CFG(8, 256, 3, 256, 16, 16, 16)
+SDSP_FFT_CFG(9, 256, 3, 512, 16, 16, 16, 2)
+SDSP_FFT_CFG(10, 256, 3, 1024, 16, 16, 16, 4)
+SDSP_FFT_CFG(11, 256, 3, 2048, 16, 16, 16, 8)
+SDSP_FFT_CFG(12, 256, 3, 4096, 16, 16, 16, 16)
+SDSP_FFT_CFG(13, 512, 1, 8192, 16, 16, 16, 16, 2)
+SDSP_FFT_CFG(14, 1024, 1, 16384, 16, 16, 16, 16, 4)
+#undef SDSP_FFT_CFG
+
+static constexpr int MAX_LOG2N_F32 = 14;
+static constexpr int MAX_LOG2N_F64 = 13;
+
+template <int LG>
+static int setup_for(FftPlan &p)
+{
+    using C = CfgFor<LG>;
+    if (p.precision == SDSP_B200_F32)
+        return setup_cta<typename C::type, float, C::THREADS, C::MINB>(p);
+    if constexpr (LG <= MAX_LOG2N_F64)
+        return setup_cta<typename C::type, double, C::THREADS, (C::MINB > 2 ? 2 : C::MINB)>(p);
+    else
+        return set_error(SDSP_B200_ERR_UNSUPPORTED, "fft: n=%u in f64 is larger than one CTA can hold and the multi-pass path is not built", p.n);
+}
+
+template <int LG>
+static int emulate_for(int precision, bool inverse, void *frame)
+{
+    using C = CfgFor<LG>;
+    if (precision == SDSP_B200_F32)
+        emulate_cfg<typename C::type, float>(frame, inverse);
+    else
+        emulate_cfg<typename C::type, double>(frame, inverse);
+    return SDSP_B200_OK;
+}
+
+#define SDSP_FOR_EACH_LG(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14)
+
+static int setup_plan(FftPlan &p)
+{
+    switch (ilog2(p.n)) {
+#define X(LG) \
+    case LG: return setup_for<LG>(p);
+        SDSP_FOR_EACH_LG(X)
+#undef X
+    default:
+        return set_error(SDSP_B200_ERR_UNSUPPORTED, "fft: n=%u is larger than one CTA can hold and the multi-pass path is not built", p.n);
+    }
+}
+
+static int emulate_dispatch(uint32_t n, int precision, bool inverse, void *frame)
+{
+    switch (ilog2(n)) {
+#define X(LG) \
+    case LG: return emulate_for<LG>(precision, inverse, frame);
+        SDSP_FOR_EACH_LG(X)
+#undef X
+    default: return set_error(SDSP_B200_ERR_UNSUPPORTED, "emulate_fft: n=%u not built", n);
+    }
+}
+
+static int check_fft_args(uint32_t n, int radix, int precision, int direction)
+{
+    if (radix != 2 && radix != 4)
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "fft: radix must be 2 or 4 (got %d)", radix);
+    if (precision != SDSP_B200_F32 && precision != SDSP_B200_F64)
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "fft: bad precision %d", precision);
+    if (direction != SDSP_B200_FORWARD && direction != SDSP_B200_REVERSE)
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "fft: bad direction %d", direction);
+    if (!is_pow2(n) || n < 2) // reference fft.h:261 "FFT size must be a power of 2!"
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "FFT size must be a power of 2! (n=%u)", n);
+    if (radix == 4 && (ilog2(n) % 2) != 0) // reference fft.h:304
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "FFT radix 4 size must be a power of 4! (n=%u)", n);
+    return SDSP_B200_OK;
+}
+} // namespace sdsp_b200
+
+using namespace sdsp_b200;
+
+struct sdsp_b200_fft_plan_s {
+    FftPlan p;
+};
+
+extern "C" {
+
+int sdsp_b200_fft_plan_create(sdsp_b200_fft_plan *plan, uint32_t n, int radix, int precision, int direction, int device)
+{
+    if (!plan)
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "fft_plan_create: null out pointer");
+    *plan = nullptr;
+    int rc = check_fft_args(n, radix, precision, direction);
+    if (rc)
+        return rc;
+    rc = ensure_device(device);
+    if (rc)
+        return rc;
+    auto *h = new sdsp_b200_fft_plan_s();
+    h->p.n = n;
+    h->p.radix = radix;
+    h->p.precision = precision;
+    h->p.direction = direction;
+    h->p.device = device;
+    h->p.sm_count = device_sm_count(device);
+    rc = setup_plan(h->p);
+    if (rc) {
+        if (h->p.d_tw)
+            cudaFree(h->p.d_tw);
+        delete h;
+        return rc;
+    }
+    *plan = h;
+    return SDSP_B200_OK;
+}
+
+int sdsp_b200_fft_plan_destroy(sdsp_b200_fft_plan plan)
+{
+    if (!plan)
+        return SDSP_B200_OK;
+    cudaSetDevice(plan->p.device);
+    if (plan->p.d_tw)
+        cudaFree(plan->p.d_tw);
+    if (plan->p.d_stage)
+        cudaFree(plan->p.d_stage);
+    delete plan;
+    return SDSP_B200_OK;
+}
+
+int sdsp_b200_fft_exec(sdsp_b200_fft_plan plan, void *data, size_t n_frames, int ptr_kind, void *stream)
+{
+    if (!plan)
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "fft_exec: null plan");
+    if (n_frames == 0)
+        return SDSP_B200_OK;
+    if (!data)
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "fft_exec: null data");
+    FftPlan &p = plan->p;
+    SDSP_CUDA(cudaSetDevice(p.device));
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const size_t elem = (p.precision == SDSP_B200_F32 ? sizeof(float) : sizeof(double)) * 2;
+    if ((reinterpret_cast<uintptr_t>(data) % elem) != 0)
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "fft_exec: data must be aligned to one complex element (%zu bytes)", elem);
+    if (ptr_kind == SDSP_B200_PTR_DEVICE)
+        return p.launch(p, data, n_frames, s);
+    if (ptr_kind != SDSP_B200_PTR_HOST)
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "fft_exec: bad ptr_kind %d", ptr_kind);
+
+    // host data: stage through device memory in slabs so transfers of one slab overlap the transform
+    // of another (three streams would be overkill: H2D, kernel and D2H of consecutive slabs are chained
+    // on two alternating streams)
+    std::lock_guard<std::mutex> lock(p.mu);
+    const size_t frame_bytes = (size_t)p.n * elem;
+    size_t slab_frames = (64u << 20) / frame_bytes;
+    if (slab_frames < 1)
+        slab_frames = 1;
+    if (slab_frames > n_frames)
+        slab_frames = n_frames;
+    const int nbuf = n_frames > slab_frames ? 2 : 1;
+    const size_t need = slab_frames * frame_bytes * nbuf;
+    if (p.stage_bytes < need) {
+        if (p.d_stage)
+            cudaFree(p.d_stage);
+        p.d_stage = nullptr;
+        p.stage_bytes = 0;
+        cudaError_t e = cudaMalloc(&p.d_stage, need);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return set_error(SDSP_B200_ERR_OOM, "fft_exec: cannot allocate %zu bytes of staging memory", need);
+        }
+        p.stage_bytes = need;
+    }
+    cudaStream_t st[2] = { nullptr, nullptr };
+    for (int i = 0; i < nbuf; i++)
+        SDSP_CUDA(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
+    int rc = SDSP_B200_OK;
+    size_t done = 0;
+    int which = 0;
+    while (done < n_frames && rc == SDSP_B200_OK) {
+        const size_t cnt = (n_frames - done) < slab_frames ? (n_frames - done) : slab_frames;
+        char *h = static_cast<char *>(data) + done * frame_bytes;
+        char *d = static_cast<char *>(p.d_stage) + (size_t)which * slab_frames * frame_bytes;
+        cudaStream_t cs = st[which];
+        if (cudaMemcpyAsync(d, h, cnt * frame_bytes, cudaMemcpyHostToDevice, cs) != cudaSuccess)
+            rc = cuda_fail((int)cudaGetLastError(), "H2D", __FILE__, __LINE__);
+        if (rc == SDSP_B200_OK)
+            rc = p.launch(p, d, cnt, cs);
+        if (rc == SDSP_B200_OK && cudaMemcpyAsync(h, d, cnt * frame_bytes, cudaMemcpyDeviceToHost, cs) != cudaSuccess)
+            rc = cuda_fail((int)cudaGetLastError(), "D2H", __FILE__, __LINE__);
+        done += cnt;
+        which = (which + 1) % nbuf;
+    }
+    for (int i = 0; i < nbuf; i++) {
+        cudaError_t e = cudaStreamSynchronize(st[i]);
+        if (e != cudaSuccess && rc == SDSP_B200_OK)
+            rc = cuda_fail((int)e, "cudaStreamSynchronize", __FILE__, __LINE__);
+        cudaStreamDestroy(st[i]);
+    }
+    (void)s;
+    return rc;
+}
+
+int sdsp_b200_fft_plan_describe(sdsp_b200_fft_plan plan, char *buf, size_t buf_len)
+{
+    if (!plan || !buf || buf_len == 0)
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "fft_plan_describe: bad arguments");
+    const FftPlan &p = plan->p;
+    snprintf(buf, buf_len,
+             "fft n=%u %s %s radix-arg=%d: single-CTA kernel, passes=%d radices=[%d,%d,%d,%d] points/thread=%d "
+             "threads/CTA=%d frames/CTA=%d smem/CTA=%zuB CTAs/SM=%d SMs=%d twiddle-table=%zuB",
+             p.n, p.precision == SDSP_B200_F32 ? "f32" : "f64", p.direction == SDSP_B200_FORWARD ? "forward" : "reverse", p.radix,
+             p.npass, p.radices[0], p.radices[1], p.radices[2], p.radices[3], p.e, p.threads, p.frames_per_cta, p.smem_bytes,
+             p.ctas_per_sm, p.sm_count, p.tw_bytes);
+    return SDSP_B200_OK;
+}
+
+int sdsp_b200_fft_plan_launches(sdsp_b200_fft_plan plan, size_t n_frames, int *launches)
+{
+    if (!plan || !launches)
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "fft_plan_launches: bad arguments");
+    *launches = n_frames ? 1 : 0;
+    return SDSP_B200_OK;
+}
+
+int sdsp_b200_digit_reverse_table(uint32_t n, uint32_t base, int half_table, uint32_t *out, int device)
+{
+    if (!out)
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "digit_reverse_table: null out");
+    if (base != 2 && base != 4)
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "digit_reverse_table: base must be 2 or 4");
+    if (!is_pow2(n) || n < 2 || (base == 4 && ilog2(n) % 2))
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "digit_reverse_table: n=%u is not a power of %u", n, base);
+    int rc = ensure_device(device);
+    if (rc)
+        return rc;
+    uint32_t *d = nullptr;
+    SDSP_CUDA(cudaMalloc(&d, (size_t)n * sizeof(uint32_t)));
+    digit_reverse_table_kernel<<<(n + 255) / 256, 256>>>(d, n, ilog2(n), base, half_table);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess)
+        e = cudaMemcpy(out, d, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess)
+        return cuda_fail((int)e, "digit_reverse_table", __FILE__, __LINE__);
+    return SDSP_B200_OK;
+}
+
+int sdsp_b200_digit_reverse_permute(void *data, uint32_t n, uint32_t base, int precision, size_t n_frames, int ptr_kind,
+                                    int device, void *stream)
+{
+    if (base != 2 && base != 4)
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "digit_reverse_permute: base must be 2 or 4");
+    if (!is_pow2(n) || n < 2 || (base == 4 && ilog2(n) % 2))
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "digit_reverse_permute: n=%u is not a power of %u", n, base);
+    if (n_frames == 0)
+        return SDSP_B200_OK;
+    if (!data)
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "digit_reverse_permute: null data");
+    int rc = ensure_device(device);
+    if (rc)
+        return rc;
+    const size_t elem = (precision == SDSP_B200_F32 ? sizeof(float) : sizeof(double)) * 2;
+    const size_t bytes = n_frames * (size_t)n * elem;
+    void *d = data;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (ptr_kind == SDSP_B200_PTR_HOST) {
+        SDSP_CUDA(cudaMalloc(&d, bytes));
+        cudaError_t e = cudaMemcpy(d, data, bytes, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            cudaFree(d);
+            return cuda_fail((int)e, "H2D", __FILE__, __LINE__);
+        }
+        s = nullptr;
+    }
+    const size_t total = n_frames * (size_t)n;
+    const unsigned grid = (unsigned)((total + 255) / 256);
+    if (precision == SDSP_B200_F32)
+        digit_reverse_permute_kernel<float><<<grid, 256, 0, s>>>(reinterpret_cast<cplx<float> *>(d), n, ilog2(n), base, n_frames);
+    else
+        digit_reverse_permute_kernel<double><<<grid, 256, 0, s>>>(reinterpret_cast<cplx<double> *>(d), n, ilog2(n), base, n_frames);
+    cudaError_t e = cudaGetLastError();
+    if (ptr_kind == SDSP_B200_PTR_HOST) {
+        if (e == cudaSuccess)
+            e = cudaMemcpy(data, d, bytes, cudaMemcpyDeviceToHost);
+        cudaFree(d);
+    }
+    if (e != cudaSuccess)
+        return cuda_fail((int)e, "digit_reverse_permute", __FILE__, __LINE__);
+    return SDSP_B200_OK;
+}
+
+int sdsp_b200_debug_emulate_fft(uint32_t n, int precision, int direction, void *data, size_t n_frames)
+{
+    int rc = check_fft_args(n, 2, precision, direction);
+    if (rc)
+        return rc;
+    const size_t elem = (precision == SDSP_B200_F32 ? sizeof(float) : sizeof(double)) * 2;
+    for (size_t f = 0; f < n_frames; f++) {
+        rc = emulate_dispatch(n, precision, direction == SDSP_B200_REVERSE, static_cast<char *>(data) + f * (size_t)n * elem);
+        if (rc)
+            return rc;
+    }
+    return SDSP_B200_OK;
+}
+}

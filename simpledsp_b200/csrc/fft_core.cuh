@@ -1,0 +1,281 @@
+// fft_core.cuh -- per-thread arithmetic of the batched FFT kernels (host + device).
+//
+// What it replaces: the butterfly loops of sdsp::fft_radix2 (reference include/sdsp/fft.h:276-294)
+// and sdsp::fft_radix4 (:311-349) together with their digit-reversal sweeps (:269-273, :351-355).
+//
+// How (B200 design, not the reference's): a frame of N = R0*R1*...*R(p-1) points is transformed by p
+// register-resident passes.  Every thread owns E points; in pass i it performs E/Ri radix-Ri
+// butterflies entirely in registers.  Between passes the frame is exchanged through shared memory in
+// the Stockham auto-sort arrangement, so
+//   * every pass reads  position  t + (N/E)*e            (t = thread in frame, e < E)
+//   * pass i writes     position  K + Pi*k + Pi*Ri*m      (Pi = R0*..*R(i-1), K = b mod Pi, m = b div Pi,
+//                                                          b = t + (N/E)*q the butterfly, k its output)
+// and the last pass writes natural-order output with the same coalesced pattern the first pass read
+// with.  The digit reversal of the reference is therefore absorbed into the exchange addressing; no
+// separate permutation pass touches memory.  Twiddles W_{N/Pi}^(m*k) come from per-pass tables laid
+// out [k-1][m] so that a warp reads them contiguously.
+//
+// Everything here is __host__ __device__ so that sdsp_b200_debug_emulate_fft can run the identical
+// code on the CPU (index arithmetic and rounding can be checked without a GPU).
+#pragma once
+#include "common.h"
+
+namespace sdsp_b200
+{
+// ------------------------------------------------------------------------------------------------
+// factorisation of one frame
+template <int N_, int E_, int R0_, int R1_ = 1, int R2_ = 1, int R3_ = 1>
+struct FftCfg {
+    static constexpr int N = N_;  // points per frame
+    static constexpr int E = E_;  // points per thread
+    static constexpr int R0 = R0_, R1 = R1_, R2 = R2_, R3 = R3_;
+    static constexpr int NPASS = (R0_ > 1) + (R1_ > 1) + (R2_ > 1) + (R3_ > 1);
+    static constexpr int TPF = N_ / E_; // threads per frame
+    static constexpr int S = N_ / E_;   // distance between the points a thread owns
+    static_assert(R0_ * R1_ * R2_ * R3_ == N_, "radices must multiply to N");
+    static_assert(R0_ <= E_ && R1_ <= E_ && R2_ <= E_ && R3_ <= E_, "radix larger than points per thread");
+    static_assert(N_ % E_ == 0, "E must divide N");
+
+    SDSP_HD static constexpr int radix(int p)
+    {
+        return p == 0 ? R0_ : p == 1 ? R1_ : p == 2 ? R2_ : R3_;
+    }
+    // product of the radices of the passes before p
+    SDSP_HD static constexpr int pprev(int p)
+    {
+        return p == 0 ? 1 : p == 1 ? R0_ : p == 2 ? R0_ * R1_ : R0_ * R1_ * R2_;
+    }
+    // entries of the twiddle table of pass p: (R-1) rows of N/(pprev*R) values; the last pass has none
+    SDSP_HD static constexpr int tw_count(int p)
+    {
+        return p + 1 >= NPASS ? 0 : (radix(p) - 1) * (N_ / (pprev(p) * radix(p)));
+    }
+    SDSP_HD static constexpr int tw_offset(int p)
+    {
+        return p == 0 ? 0 : tw_offset(p - 1) + tw_count(p - 1);
+    }
+    // shared-memory exchange: one spare element after every 16 keeps both the strided writes of a pass
+    // and the unit-stride reads of the next one free of bank conflicts (8-byte and 16-byte elements)
+    SDSP_HD static constexpr int pad(int pos)
+    {
+        return pos + (pos >> 4);
+    }
+    static constexpr int PADDED_N = N_ + (N_ >> 4);
+};
+
+// ------------------------------------------------------------------------------------------------
+// butterflies, forward sign (e^{-i...}); natural-order in, natural-order out, in place
+
+template <typename T>
+SDSP_HD cplx<T> mul_neg_i(cplx<T> a) // a * (-i)
+{
+    return { a.y, -a.x };
+}
+
+template <typename T>
+SDSP_HD void dft2(cplx<T> &a, cplx<T> &b)
+{
+    const cplx<T> t = a;
+    a = t + b;
+    b = t - b;
+}
+
+template <typename T>
+SDSP_HD void dft4(cplx<T> &a0, cplx<T> &a1, cplx<T> &a2, cplx<T> &a3)
+{
+    const cplx<T> s02 = a0 + a2, d02 = a0 - a2;
+    const cplx<T> s13 = a1 + a3, d13 = mul_neg_i(a1 - a3);
+    a0 = s02 + s13;
+    a1 = d02 + d13;
+    a2 = s02 - s13;
+    a3 = d02 - d13;
+}
+
+template <typename T>
+struct FftConst {
+    static constexpr T SQRT1_2 = (T)0.70710678118654752440084436210484903928L;
+    static constexpr T COS_PI_8 = (T)0.92387953251128675612818318939678828682L;
+    static constexpr T SIN_PI_8 = (T)0.38268343236508977172845998403039886676L;
+};
+
+template <int R, typename T>
+struct Dft;
+
+template <typename T>
+struct Dft<2, T> {
+    SDSP_HD static void run(cplx<T> (&a)[2])
+    {
+        dft2(a[0], a[1]);
+    }
+};
+
+template <typename T>
+struct Dft<4, T> {
+    SDSP_HD static void run(cplx<T> (&a)[4])
+    {
+        dft4(a[0], a[1], a[2], a[3]);
+    }
+};
+
+template <typename T>
+struct Dft<8, T> {
+    SDSP_HD static void run(cplx<T> (&a)[8])
+    {
+        constexpr T h = FftConst<T>::SQRT1_2;
+        // decimation in frequency: even outputs from sums, odd outputs from twiddled differences
+        cplx<T> e0 = a[0] + a[4], e1 = a[1] + a[5], e2 = a[2] + a[6], e3 = a[3] + a[7];
+        cplx<T> o0 = a[0] - a[4], d1 = a[1] - a[5], d2 = a[2] - a[6], d3 = a[3] - a[7];
+        cplx<T> o1 = { h * (d1.x + d1.y), h * (d1.y - d1.x) };  // * W8^1 = (1 - i)/sqrt2
+        cplx<T> o2 = mul_neg_i(d2);                              // * W8^2 = -i
+        cplx<T> o3 = { h * (d3.y - d3.x), -(h * (d3.x + d3.y)) }; // * W8^3 = (-1 - i)/sqrt2
+        dft4(e0, e1, e2, e3);
+        dft4(o0, o1, o2, o3);
+        a[0] = e0;
+        a[1] = o0;
+        a[2] = e1;
+        a[3] = o1;
+        a[4] = e2;
+        a[5] = o2;
+        a[6] = e3;
+        a[7] = o3;
+    }
+};
+
+template <typename T>
+struct Dft<16, T> {
+    SDSP_HD static void run(cplx<T> (&a)[16])
+    {
+        constexpr T h = FftConst<T>::SQRT1_2, c = FftConst<T>::COS_PI_8, s = FftConst<T>::SIN_PI_8;
+        // n = b + 4c, k = k1 + 4 k2:  X[k1 + 4 k2] = sum_b W4^(b k2) [ W16^(b k1) sum_c a[b + 4c] W4^(c k1) ]
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int b = 0; b < 4; b++)
+            dft4(a[b], a[b + 4], a[b + 8], a[b + 12]); // a[b + 4 k1] = inner sum
+        // W16^(b k1), b, k1 in 1..3 : exponents 1 2 3 / 2 4 6 / 3 6 9
+        a[1 + 4] = cmul(a[1 + 4], cplx<T>{ c, -s });
+        a[1 + 8] = cplx<T>{ h * (a[1 + 8].x + a[1 + 8].y), h * (a[1 + 8].y - a[1 + 8].x) };
+        a[1 + 12] = cmul(a[1 + 12], cplx<T>{ s, -c });
+        a[2 + 4] = cplx<T>{ h * (a[2 + 4].x + a[2 + 4].y), h * (a[2 + 4].y - a[2 + 4].x) };
+        a[2 + 8] = mul_neg_i(a[2 + 8]);
+        a[2 + 12] = cplx<T>{ h * (a[2 + 12].y - a[2 + 12].x), -(h * (a[2 + 12].x + a[2 + 12].y)) };
+        a[3 + 4] = cmul(a[3 + 4], cplx<T>{ s, -c });
+        a[3 + 8] = cplx<T>{ h * (a[3 + 8].y - a[3 + 8].x), -(h * (a[3 + 8].x + a[3 + 8].y)) };
+        a[3 + 12] = cmul(a[3 + 12], cplx<T>{ -c, s });
+        cplx<T> o[16];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int k1 = 0; k1 < 4; k1++) {
+            cplx<T> x0 = a[0 + 4 * k1], x1 = a[1 + 4 * k1], x2 = a[2 + 4 * k1], x3 = a[3 + 4 * k1];
+            dft4(x0, x1, x2, x3); // over b -> k2
+            o[k1] = x0;
+            o[k1 + 4] = x1;
+            o[k1 + 8] = x2;
+            o[k1 + 12] = x3;
+        }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int k = 0; k < 16; k++)
+            a[k] = o[k];
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// one pass over the E points a thread holds.
+//   in : v[e] = element at position t + S*e of the current arrangement
+//   out: v[q + (E/R)*k] = output k of butterfly b = t + S*q, already multiplied by the pass twiddle
+template <class Cfg, int P, typename T>
+SDSP_HD void fft_pass(cplx<T> (&v)[Cfg::E], int t, const cplx<T> *__restrict__ tw)
+{
+    constexpr int R = Cfg::radix(P);
+    constexpr int G = Cfg::E / R;              // butterflies per thread
+    constexpr int PP = Cfg::pprev(P);          // points already resolved per sub-transform
+    constexpr int M = Cfg::N / (PP * R);       // range of m
+    constexpr bool LAST = (P + 1 == Cfg::NPASS);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int q = 0; q < G; q++) {
+        cplx<T> a[R];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int j = 0; j < R; j++)
+            a[j] = v[q + G * j];
+        Dft<R, T>::run(a);
+        if (!LAST) {
+            const int b = t + Cfg::S * q;
+            const int m = b / PP;
+            const cplx<T> *row = tw + Cfg::tw_offset(P) + m;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int k = 1; k < R; k++)
+                a[k] = cmul(a[k], row[(k - 1) * M]);
+        }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int k = 0; k < R; k++)
+            v[q + G * k] = a[k];
+    }
+}
+
+// where output slot e = q + (E/R)*k of pass P lands in the next arrangement
+template <class Cfg, int P>
+SDSP_HD int fft_out_pos(int t, int e)
+{
+    constexpr int R = Cfg::radix(P);
+    constexpr int G = Cfg::E / R;
+    constexpr int PP = Cfg::pprev(P);
+    const int q = e % G, k = e / G;
+    const int b = t + Cfg::S * q;
+    return (b % PP) + PP * k + PP * R * (b / PP);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host emulation of one frame: every "thread" runs the very pass code the kernel runs, the shared
+// memory exchange is an array indexed through the same pad() function.
+template <class Cfg, typename T, int P>
+inline void fft_emulate_pass(cplx<T> *cur, cplx<T> *nxt, const cplx<T> *tw)
+{
+    for (int t = 0; t < Cfg::TPF; t++) {
+        cplx<T> v[Cfg::E];
+        for (int e = 0; e < Cfg::E; e++)
+            v[e] = cur[P == 0 ? (t + Cfg::S * e) : Cfg::pad(t + Cfg::S * e)];
+        fft_pass<Cfg, P, T>(v, t, tw);
+        for (int e = 0; e < Cfg::E; e++) {
+            if (P + 1 == Cfg::NPASS)
+                nxt[t + Cfg::S * e] = v[e]; // natural order: slot e of thread t is output t + S*e
+            else
+                nxt[Cfg::pad(fft_out_pos<Cfg, P>(t, e))] = v[e];
+        }
+    }
+    if (P + 1 < Cfg::NPASS)
+        fft_emulate_pass<Cfg, T, (P + 1 < Cfg::NPASS ? P + 1 : P)>(nxt, cur, tw);
+}
+
+// Returns with the result in `frame` (natural order).  inverse is the re/im swap identity
+// IDFT(x) = swap(DFT(swap(x))) / N, which is exact, so only forward butterflies are ever compiled.
+template <class Cfg, typename T>
+inline void fft_emulate_frame(cplx<T> *frame, const cplx<T> *tw, bool inverse, T scale)
+{
+    constexpr int BUF = Cfg::PADDED_N > Cfg::N ? Cfg::PADDED_N : Cfg::N;
+    cplx<T> *a = new cplx<T>[BUF]();
+    cplx<T> *b = new cplx<T>[BUF]();
+    for (int i = 0; i < Cfg::N; i++)
+        a[i] = inverse ? cplx<T>{ frame[i].y, frame[i].x } : frame[i];
+    fft_emulate_pass<Cfg, T, 0>(a, b, tw);
+    const cplx<T> *res = (Cfg::NPASS % 2) ? b : a;
+    for (int i = 0; i < Cfg::N; i++) {
+        cplx<T> r = res[i];
+        if (inverse)
+            r = cplx<T>{ r.y * scale, r.x * scale };
+        frame[i] = r;
+    }
+    delete[] a;
+    delete[] b;
+}
+} // namespace sdsp_b200

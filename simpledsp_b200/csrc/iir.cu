@@ -1,0 +1,643 @@
+// iir.cu -- cascaded second-order-section IIR banks for sm_100a: kernels, banks, C-ABI entry points.
+//
+// Replaces sdsp::casc_2o_iir<m_t> and casc_2o_iir_lp/_hp/_bp<m_t> (reference
+// include/sdsp/casc_2o_iir.h:8-468) for banks of independent channels resident in HBM.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <tuple>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "iir_core.cuh"
+#include "iir_internal.h"
+
+namespace sdsp_b200
+{
+// =================================================================================================
+// sequential path, generic addressing: lane per channel, a warp owns 32 channels and walks the time
+// axis in tiles of 32 samples.  The tile is transposed through a warp-private shared-memory patch so
+// that global traffic is row-contiguous (128 B per channel row for fp32) while every lane consumes its
+// own channel in order.  The next tile is fetched into registers while the current one is filtered.
+template <typename T, int M>
+__device__ __forceinline__ void iir_load_channel(IirCoef<T, M> &c, IirState<T, M> &s, const T *__restrict__ coef,
+                                                 const T *__restrict__ state, size_t n_channels, size_t ch, bool active)
+{
+    if (active) {
+        c.gain = coef[ch];
+#pragma unroll
+        for (int j = 0; j < M; j++) {
+            c.b1[j] = coef[(size_t)(1 + j) * n_channels + ch];
+            c.b2[j] = coef[(size_t)(1 + M + j) * n_channels + ch];
+            c.na1[j] = coef[(size_t)(1 + 2 * M + j) * n_channels + ch];
+            c.na2[j] = coef[(size_t)(1 + 3 * M + j) * n_channels + ch];
+        }
+#pragma unroll
+        for (int r = 0; r <= M; r++) {
+            s.h[r][0] = state[(size_t)(2 * r) * n_channels + ch];
+            s.h[r][1] = state[(size_t)(2 * r + 1) * n_channels + ch];
+        }
+    } else {
+        c.gain = 0;
+#pragma unroll
+        for (int j = 0; j < M; j++)
+            c.b1[j] = c.b2[j] = c.na1[j] = c.na2[j] = 0;
+#pragma unroll
+        for (int r = 0; r <= M; r++)
+            s.h[r][0] = s.h[r][1] = 0;
+    }
+}
+
+template <typename T, int M>
+__device__ __forceinline__ void iir_store_state(const IirState<T, M> &s, T *__restrict__ state, size_t n_channels, size_t ch)
+{
+#pragma unroll
+    for (int r = 0; r <= M; r++) {
+        state[(size_t)(2 * r) * n_channels + ch] = s.h[r][0];
+        state[(size_t)(2 * r + 1) * n_channels + ch] = s.h[r][1];
+    }
+}
+
+template <typename T, int M, int KIND, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+    iir_seq_kernel(T *__restrict__ data, size_t n_samples, size_t stride, const T *__restrict__ coef, T *__restrict__ state,
+                   size_t n_channels)
+{
+    constexpr int TS = 32;
+    __shared__ T tile[WARPS][32][TS + 1];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t ch0 = ((size_t)blockIdx.x * WARPS + warp) * 32;
+    if (ch0 >= n_channels)
+        return; // warps are independent: nothing below synchronises across the block
+    const size_t ch = ch0 + lane;
+    const bool active = ch < n_channels;
+    const int rows = (int)((n_channels - ch0) < 32 ? (n_channels - ch0) : 32);
+
+    IirCoef<T, M> c;
+    IirState<T, M> s;
+    iir_load_channel<T, M>(c, s, coef, state, n_channels, ch, active);
+
+    T(*my)[TS + 1] = tile[warp];
+    T *base = data + ch0 * stride + lane;
+    T nxt[32];
+    // prefetch tile 0
+#pragma unroll
+    for (int r = 0; r < 32; r++)
+        nxt[r] = (r < rows && (size_t)lane < n_samples) ? base[(size_t)r * stride] : (T)0;
+
+    for (size_t n0 = 0; n0 < n_samples; n0 += TS) {
+#pragma unroll
+        for (int r = 0; r < 32; r++)
+            my[r][lane] = nxt[r];
+        __syncwarp();
+        const size_t n1 = n0 + TS;
+        if (n1 < n_samples) {
+            const bool col_ok = n1 + lane < n_samples;
+#pragma unroll
+            for (int r = 0; r < 32; r++)
+                nxt[r] = (r < rows && col_ok) ? base[(size_t)r * stride + n1] : (T)0;
+        }
+        const int cnt = (int)((n_samples - n0) < TS ? (n_samples - n0) : TS);
+        if (cnt == TS) {
+#pragma unroll 8
+            for (int i = 0; i < TS; i++)
+                my[lane][i] = iir_step<T, M, KIND>(my[lane][i], c, s);
+        } else {
+            for (int i = 0; i < cnt; i++)
+                my[lane][i] = iir_step<T, M, KIND>(my[lane][i], c, s);
+        }
+        __syncwarp();
+        const bool col_ok = n0 + lane < n_samples;
+#pragma unroll
+        for (int r = 0; r < 32; r++)
+            if (r < rows && col_ok)
+                base[(size_t)r * stride + n0] = my[r][lane];
+        __syncwarp();
+    }
+    if (active)
+        iir_store_state<T, M>(s, state, n_channels, ch);
+}
+
+// =================================================================================================
+template <typename T, int M, int KIND>
+static int launch_seq(const IirBank &b, void *data, size_t n_samples, size_t stride, cudaStream_t stream)
+{
+    constexpr int WARPS = 2;
+    const size_t groups = (b.n_channels + 31) / 32;
+    const unsigned grid = (unsigned)((groups + WARPS - 1) / WARPS);
+    iir_seq_kernel<T, M, KIND, WARPS><<<grid, WARPS * 32, 0, stream>>>(static_cast<T *>(data), n_samples, stride,
+                                                                      static_cast<const T *>(b.d_coef), static_cast<T *>(b.d_state),
+                                                                      b.n_channels);
+    SDSP_CUDA(cudaGetLastError());
+    return SDSP_B200_OK;
+}
+
+template <typename T, int M>
+static int launch_seq_kind(const IirBank &b, void *data, size_t n_samples, size_t stride, cudaStream_t stream)
+{
+    switch (b.numerator) {
+    case NUM_GENERIC: return launch_seq<T, M, NUM_GENERIC>(b, data, n_samples, stride, stream);
+    case NUM_LP: return launch_seq<T, M, NUM_LP>(b, data, n_samples, stride, stream);
+    case NUM_HP: return launch_seq<T, M, NUM_HP>(b, data, n_samples, stride, stream);
+    default: return launch_seq<T, M, NUM_BP>(b, data, n_samples, stride, stream);
+    }
+}
+
+template <typename T>
+static int launch_seq_sections(const IirBank &b, void *data, size_t n_samples, size_t stride, cudaStream_t stream)
+{
+    switch (b.sections) {
+    case 1: return launch_seq_kind<T, 1>(b, data, n_samples, stride, stream);
+    case 2: return launch_seq_kind<T, 2>(b, data, n_samples, stride, stream);
+    case 3: return launch_seq_kind<T, 3>(b, data, n_samples, stride, stream);
+    case 4: return launch_seq_kind<T, 4>(b, data, n_samples, stride, stream);
+    case 5: return launch_seq_kind<T, 5>(b, data, n_samples, stride, stream);
+    case 6: return launch_seq_kind<T, 6>(b, data, n_samples, stride, stream);
+    case 7: return launch_seq_kind<T, 7>(b, data, n_samples, stride, stream);
+    case 8: return launch_seq_kind<T, 8>(b, data, n_samples, stride, stream);
+    default: return set_error(SDSP_B200_ERR_UNSUPPORTED, "iir: sections=%d not built (1..8)", b.sections);
+    }
+}
+
+int iir_launch_sequential(const IirBank &b, void *data, size_t n_samples, size_t stride, cudaStream_t stream)
+{
+    if (b.precision == SDSP_B200_F32)
+        return launch_seq_sections<float>(b, data, n_samples, stride, stream);
+    return launch_seq_sections<double>(b, data, n_samples, stride, stream);
+}
+
+// =================================================================================================
+// host emulation of the sequential path (same iir_step, compiled for the host)
+template <typename T, int M, int KIND>
+static void emulate_seq(double gain, const double *b, const double *a, double *mem, void *data, size_t n)
+{
+    IirCoef<T, M> c;
+    IirState<T, M> s;
+    iir_pack_coef<T, M>(c, gain, b, a);
+    for (int r = 0; r <= M; r++) {
+        s.h[r][0] = (T)mem[2 * r];
+        s.h[r][1] = (T)mem[2 * r + 1];
+    }
+    T *d = static_cast<T *>(data);
+    for (size_t i = 0; i < n; i++)
+        d[i] = iir_step<T, M, KIND>(d[i], c, s);
+    for (int r = 0; r <= M; r++) {
+        mem[2 * r] = (double)s.h[r][0];
+        mem[2 * r + 1] = (double)s.h[r][1];
+    }
+}
+
+template <typename T, int M>
+static void emulate_seq_kind(int kind, double gain, const double *b, const double *a, double *mem, void *data, size_t n)
+{
+    switch (kind) {
+    case NUM_GENERIC: emulate_seq<T, M, NUM_GENERIC>(gain, b, a, mem, data, n); break;
+    case NUM_LP: emulate_seq<T, M, NUM_LP>(gain, b, a, mem, data, n); break;
+    case NUM_HP: emulate_seq<T, M, NUM_HP>(gain, b, a, mem, data, n); break;
+    default: emulate_seq<T, M, NUM_BP>(gain, b, a, mem, data, n); break;
+    }
+}
+
+template <typename T>
+static int emulate_seq_sections(int sections, int kind, double gain, const double *b, const double *a, double *mem, void *data,
+                                size_t n)
+{
+    switch (sections) {
+#define X(MM) \
+    case MM: emulate_seq_kind<T, MM>(kind, gain, b, a, mem, data, n); return SDSP_B200_OK;
+        X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8)
+#undef X
+    default: return set_error(SDSP_B200_ERR_UNSUPPORTED, "iir: sections=%d not built (1..8)", sections);
+    }
+}
+
+// =================================================================================================
+// Butterworth designers -- host scalar code.  Bilinear-transform prototype sections exactly as the
+// reference parameterises them (casc_2o_iir.h:168-194 lp, :140-166 hp, :82-138 bp): section k has
+//   beta  = (1 - t)/(1 + t)/2,  t = d_k sin(e)/2,  gamma = (1/2 + beta) cos(e),  a = {1, -2 gamma, 2 beta}
+// with e the (warped) centre angle and d_k = 2 sin((2k+1) pi / (4 m)) the Butterworth damping.
+static void design_section(double dk, double e, double &beta, double &gamma)
+{
+    const double t = dk * std::sin(e) / 2;
+    beta = (1 - t) / (1 + t) / 2;
+    gamma = (0.5 + beta) * std::cos(e);
+}
+
+static int design_lp_hp(int m, double f0, double fs, double gain_in, bool hp, double *gain, double *b, double *a)
+{
+    if (m < 1 || m > 8 || !gain || !b || !a)
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "iir_design: bad arguments (sections=%d)", m);
+    double g = gain_in;
+    const double e0 = 2 * M_PI * f0 / fs;
+    for (int k = 0; k < m; k++) {
+        const double dk = 2 * std::sin((2 * k + 1) * M_PI / (4.0 * m));
+        double beta, gamma;
+        design_section(dk, e0, beta, gamma);
+        const double alpha = hp ? (0.5 + beta + gamma) / 4 : (0.5 + beta - gamma) / 4;
+        g *= 2 * alpha;
+        b[3 * k + 0] = 1.0;
+        b[3 * k + 1] = hp ? -2.0 : 2.0;
+        b[3 * k + 2] = 1.0;
+        a[3 * k + 0] = 1.0;
+        a[3 * k + 1] = -2 * gamma;
+        a[3 * k + 2] = 2 * beta;
+    }
+    *gain = g;
+    return SDSP_B200_OK;
+}
+
+static int design_bp(int m, double f0, double fs, double q, double gain_in, double *gain, double *b, double *a)
+{
+    if (m < 2 || m > 8 || (m % 2) || !gain || !b || !a)
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "iir_design_bp: sections must be even, 2..8 (got %d)", m);
+    double g = gain_in;
+    const double e0 = 2 * M_PI * f0 / fs;
+    const double de = 2 * std::tan(e0 / (2 * q)) / std::sin(e0);
+    const double th = std::tan(e0 / 2.0);
+    for (int k = 0; k < m / 2; k++) {
+        const double d = 2 * std::sin((2 * k + 1) * M_PI / (2.0 * m));
+        const double aa = (1 + de * de / 4.0) * 2 / d / de;
+        const double dk = std::sqrt(de * d / (aa + std::sqrt(aa * aa - 1)));
+        const double bb = d * de / dk / 2.0;
+        const double w = bb + std::sqrt(bb * bb - 1);
+        const double e1 = 2.0 * std::atan(th / w);
+        const double e2 = 2.0 * std::atan(w * th);
+        double beta1, gamma1, beta2, gamma2;
+        design_section(dk, e1, beta1, gamma1);
+        design_section(dk, e2, beta2, gamma2);
+        const double t = std::sqrt(1 + (w - 1 / w) / dk * (w - 1 / w) / dk);
+        const double alpha1 = (0.5 - beta1) * t / 2.0;
+        const double alpha2 = (0.5 - beta2) * t / 2.0;
+        g *= 4 * alpha1 * alpha2;
+        for (int h = 0; h < 2; h++) {
+            double *bs = b + 3 * (2 * k + h), *as = a + 3 * (2 * k + h);
+            bs[0] = 1.0;
+            bs[1] = 0.0;
+            bs[2] = -1.0;
+            as[0] = 1.0;
+            as[1] = -2 * (h ? gamma2 : gamma1);
+            as[2] = 2 * (h ? beta2 : beta1);
+        }
+    }
+    *gain = g;
+    return SDSP_B200_OK;
+}
+
+// =================================================================================================
+static int check_bank_args(int sections, int precision, int numerator)
+{
+    if (sections < 1 || sections > 8)
+        return set_error(SDSP_B200_ERR_UNSUPPORTED, "iir: sections=%d not built (1..8)", sections);
+    if (precision != SDSP_B200_F32 && precision != SDSP_B200_F64)
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "iir: bad precision %d", precision);
+    if (numerator < 0 || numerator > 3)
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "iir: bad numerator kind %d", numerator);
+    return SDSP_B200_OK;
+}
+
+template <typename T>
+static void pack_coef_soa(std::vector<T> &out, int m, size_t count, const double *gain, const double *b, const double *a)
+{
+    // [k][c] with k = gain, b1[0..m), b2[0..m), -a1[0..m), -a2[0..m)
+    out.assign((size_t)iir_coef_count(m) * count, (T)0);
+    for (size_t c = 0; c < count; c++) {
+        out[c] = (T)gain[c];
+        for (int j = 0; j < m; j++) {
+            const double *bj = b ? b + (c * m + j) * 3 : nullptr;
+            const double *aj = a + (c * m + j) * 3;
+            out[(size_t)(1 + j) * count + c] = bj ? (T)bj[1] : (T)0;
+            out[(size_t)(1 + m + j) * count + c] = bj ? (T)bj[2] : (T)0;
+            out[(size_t)(1 + 2 * m + j) * count + c] = (T)(-aj[1]);
+            out[(size_t)(1 + 3 * m + j) * count + c] = (T)(-aj[2]);
+        }
+    }
+}
+
+static size_t elem_size(int precision)
+{
+    return precision == SDSP_B200_F32 ? sizeof(float) : sizeof(double);
+}
+
+// rows of a [rows][n_channels] device array <-> [rows][count] host block at channel offset `first`
+static int copy_rows(const IirBank &b, void *dev, void *host, int rows, size_t first, size_t count, bool to_device)
+{
+    const size_t es = elem_size(b.precision);
+    char *d = static_cast<char *>(dev) + first * es;
+    if (to_device)
+        SDSP_CUDA(cudaMemcpy2D(d, b.n_channels * es, host, count * es, count * es, rows, cudaMemcpyHostToDevice));
+    else
+        SDSP_CUDA(cudaMemcpy2D(host, count * es, d, b.n_channels * es, count * es, rows, cudaMemcpyDeviceToHost));
+    return SDSP_B200_OK;
+}
+} // namespace sdsp_b200
+
+using namespace sdsp_b200;
+
+struct sdsp_b200_iir_bank_s {
+    IirBank b;
+};
+
+extern "C" {
+
+int sdsp_b200_iir_bank_create(sdsp_b200_iir_bank *bank, int sections, size_t n_channels, int precision, int numerator, int device)
+{
+    if (!bank)
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "iir_bank_create: null out pointer");
+    *bank = nullptr;
+    int rc = check_bank_args(sections, precision, numerator);
+    if (rc)
+        return rc;
+    if (n_channels == 0)
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "iir_bank_create: n_channels must be positive");
+    rc = ensure_device(device);
+    if (rc)
+        return rc;
+    auto *h = new sdsp_b200_iir_bank_s();
+    IirBank &b = h->b;
+    b.sections = sections;
+    b.n_channels = n_channels;
+    b.precision = precision;
+    b.numerator = numerator;
+    b.device = device;
+    b.sm_count = device_sm_count(device);
+    const size_t es = elem_size(precision);
+    const size_t coef_bytes = (size_t)iir_coef_count(sections) * n_channels * es;
+    const size_t state_bytes = (size_t)iir_state_count(sections) * n_channels * es;
+    if (cudaMalloc(&b.d_coef, coef_bytes) != cudaSuccess || cudaMalloc(&b.d_state, state_bytes) != cudaSuccess) {
+        cudaGetLastError();
+        if (b.d_coef)
+            cudaFree(b.d_coef);
+        delete h;
+        return set_error(SDSP_B200_ERR_OOM, "iir_bank_create: cannot allocate bank for %zu channels", n_channels);
+    }
+    cudaMemset(b.d_coef, 0, coef_bytes);
+    cudaMemset(b.d_state, 0, state_bytes);
+    *bank = h;
+    return SDSP_B200_OK;
+}
+
+int sdsp_b200_iir_bank_destroy(sdsp_b200_iir_bank bank)
+{
+    if (!bank)
+        return SDSP_B200_OK;
+    IirBank &b = bank->b;
+    cudaSetDevice(b.device);
+    iir_bank_release_aux(b);
+    if (b.d_coef)
+        cudaFree(b.d_coef);
+    if (b.d_state)
+        cudaFree(b.d_state);
+    if (b.d_stage)
+        cudaFree(b.d_stage);
+    delete bank;
+    return SDSP_B200_OK;
+}
+
+int sdsp_b200_iir_bank_set_coeffs(sdsp_b200_iir_bank bank, size_t first, size_t count, const double *gain, const double *bco,
+                                  const double *aco)
+{
+    if (!bank || !gain || !aco)
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "iir_bank_set_coeffs: null argument");
+    IirBank &b = bank->b;
+    if (b.numerator == NUM_GENERIC && !bco)
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "iir_bank_set_coeffs: a generic bank needs b coefficients");
+    if (first + count > b.n_channels)
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "iir_bank_set_coeffs: channels [%zu,%zu) outside bank of %zu", first, first + count,
+                         b.n_channels);
+    if (count == 0)
+        return SDSP_B200_OK;
+    SDSP_CUDA(cudaSetDevice(b.device));
+    int rc;
+    if (b.precision == SDSP_B200_F32) {
+        std::vector<float> soa;
+        pack_coef_soa<float>(soa, b.sections, count, gain, bco, aco);
+        rc = copy_rows(b, b.d_coef, soa.data(), iir_coef_count(b.sections), first, count, true);
+    } else {
+        std::vector<double> soa;
+        pack_coef_soa<double>(soa, b.sections, count, gain, bco, aco);
+        rc = copy_rows(b, b.d_coef, soa.data(), iir_coef_count(b.sections), first, count, true);
+    }
+    if (rc == SDSP_B200_OK) {
+        // keep a host copy in double: the scan path derives its propagation tables from it
+        const int m = b.sections;
+        if (b.h_gain.size() != b.n_channels) {
+            b.h_gain.assign(b.n_channels, 1.0);
+            b.h_b.assign(b.n_channels * m * 3, 0.0);
+            b.h_a.assign(b.n_channels * m * 3, 0.0);
+        }
+        for (size_t c = 0; c < count; c++) {
+            b.h_gain[first + c] = gain[c];
+            for (int k = 0; k < 3 * m; k++) {
+                b.h_b[(first + c) * 3 * m + k] = bco ? bco[c * 3 * m + k] : 0.0;
+                b.h_a[(first + c) * 3 * m + k] = aco[c * 3 * m + k];
+            }
+        }
+        b.coef_version++;
+    }
+    return rc;
+}
+
+static int state_io(sdsp_b200_iir_bank bank, size_t first, size_t count, double *mem, bool to_device)
+{
+    if (!bank || !mem)
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "iir_bank_state: null argument");
+    IirBank &b = bank->b;
+    if (first + count > b.n_channels)
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "iir_bank_state: channels [%zu,%zu) outside bank of %zu", first, first + count,
+                         b.n_channels);
+    if (count == 0)
+        return SDSP_B200_OK;
+    SDSP_CUDA(cudaSetDevice(b.device));
+    const int rows = iir_state_count(b.sections);
+    // host layout mem[c][row][2]  <->  device layout [2*row + i][channel]
+    if (b.precision == SDSP_B200_F32) {
+        std::vector<float> soa((size_t)rows * count);
+        if (to_device) {
+            for (size_t c = 0; c < count; c++)
+                for (int k = 0; k < rows; k++)
+                    soa[(size_t)k * count + c] = (float)mem[c * rows + k];
+            return copy_rows(b, b.d_state, soa.data(), rows, first, count, true);
+        }
+        int rc = copy_rows(b, b.d_state, soa.data(), rows, first, count, false);
+        for (size_t c = 0; c < count && rc == 0; c++)
+            for (int k = 0; k < rows; k++)
+                mem[c * rows + k] = (double)soa[(size_t)k * count + c];
+        return rc;
+    }
+    std::vector<double> soa((size_t)rows * count);
+    if (to_device) {
+        for (size_t c = 0; c < count; c++)
+            for (int k = 0; k < rows; k++)
+                soa[(size_t)k * count + c] = mem[c * rows + k];
+        return copy_rows(b, b.d_state, soa.data(), rows, first, count, true);
+    }
+    int rc = copy_rows(b, b.d_state, soa.data(), rows, first, count, false);
+    for (size_t c = 0; c < count && rc == 0; c++)
+        for (int k = 0; k < rows; k++)
+            mem[c * rows + k] = soa[(size_t)k * count + c];
+    return rc;
+}
+
+int sdsp_b200_iir_bank_set_state(sdsp_b200_iir_bank bank, size_t first, size_t count, const double *mem)
+{
+    return state_io(bank, first, count, const_cast<double *>(mem), true);
+}
+
+int sdsp_b200_iir_bank_get_state(sdsp_b200_iir_bank bank, size_t first, size_t count, double *mem)
+{
+    return state_io(bank, first, count, mem, false);
+}
+
+int sdsp_b200_iir_bank_reset_state(sdsp_b200_iir_bank bank)
+{
+    if (!bank)
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "iir_bank_reset_state: null bank");
+    IirBank &b = bank->b;
+    SDSP_CUDA(cudaSetDevice(b.device));
+    SDSP_CUDA(cudaMemset(b.d_state, 0, (size_t)iir_state_count(b.sections) * b.n_channels * elem_size(b.precision)));
+    return SDSP_B200_OK;
+}
+
+int sdsp_b200_iir_bank_process(sdsp_b200_iir_bank bank, void *data, size_t n_samples, size_t channel_stride, int ptr_kind, int path,
+                               void *stream)
+{
+    if (!bank)
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "iir_bank_process: null bank");
+    if (n_samples == 0)
+        return SDSP_B200_OK;
+    if (!data)
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "iir_bank_process: null data");
+    IirBank &b = bank->b;
+    if (channel_stride < n_samples && b.n_channels > 1)
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "iir_bank_process: channel_stride %zu < n_samples %zu", channel_stride, n_samples);
+    if (path < SDSP_B200_IIR_AUTO || path > SDSP_B200_IIR_SCAN)
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "iir_bank_process: bad path %d", path);
+    const size_t es = elem_size(b.precision);
+    if (reinterpret_cast<uintptr_t>(data) % es)
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "iir_bank_process: data not aligned to its element size");
+    SDSP_CUDA(cudaSetDevice(b.device));
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+
+    if (ptr_kind == SDSP_B200_PTR_DEVICE)
+        return iir_dispatch(b, data, n_samples, channel_stride, path, s);
+    if (ptr_kind != SDSP_B200_PTR_HOST)
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "iir_bank_process: bad ptr_kind %d", ptr_kind);
+
+    std::lock_guard<std::mutex> lock(b.mu);
+    // compact staging copy [channel][n_samples], row pitch rounded to 16 bytes so the TMA path applies
+    const size_t pitch_elems = (n_samples * es + 15) / 16 * 16 / es;
+    const size_t need = b.n_channels * pitch_elems * es;
+    if (b.stage_bytes < need) {
+        if (b.d_stage)
+            cudaFree(b.d_stage);
+        b.d_stage = nullptr;
+        b.stage_bytes = 0;
+        if (cudaMalloc(&b.d_stage, need) != cudaSuccess) {
+            cudaGetLastError();
+            return set_error(SDSP_B200_ERR_OOM, "iir_bank_process: cannot allocate %zu bytes of staging memory", need);
+        }
+        b.stage_bytes = need;
+    }
+    SDSP_CUDA(cudaMemcpy2DAsync(b.d_stage, pitch_elems * es, data, channel_stride * es, n_samples * es, b.n_channels,
+                                cudaMemcpyHostToDevice, s));
+    int rc = iir_dispatch(b, b.d_stage, n_samples, pitch_elems, path, s);
+    if (rc)
+        return rc;
+    SDSP_CUDA(cudaMemcpy2DAsync(data, channel_stride * es, b.d_stage, pitch_elems * es, n_samples * es, b.n_channels,
+                                cudaMemcpyDeviceToHost, s));
+    SDSP_CUDA(cudaStreamSynchronize(s));
+    return SDSP_B200_OK;
+}
+
+int sdsp_b200_iir_bank_describe(sdsp_b200_iir_bank bank, size_t n_samples, size_t channel_stride, int path, char *buf, size_t buf_len)
+{
+    if (!bank || !buf || !buf_len)
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "iir_bank_describe: bad arguments");
+    return iir_describe(bank->b, n_samples, channel_stride, path, buf, buf_len);
+}
+
+int sdsp_b200_iir_design_lp(int sections, double f0, double fs, double gain_in, double *gain, double *b, double *a)
+{
+    return design_lp_hp(sections, f0, fs, gain_in, false, gain, b, a);
+}
+int sdsp_b200_iir_design_hp(int sections, double f0, double fs, double gain_in, double *gain, double *b, double *a)
+{
+    return design_lp_hp(sections, f0, fs, gain_in, true, gain, b, a);
+}
+int sdsp_b200_iir_design_bp(int sections, double f0, double fs, double q, double gain_in, double *gain, double *b, double *a)
+{
+    return design_bp(sections, f0, fs, q, gain_in, gain, b, a);
+}
+
+// preload_filter (casc_2o_iir.h:196-214): every history slot of row 0 holds value*gain; for a low-pass
+// design each following row is the previous one times the section's DC gain sum(b)/(1+a1+a2); for
+// every other type the later rows are zero.
+int sdsp_b200_iir_preload_state(int sections, int filter_type, double gain, const double *b, const double *a, double value,
+                                double *mem)
+{
+    if (sections < 1 || sections > 8 || !mem || (filter_type == SDSP_B200_LOW_PASS && (!a || !b)))
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "iir_preload_state: bad arguments");
+    double v = value * gain;
+    for (int k = 0; k < 2 * (sections + 1); k++)
+        mem[k] = 0.0;
+    mem[0] = mem[1] = v;
+    if (filter_type == SDSP_B200_LOW_PASS) {
+        for (int j = 1; j <= sections; j++) {
+            v /= 1 + a[3 * (j - 1) + 1] + a[3 * (j - 1) + 2];
+            v *= b[3 * (j - 1) + 0] + b[3 * (j - 1) + 1] + b[3 * (j - 1) + 2];
+            mem[2 * j] = mem[2 * j + 1] = v;
+        }
+    }
+    return SDSP_B200_OK;
+}
+
+// a small cache of one-channel banks serves the drop-in header's single-object process() calls
+int sdsp_b200_iir_process_once(int sections, int numerator, int precision, double gain, const double *bco, const double *aco,
+                               double *mem, void *data, size_t n_samples, int device)
+{
+    int rc = check_bank_args(sections, precision, numerator);
+    if (rc)
+        return rc;
+    if (!aco || !mem || (numerator == NUM_GENERIC && !bco))
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "iir_process_once: null argument");
+    if (n_samples == 0)
+        return SDSP_B200_OK;
+    static std::mutex mu;
+    static std::map<std::tuple<int, int, int, int>, sdsp_b200_iir_bank> cache;
+    std::lock_guard<std::mutex> lock(mu);
+    auto key = std::make_tuple(sections, numerator, precision, device);
+    auto it = cache.find(key);
+    if (it == cache.end()) {
+        sdsp_b200_iir_bank nb = nullptr;
+        rc = sdsp_b200_iir_bank_create(&nb, sections, 1, precision, numerator, device);
+        if (rc)
+            return rc;
+        it = cache.emplace(key, nb).first;
+    }
+    sdsp_b200_iir_bank bk = it->second;
+    rc = sdsp_b200_iir_bank_set_coeffs(bk, 0, 1, &gain, bco, aco);
+    if (!rc)
+        rc = sdsp_b200_iir_bank_set_state(bk, 0, 1, mem);
+    if (!rc)
+        rc = sdsp_b200_iir_bank_process(bk, data, n_samples, n_samples, SDSP_B200_PTR_HOST, SDSP_B200_IIR_SEQUENTIAL, nullptr);
+    if (!rc)
+        rc = sdsp_b200_iir_bank_get_state(bk, 0, 1, mem);
+    return rc;
+}
+
+int sdsp_b200_debug_emulate_iir(int sections, int numerator, int precision, double gain, const double *bco, const double *aco,
+                                double *mem, void *data, size_t n_samples)
+{
+    int rc = check_bank_args(sections, precision, numerator);
+    if (rc)
+        return rc;
+    if (!aco || !mem || !data || (numerator == NUM_GENERIC && !bco))
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "emulate_iir: null argument");
+    if (precision == SDSP_B200_F32)
+        return emulate_seq_sections<float>(sections, numerator, gain, bco, aco, mem, data, n_samples);
+    return emulate_seq_sections<double>(sections, numerator, gain, bco, aco, mem, data, n_samples);
+}
+}

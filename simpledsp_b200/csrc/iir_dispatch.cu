@@ -1,0 +1,42 @@
+// iir_dispatch.cu -- chooses how a bank walks the time axis.
+//
+// The choice is a pure function of the bank configuration and the memory layout of the call
+// (channel count, alignment), never of the call length alone: reference test/testIIR.cpp:61-75 cuts a
+// stream into 32-sample calls and demands bit-identical output, and every sequential kernel evaluates
+// iir_step() in the same order, so SDSP_B200_IIR_AUTO only ever resolves to a sequential kernel unless
+// the caller opts into the (reassociating) scan with SDSP_B200_IIR_SCAN.
+#include <cstdio>
+
+#include "iir_internal.h"
+
+namespace sdsp_b200
+{
+int iir_dispatch(IirBank &b, void *data, size_t n_samples, size_t stride, int path, cudaStream_t stream)
+{
+    if (path == SDSP_B200_IIR_SCAN)
+        return set_error(SDSP_B200_ERR_UNSUPPORTED, "iir: the scan path is not built yet");
+    return iir_launch_sequential(b, data, n_samples, stride, stream);
+}
+
+int iir_describe(IirBank &b, size_t n_samples, size_t stride, int path, char *buf, size_t buf_len)
+{
+    snprintf(buf, buf_len, "iir bank: %zu channels x %d sections %s numerator=%d; n_samples=%zu stride=%zu path=%s -> sequential/generic",
+             b.n_channels, b.sections, b.precision == SDSP_B200_F32 ? "f32" : "f64", b.numerator, n_samples, stride,
+             path == SDSP_B200_IIR_SCAN ? "scan" : path == SDSP_B200_IIR_SEQUENTIAL ? "sequential" : "auto");
+    return SDSP_B200_OK;
+}
+
+void iir_bank_release_aux(IirBank &b)
+{
+    if (b.d_scan_tables)
+        cudaFree(b.d_scan_tables);
+    if (b.d_scan_flags)
+        cudaFree(b.d_scan_flags);
+    b.d_scan_tables = b.d_scan_flags = nullptr;
+}
+} // namespace sdsp_b200
+
+extern "C" int sdsp_b200_debug_emulate_iir_scan(int, int, int, double, const double *, const double *, double *, void *, size_t, int, int)
+{
+    return sdsp_b200::set_error(SDSP_B200_ERR_UNSUPPORTED, "emulate_iir_scan: the scan path is not built yet");
+}

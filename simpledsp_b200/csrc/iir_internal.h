@@ -1,0 +1,39 @@
+// iir_internal.h -- bank object and the launchers shared by the IIR translation units (internal).
+#pragma once
+#include <mutex>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "common.h"
+
+namespace sdsp_b200
+{
+struct IirBank {
+    int sections = 0, precision = 0, numerator = 0, device = 0, sm_count = 0;
+    size_t n_channels = 0;
+    void *d_coef = nullptr;  // [1 + 4m][n_channels]   gain, b1[m], b2[m], -a1[m], -a2[m]
+    void *d_state = nullptr; // [2(m + 1)][n_channels] row r: x[n-1], x[n-2]
+    // host copy of the coefficients in double (scan tables are derived from it)
+    std::vector<double> h_gain, h_b, h_a;
+    unsigned long coef_version = 0;
+    // scan path: per-channel propagation tables on the device, rebuilt when the coefficients change
+    void *d_scan_tables = nullptr;
+    size_t scan_tables_bytes = 0;
+    unsigned long scan_tables_version = ~0ul;
+    int scan_chunk = 0;
+    void *d_scan_flags = nullptr;
+    size_t scan_flags_bytes = 0;
+    // host staging
+    void *d_stage = nullptr;
+    size_t stage_bytes = 0;
+    std::mutex mu;
+};
+
+// iir.cu
+int iir_launch_sequential(const IirBank &b, void *data, size_t n_samples, size_t stride, cudaStream_t stream);
+// iir_dispatch.cu
+int iir_dispatch(IirBank &b, void *data, size_t n_samples, size_t stride, int path, cudaStream_t stream);
+int iir_describe(IirBank &b, size_t n_samples, size_t stride, int path, char *buf, size_t buf_len);
+void iir_bank_release_aux(IirBank &b);
+} // namespace sdsp_b200

@@ -1,0 +1,101 @@
+"""Batched FFT: host-side mirror of sdsp::fft_radix2 / sdsp::fft_radix4 (reference include/sdsp/fft.h:258-360)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _capi as K
+from ._buffers import describe
+
+_COMPLEX = {"complex64": K.F32, "complex128": K.F64}
+
+
+class FftPlan:
+    """A transform of ``n`` points, batched over frames: ``sdsp_b200_fft_plan_*`` of include/sdsp_b200.h.
+
+    radix is the reference's entry point (2 -> fft_radix2, any power of 2; 4 -> fft_radix4, powers of 4).
+    direction: FORWARD = forward_fft (fft.h:135-146), REVERSE = reverse_fft with the 1/N scale (:121-133).
+    """
+
+    def __init__(self, n: int, radix: int = 2, precision: int = K.F32, direction: int = K.FORWARD, device: int = 0):
+        self._h = C.c_void_p()
+        K.check(K.lib().sdsp_b200_fft_plan_create(C.byref(self._h), n, radix, precision, direction, device))
+        self.n, self.radix, self.precision, self.direction, self.device = n, radix, precision, direction, device
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            K.lib().sdsp_b200_fft_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def describe(self) -> str:
+        buf = C.create_string_buffer(1024)
+        K.check(K.lib().sdsp_b200_fft_plan_describe(self._h, buf, len(buf)))
+        return buf.value.decode()
+
+    def launches(self, n_frames: int) -> int:
+        out = C.c_int()
+        K.check(K.lib().sdsp_b200_fft_plan_launches(self._h, n_frames, C.byref(out)))
+        return out.value
+
+    def exec_ptr(self, ptr: int, n_frames: int, ptr_kind: int, stream=None) -> None:
+        K.check(K.lib().sdsp_b200_fft_exec(self._h, ptr, n_frames, ptr_kind, stream))
+
+    def __call__(self, data):
+        """Transform every length-n row of ``data`` in place (numpy: staged through the device;
+        torch CUDA tensor: in place on the current stream, asynchronously).  Returns ``data``."""
+        ptr, kind, stream, prec, dev = describe(data, _COMPLEX)
+        if prec != self.precision:
+            raise TypeError("dtype does not match the plan's precision")
+        if dev is not None and dev != self.device:
+            raise ValueError("tensor lives on another device than the plan")
+        if data.shape[-1] != self.n:
+            raise ValueError(f"last dimension must be {self.n}")
+        total = 1
+        for s in data.shape:
+            total *= int(s)
+        self.exec_ptr(ptr, total // self.n, kind, stream)
+        return data
+
+
+_plans = {}
+
+
+def _plan_for(data, radix, inverse):
+    ptr, kind, stream, prec, dev = describe(data, _COMPLEX)
+    key = (int(data.shape[-1]), radix, prec, K.REVERSE if inverse else K.FORWARD, dev or 0)
+    p = _plans.get(key)
+    if p is None:
+        p = _plans[key] = FftPlan(*key)
+    return p
+
+
+def fft_radix2(data, inverse: bool = False):
+    """sdsp::fft_radix2<T>(data) on every row of ``data``, in place (fft.h:258-299)."""
+    return _plan_for(data, 2, inverse)(data)
+
+
+def fft_radix4(data, inverse: bool = False):
+    """sdsp::fft_radix4<T>(data) on every row of ``data``, in place (fft.h:301-360)."""
+    return _plan_for(data, 4, inverse)(data)
+
+
+def digit_reverse_table(n: int, base: int, half_table: bool = False, device: int = 0) -> np.ndarray:
+    """digit_reverse<N,base> for every index, or calc_swap_lookup<N,base> when half_table
+    (fft.h:217-256), computed on the device."""
+    out = np.zeros(n, dtype=np.uint32)
+    K.check(K.lib().sdsp_b200_digit_reverse_table(n, base, int(half_table), out.ctypes.data_as(C.POINTER(C.c_uint32)), device))
+    return out
+
+
+def digit_reverse_permute(data, base: int, device: int = 0):
+    """out[rev(i)] = in[i] on every row, in place: the swap sweep of fft.h:269-273 / 351-355."""
+    ptr, kind, stream, prec, dev = describe(data, _COMPLEX)
+    n = int(data.shape[-1])
+    total = 1
+    for s in data.shape:
+        total *= int(s)
+    K.check(K.lib().sdsp_b200_digit_reverse_permute(ptr, n, base, prec, total // n, kind, dev if dev is not None else device, stream))
+    return data

@@ -1,0 +1,115 @@
+"""C-ABI library checks that need no GPU: it loads, exports every declared symbol, validates arguments,
+designs filters exactly like the oracle, and the host emulation of the kernels' per-thread code agrees
+with the oracle (index arithmetic / rounding of the CUDA path, checked where no device exists)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import simpledsp_b200 as S
+from oracle import oracle as O
+from simpledsp_b200 import _capi as K
+from tests.util import FFT_TOL, IIR_GOLDEN_ABS, IIR_TOL, ROOT, golden_impulses, peak_rel, ref_vectors, rel_l2
+
+dp = C.POINTER(C.c_double)
+
+
+def _has_gpu():
+    n = C.c_int()
+    return K.lib().sdsp_b200_device_count(C.byref(n)) == K.OK and n.value > 0
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "sdsp_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(sdsp_b200_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 30
+    lib = C.CDLL(K.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/sdsp_b200.h but not exported"
+    assert declared == set(K.SIGNATURES), declared ^ set(K.SIGNATURES)
+    assert K.lib().sdsp_b200_version() == 100
+
+
+def test_no_device_is_a_loud_error_not_a_fallback():
+    if _has_gpu():
+        pytest.skip("a GPU is present")
+    x = np.zeros(64, dtype=np.complex64)
+    with pytest.raises(S.SdspError) as e:
+        S.fft_radix2(x)
+    assert e.value.status == K.ERR_NO_DEVICE
+    with pytest.raises(S.SdspError):
+        S.IirBank(4, 8)
+    with pytest.raises(S.SdspError):
+        S.digit_reverse_table(64, 2)
+
+
+def test_argument_validation():
+    L = K.lib()
+    h = C.c_void_p()
+    assert L.sdsp_b200_fft_plan_create(C.byref(h), 100, 2, K.F32, K.FORWARD, 0) == K.ERR_INVALID_ARG
+    assert b"power of 2" in L.sdsp_b200_last_error()       # fft.h:261
+    assert L.sdsp_b200_fft_plan_create(C.byref(h), 32, 4, K.F32, K.FORWARD, 0) == K.ERR_INVALID_ARG
+    assert b"power of 4" in L.sdsp_b200_last_error()       # fft.h:304
+    assert L.sdsp_b200_fft_plan_create(C.byref(h), 64, 3, K.F32, K.FORWARD, 0) == K.ERR_INVALID_ARG
+    assert L.sdsp_b200_iir_bank_create(C.byref(h), 9, 4, K.F32, 0, 0) == K.ERR_UNSUPPORTED
+    assert L.sdsp_b200_iir_bank_create(C.byref(h), 4, 0, K.F32, 0, 0) == K.ERR_INVALID_ARG
+    assert L.sdsp_b200_digit_reverse_table(48, 2, 0, None, 0) == K.ERR_INVALID_ARG
+    with pytest.raises(ValueError):
+        S.casc_2o_iir(3)                                    # casc_2o_iir.h:25 "M must be even!"
+
+
+@pytest.mark.parametrize("sections", [2, 4, 6, 8])
+def test_designers_match_oracle_bit_for_bit(sections):
+    for ftype in (1, 2, 3):
+        for f0, fs, q, gain in ((200.0, 39e3, 1.4, 1.0), (2000.0, 39e3, 0.8, 2.0), (15000.0, 39e3, 2.0, 0.5), (10e3, 100e3, 1.1, 1.0)):
+            g, b, a = S.design(ftype, sections, f0, fs, q, gain)
+            f = O.Iir(sections)
+            f.design(ftype, f0, fs, q, gain)
+            og, ob, oa = f.coefficients()
+            assert g == og and np.array_equal(b, ob) and np.array_equal(a, oa)
+
+
+def test_preload_state_matches_oracle():
+    for ftype in (1, 2, 3):
+        f = S.casc_2o_iir(4)
+        {1: f.set_lp_coeff, 2: f.set_hp_coeff}.get(ftype, lambda a, b: f.set_bp_coeff(a, b, 1.1))(10e3, 100e3)
+        f.preload_filter(10.0)
+        o = O.Iir(4)
+        o.design(ftype, 10e3, 100e3, 1.1)
+        o.preload_filter(10.0)
+        want = np.array([[o._s.mem[r][0], o._s.mem[r][1]] for r in range(5)])
+        assert np.array_equal(f.mem, want)
+
+
+@pytest.mark.parametrize("lg", range(1, 15))
+def test_emulated_fft_kernel_code_matches_oracle(lg):
+    n = 1 << lg
+    rng = np.random.default_rng(lg)
+    x = rng.standard_normal((2, n)).astype(np.float32) + 1j * rng.standard_normal((2, n)).astype(np.float32)
+    x = x.astype(np.complex128)
+    for inv in (False, True):
+        ref = O.fft(x, 2, inv) if n >= 4 else (np.fft.ifft(x) if inv else np.fft.fft(x))
+        for name, prec, dt in (("f64", K.F64, np.complex128), ("f32", K.F32, np.complex64)):
+            if prec == K.F64 and lg > 13:
+                continue
+            a = np.ascontiguousarray(x.astype(dt))
+            K.check(K.lib().sdsp_b200_debug_emulate_fft(n, prec, int(inv), a.ctypes.data, 2))
+            assert rel_l2(a, ref) < FFT_TOL[name] * (1e-3 if name == "f64" else 0.1), (n, name, inv)
+
+
+def test_emulated_iir_kernel_code_matches_golden():
+    for name, ftype, fs, f0, q, n, h in golden_impulses():
+        g, b, a = S.design(ftype, 4, f0, fs, q)
+        for num in (0, ftype):
+            for pname, prec, dt in (("f64", K.F64, np.float64), ("f32", K.F32, np.float32)):
+                x = np.zeros(n, dtype=dt)
+                x[0] = 1
+                mem = np.zeros((5, 2))
+                K.check(K.lib().sdsp_b200_debug_emulate_iir(4, num, prec, g, b.ctypes.data_as(dp), a.ctypes.data_as(dp),
+                                                            mem.ctypes.data_as(dp), x.ctypes.data, n))
+                if pname == "f64":
+                    assert np.abs(x - h).max() < IIR_GOLDEN_ABS
+                assert peak_rel(x, h) < IIR_TOL[pname], (name, num, pname)

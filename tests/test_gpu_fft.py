@@ -1,0 +1,158 @@
+"""GPU parity of the batched FFT, through the C ABI.  Run with -m gpu on a B200."""
+import numpy as np
+import pytest
+
+import simpledsp_b200 as S
+from oracle import oracle as O
+from simpledsp_b200 import _capi as K
+from tests.util import FFT_TOL, f32_noise, ref_vectors, rel_l2
+
+pytestmark = pytest.mark.gpu
+EPS = np.finfo(np.float64).eps
+PREC = {"f64": (K.F64, np.complex128), "f32": (K.F32, np.complex64)}
+
+
+def oracle_fft(x, inverse=False):
+    x = np.asarray(x, dtype=np.complex128)
+    n = x.shape[-1]
+    if n < 4:
+        return np.fft.ifft(x) if inverse else np.fft.fft(x)
+    radix = 4 if (n.bit_length() - 1) % 2 == 0 else 2
+    return O.fft(x, radix, inverse)
+
+
+# ------------------------------------------------------------------ integer path: bit exact
+@pytest.mark.parametrize("n", [2, 4, 8, 16, 64, 256, 1024, 2048, 4096, 16384, 65536])
+def test_digit_reversal_tables_bit_exact(n):
+    for base in (2, 4):
+        if base == 4 and (n.bit_length() - 1) % 2:
+            continue
+        if n >= 4:
+            assert np.array_equal(S.digit_reverse_table(n, base, half_table=True), O.swap_lookup(n, base)), (n, base)
+        if n >= base:
+            assert np.array_equal(S.digit_reverse_table(n, base), O.digit_reverse(n, base)), (n, base)
+
+
+@pytest.mark.parametrize("n,base", [(64, 2), (64, 4), (1024, 4), (2048, 2), (4096, 4)])
+def test_digit_reverse_permute_matches_swap_sweep(n, base):
+    rng = np.random.default_rng(n)
+    x = (rng.standard_normal((5, n)) + 1j * rng.standard_normal((5, n))).astype(np.complex64)
+    rev = O.digit_reverse(n, base)
+    want = np.empty_like(x)
+    want[:, rev] = x
+    got = S.digit_reverse_permute(x.copy(), base)
+    assert np.array_equal(got, want)
+    assert np.array_equal(S.digit_reverse_permute(got.copy(), base), x)  # involution
+
+
+# ------------------------------------------------------------------ parity against the oracle
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("lg", range(1, 15))
+def test_fft_matches_oracle_all_sizes(lg, prec):
+    n = 1 << lg
+    if prec == "f64" and lg > 13:
+        pytest.skip("f64 16384 needs the multi-pass path")
+    code, dt = PREC[prec]
+    rng = np.random.default_rng(100 + lg)
+    frames = 7 if n <= 4096 else 3
+    x = f32_noise(rng, (frames, n)) + 1j * f32_noise(rng, (frames, n))
+    for inv in (False, True):
+        ref = oracle_fft(x, inv)
+        for radix in (2, 4):
+            if radix == 4 and lg % 2:
+                continue
+            got = S.FftPlan(n, radix, code, K.REVERSE if inv else K.FORWARD)(np.ascontiguousarray(x.astype(dt)))
+            assert rel_l2(got, ref) <= FFT_TOL[prec], (n, prec, inv, radix)
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_fft_matches_reference_vectors(prec):
+    code, dt = PREC[prec]
+    z = ref_vectors()
+    for n in (4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096):
+        x = z[f"fft_in_{n}"]
+        for radix in (2, 4):
+            for d, inv in (("fwd", False), ("inv", True)):
+                key = f"fft_r{radix}_{d}_{n}"
+                if key not in z:
+                    continue
+                got = (S.fft_radix4 if radix == 4 else S.fft_radix2)(np.ascontiguousarray(x.astype(dt)), inverse=inv)
+                assert rel_l2(got, z[key]) <= FFT_TOL[prec], key
+
+
+@pytest.mark.parametrize("fn", [S.fft_radix2, S.fft_radix4])
+def test_reference_known_answer_tests(fn):
+    # reference test/testFFT.cpp:17-68, 127-178 with the reference's own bound 4*N*eps
+    N, n = 64, 7
+    i = np.arange(N)
+    s = np.cos(n * 2 * np.pi * i / N).astype(np.complex128)
+    Sx = np.zeros(N, dtype=np.complex128)
+    Sx[n] = Sx[N - n] = N / 2
+    tol = 4 * N * EPS
+    assert np.abs(fn(s.copy()) - Sx).max() < tol
+    assert np.abs(fn(Sx.copy(), inverse=True) - s).max() < tol
+    s2 = np.cos(n * 2 * np.pi * i / N + np.pi / 2).astype(np.complex128)
+    S2 = np.zeros(N, dtype=np.complex128)
+    S2[n], S2[N - n] = 1j * N / 2, -1j * N / 2
+    assert np.abs(fn(s2.copy()) - S2).max() < tol
+    # linearity, test/testFFT.cpp:70-125, 180-235
+    N, fs, a1, a2 = 256, 8000.0, 1.5, 2.5
+    i = np.arange(N)
+    x1 = np.sin(2 * np.pi * 1000.0 / fs * i).astype(np.complex128)
+    x2 = np.sin(2 * np.pi * 500.0 / fs * i).astype(np.complex128)
+    lhs = fn(a1 * x1 + a2 * x2)
+    rhs = a1 * fn(x1.copy()) + a2 * fn(x2.copy())
+    assert np.abs(lhs - rhs).max() < 4 * N * EPS
+
+
+@pytest.mark.parametrize("frames", [1, 2, 3, 15, 16, 17, 255, 257, 1000])
+def test_ragged_frame_counts(frames):
+    rng = np.random.default_rng(frames)
+    for n in (16, 64, 1024):
+        x = (f32_noise(rng, (frames, n)) + 1j * f32_noise(rng, (frames, n)))
+        got = S.fft_radix2(np.ascontiguousarray(x.astype(np.complex64)))
+        assert rel_l2(got, np.fft.fft(x)) <= FFT_TOL["f32"]
+    assert S.fft_radix2(np.zeros((0, 64), dtype=np.complex64)).shape == (0, 64)  # empty batch is a no-op
+
+
+# ------------------------------------------------------------------ device-resident data, full size
+def test_device_pointer_path_and_full_size_properties():
+    torch = pytest.importorskip("torch")
+    n, frames = 4096, 65536  # BASELINE config 2
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    x = torch.randn(frames, n, 2, device="cuda", generator=g, dtype=torch.float32)
+    xc = torch.view_as_complex(x)
+    fwd = S.FftPlan(n, 4, K.F32, K.FORWARD)
+    inv = S.FftPlan(n, 4, K.F32, K.REVERSE)
+    y = xc.clone()
+    fwd(y)
+    torch.cuda.synchronize()
+    # sampled frames against the oracle
+    idx = torch.linspace(0, frames - 1, 64).long()
+    ref = oracle_fft(xc[idx].cpu().numpy())
+    assert rel_l2(y[idx].cpu().numpy(), ref) <= FFT_TOL["f32"]
+    # Parseval on every frame: sum |X|^2 = N sum |x|^2
+    e_t = (xc.abs() ** 2).sum(dim=1, dtype=torch.float64)
+    e_f = (y.abs() ** 2).sum(dim=1, dtype=torch.float64) / n
+    assert float(((e_t - e_f).abs() / e_t).max()) < 1e-5
+    # round trip on every frame
+    inv(y)
+    torch.cuda.synchronize()
+    err = (y - xc).abs().pow(2).sum(dim=1).sqrt() / xc.abs().pow(2).sum(dim=1).sqrt()
+    assert float(err.max()) <= 2 * FFT_TOL["f32"]
+
+
+def test_device_f64_batch_linearity():
+    torch = pytest.importorskip("torch")
+    n, frames = 4096, 2048
+    g = torch.Generator(device="cuda").manual_seed(5)
+    a = torch.view_as_complex(torch.randn(frames, n, 2, device="cuda", generator=g, dtype=torch.float64))
+    b = torch.view_as_complex(torch.randn(frames, n, 2, device="cuda", generator=g, dtype=torch.float64))
+    plan = S.FftPlan(n, 4, K.F64, K.FORWARD)
+    lhs = plan((1.5 * a + 2.5 * b).contiguous())
+    rhs = 1.5 * plan(a.clone()) + 2.5 * plan(b.clone())
+    torch.cuda.synchronize()
+    err = (lhs - rhs).abs().pow(2).sum(dim=1).sqrt() / rhs.abs().pow(2).sum(dim=1).sqrt()
+    assert float(err.max()) <= FFT_TOL["f64"]
+    ref = oracle_fft(a[:4].cpu().numpy())
+    assert rel_l2(plan(a[:4].clone()).cpu().numpy(), ref) <= FFT_TOL["f64"]

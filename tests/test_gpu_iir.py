@@ -1,0 +1,145 @@
+"""GPU parity of the cascaded-biquad IIR banks, through the C ABI.  Run with -m gpu on a B200."""
+import numpy as np
+import pytest
+
+import simpledsp_b200 as S
+from oracle import oracle as O
+from simpledsp_b200 import _capi as K
+from tests.util import IIR_GOLDEN_ABS, IIR_TOL, f32_noise, golden_impulses, peak_rel, ref_vectors
+
+pytestmark = pytest.mark.gpu
+PREC = {"f64": (K.F64, np.float64), "f32": (K.F32, np.float32)}
+CLS = {0: S.casc_2o_iir, 1: S.casc_2o_iir_lp, 2: S.casc_2o_iir_hp, 3: S.casc_2o_iir_bp}
+
+
+def _design(f, ftype, f0, fs, q, gain=1.0):
+    if ftype == 1:
+        f.set_lp_coeff(f0, fs, gain)
+    elif ftype == 2:
+        f.set_hp_coeff(f0, fs, gain)
+    else:
+        f.set_bp_coeff(f0, fs, q, gain)
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_golden_impulse_responses_and_block_streaming(prec):
+    # reference test/testIIR.cpp:32-77 (generic) and :223-430 (fixed numerators)
+    code, dt = PREC[prec]
+    for name, ftype, fs, f0, q, n, h in golden_impulses():
+        for num in (0, ftype):
+            f = CLS[num](4, code)
+            _design(f, ftype, f0, fs, q)
+            f2 = f.copy()
+            x = np.zeros(n, dtype=dt)
+            x[0] = 1.0
+            y = f.process(x.copy())
+            if prec == "f64":
+                assert np.abs(y - h).max() < IIR_GOLDEN_ABS, (name, num)
+            assert peak_rel(y, h) <= IIR_TOL[prec], (name, num)
+            y2 = x.copy()
+            for i in range(0, n, 32):  # 32-sample blocks and the 8-sample tail: exact equality
+                f2.process(y2[i:i + 32])
+            assert np.array_equal(y, y2), (name, num)
+
+
+def test_gain_and_preload():
+    # reference test/testIIR.cpp:79-218
+    fs, f0, q = 100e3, 10e3, 1.1
+    for ftype in (1, 2, 3):
+        x = np.zeros(1024)
+        x[0] = 1.0
+        f1, f2 = S.casc_2o_iir(4), S.casc_2o_iir(4)
+        _design(f1, ftype, f0, fs, q, 1.0)
+        _design(f2, ftype, f0, fs, q, 2.0)
+        assert np.abs(2.0 * f1.process(x.copy()) - f2.process(x.copy())).max() < 1e-12
+        f = S.casc_2o_iir(4)
+        _design(f, ftype, f0, fs, q)
+        f.preload_filter(10.0)
+        y = f.process(np.full(1024, 10.0))
+        assert np.abs(y - (10.0 if ftype == 1 else 0.0)).max() < 1e-12
+        assert peak_rel(y, ref_vectors()[f"iir_preload_t{ftype}"]) <= IIR_TOL["f64"] or ftype != 1
+
+
+def test_matches_reference_vectors_all_section_counts():
+    z = ref_vectors()
+    x = z["iir_in"][0]
+    for key in z["iir_cases"]:
+        key = str(key)
+        _, m, kind, t, fq = key.split("_")
+        sections, ftype, f0 = int(m[1:]), int(t[1:]), float(fq[1:])
+        num = {"generic": 0, "lp": 1, "hp": 2, "bp": 3}[kind]
+        for prec in ("f64", "f32"):
+            code, dt = PREC[prec]
+            f = CLS[num](sections, code)
+            _design(f, ftype, f0, 100e3, 1.1, 1.0 if f0 > 1e3 else 0.75)
+            y = x.astype(dt)
+            f.process(y[:300])
+            f.process(y[300:])
+            tol = IIR_TOL[prec] if f0 > 1e3 or prec == "f64" else 20 * IIR_TOL[prec]  # 500 Hz/100 kHz in fp32: SURVEY H3
+            assert peak_rel(y, z[key]) <= tol, (key, prec)
+
+
+def _bank_case(n_channels, n_samples, prec, sections=4, seed=0):
+    code, dt = PREC[prec]
+    rng = np.random.default_rng(seed)
+    fs = 100e3
+    ftype = np.where(np.arange(n_channels) % 2 == 0, 1, 2)
+    f0 = np.geomspace(1e3, 20e3, n_channels)
+    gains, bs, as_ = [], [], []
+    for c in range(n_channels):
+        g, b, a = S.design(int(ftype[c]), sections, float(f0[c]), fs)
+        gains.append(g)
+        bs.append(b)
+        as_.append(a)
+    x = f32_noise(rng, (n_channels, n_samples))
+    ref = O.iir_bank_port(x, ftype, f0, fs, sections=sections)
+    bank = S.IirBank(sections, n_channels, code)
+    bank.set_coeffs(np.array(gains), np.array(bs), np.array(as_))
+    return bank, x.astype(dt), ref
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("n_channels,n_samples", [(1, 1000), (31, 257), (32, 64), (33, 4096), (100, 1000), (257, 31), (64, 1)])
+def test_bank_matches_oracle_ragged_shapes(n_channels, n_samples, prec):
+    bank, x, ref = _bank_case(n_channels, n_samples, prec, seed=n_channels)
+    y = bank.process(x.copy())
+    assert peak_rel(y, ref) <= IIR_TOL[prec]
+    # streaming: same data in three uneven calls on a fresh state gives the identical bits
+    bank.reset_state()
+    y2 = x.copy()
+    cuts = [0, n_samples // 3, n_samples // 3 + 7 if n_samples > 30 else n_samples // 3, n_samples]
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        if hi > lo:
+            part = np.ascontiguousarray(y2[:, lo:hi])
+            bank.process(part)
+            y2[:, lo:hi] = part
+    assert np.array_equal(y, y2)
+
+
+def test_bank_state_roundtrip_and_device_pointer_path():
+    torch = pytest.importorskip("torch")
+    bank, x, ref = _bank_case(96, 2048, "f32", seed=3)
+    xd = torch.from_numpy(x).cuda()
+    bank.process(xd[:, :1024].contiguous())  # first half on the device
+    st = bank.get_state()
+    assert st.shape == (96, 5, 2)
+    bank2, _, _ = _bank_case(96, 2048, "f32", seed=3)
+    bank2.set_state(st)
+    second = xd[:, 1024:].contiguous()
+    bank2.process(second)
+    torch.cuda.synchronize()
+    assert peak_rel(second.cpu().numpy(), ref[:, 1024:]) <= IIR_TOL["f32"]
+    # strided device view: channel_stride > n_samples
+    bank.reset_state()
+    wide = torch.zeros(96, 2048 + 64, device="cuda", dtype=torch.float32)
+    wide[:, :2048] = torch.from_numpy(x).cuda()
+    bank.process_ptr(wide.data_ptr(), 2048, 2048 + 64, K.PTR_DEVICE, K.IIR_AUTO, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert peak_rel(wide[:, :2048].cpu().numpy(), ref) <= IIR_TOL["f32"]
+    assert float(wide[:, 2048:].abs().max()) == 0.0  # padding untouched
+
+
+@pytest.mark.parametrize("sections", [2, 6, 8])
+def test_bank_other_section_counts(sections):
+    bank, x, ref = _bank_case(40, 512, "f64", sections=sections, seed=sections)
+    assert peak_rel(bank.process(x.copy()), ref) <= IIR_TOL["f64"]

@@ -1,0 +1,161 @@
+"""Pins the CPU oracle (oracle/sdsp_oracle.c) -- CPU only.
+
+Checked against: the reference's golden impulse responses, the analytic known answers of the
+reference's FFT tests, vectors produced by the unmodified reference headers (tests/golden/ref_vectors.npz)
+and, when it has been built, the compiled reference itself (oracle/_ref/libsdsp_ref.so)."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests.util import IIR_GOLDEN_ABS, golden_impulses, ref_vectors, rel_l2
+
+EPS = np.finfo(np.float64).eps
+KIND_OF = {1: "lp", 2: "hp", 3: "bp"}
+
+
+# ------------------------------------------------------------------ integer path: bit exact
+@pytest.mark.parametrize("n", [4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096])
+def test_swap_lookup_matches_reference_vectors(n):
+    z = ref_vectors()
+    for base in (2, 4):
+        key = f"swap_b{base}_{n}"
+        if key not in z:
+            continue
+        assert np.array_equal(O.swap_lookup(n, base), z[key])
+
+
+@pytest.mark.parametrize("n", [16384, 65536])
+def test_swap_lookup_checksums_large(n):
+    z = ref_vectors()
+    for base in (2, 4):
+        t = O.swap_lookup(n, base).astype(np.uint64)
+        got = np.array([t.sum(), (t * (np.arange(n, dtype=np.uint64) + 1)).sum()], dtype=np.uint64)
+        assert np.array_equal(got, z[f"swapsum_b{base}_{n}"])
+
+
+def test_swap_table_n16_base2_known():
+    # SURVEY 8(a) F6, probe of calc_swap_lookup<16,2>
+    assert O.swap_lookup(16, 2).tolist() == [0, 8, 4, 12, 4, 10, 6, 14, 8, 9, 10, 13, 12, 13, 14, 15]
+
+
+@pytest.mark.parametrize("n,base", [(64, 2), (64, 4), (1024, 2), (1024, 4), (4096, 4), (2048, 2)])
+def test_digit_reverse_is_an_involution(n, base):
+    r = O.digit_reverse(n, base)
+    assert np.array_equal(r[r], np.arange(n))
+    assert sorted(r.tolist()) == list(range(n))
+
+
+# ------------------------------------------------------------------ FFT
+@pytest.mark.parametrize("n", [4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096])
+def test_fft_port_matches_reference_vectors(n):
+    z = ref_vectors()
+    x = z[f"fft_in_{n}"]
+    for radix in (2, 4):
+        for d, inv in (("fwd", False), ("inv", True)):
+            key = f"fft_r{radix}_{d}_{n}"
+            if key not in z:
+                continue
+            got = O.fft(x, radix, inv)
+            if n <= 256:  # libm and GCC's constant folding agree on every twiddle: bit exact
+                assert np.array_equal(got, z[key]), key
+            else:         # a few twiddles differ by one ulp (oracle/README.md)
+                assert rel_l2(got, z[key]) < 4 * EPS, key
+
+
+@pytest.mark.parametrize("radix", [2, 4])
+def test_fft_known_answer_tone(radix):
+    # reference test/testFFT.cpp:17-68 / 127-178
+    N, n = 64, 7
+    i = np.arange(N)
+    s = np.cos(n * 2 * np.pi * i / N).astype(np.complex128)
+    S = np.zeros(N, dtype=np.complex128)
+    S[n] = S[N - n] = N / 2
+    tol = 4 * N * EPS
+    assert np.abs(O.fft(s, radix) - S).max() < tol
+    assert np.abs(O.fft(S, radix, inverse=True) - s).max() < tol
+    s2 = np.cos(n * 2 * np.pi * i / N + np.pi / 2).astype(np.complex128)
+    S2 = np.zeros(N, dtype=np.complex128)
+    S2[n], S2[N - n] = 1j * N / 2, -1j * N / 2
+    assert np.abs(O.fft(s2, radix) - S2).max() < tol
+
+
+@pytest.mark.parametrize("radix", [2, 4])
+def test_fft_linearity(radix):
+    # reference test/testFFT.cpp:70-125 / 180-235
+    N, fs, a1, a2 = 256, 8000.0, 1.5, 2.5
+    i = np.arange(N)
+    x1 = np.sin(2 * np.pi * 1000.0 / fs * i).astype(np.complex128)
+    x2 = np.sin(2 * np.pi * 500.0 / fs * i).astype(np.complex128)
+    lhs = O.fft(a1 * x1 + a2 * x2, radix)
+    rhs = a1 * O.fft(x1, radix) + a2 * O.fft(x2, radix)
+    assert np.abs(lhs - rhs).max() < 4 * N * EPS
+
+
+def test_fft_against_numpy_and_compiled_reference():
+    rng = np.random.default_rng(7)
+    for n in (64, 1024, 4096):
+        x = rng.standard_normal((3, n)) + 1j * rng.standard_normal((3, n))
+        for radix in (2, 4):
+            assert rel_l2(O.fft(x, radix), np.fft.fft(x)) < 1e-15
+            if O.have_ref():
+                assert rel_l2(O.fft(x, radix), O.fft(x, radix, impl="reference")) < 4 * EPS
+
+
+def test_fft_rejects_bad_sizes():
+    with pytest.raises(ValueError):
+        O.fft(np.zeros(12, dtype=np.complex128), 2)
+    with pytest.raises(ValueError):
+        O.fft(np.zeros(32, dtype=np.complex128), 4)  # fft.h:304: radix 4 needs a power of 4
+
+
+# ------------------------------------------------------------------ IIR
+@pytest.mark.parametrize("impl", ["port", "reference"])
+def test_iir_golden_impulse_responses(impl):
+    # reference test/testIIR.cpp:32-77 and 223-430
+    if impl == "reference" and not O.have_ref():
+        pytest.skip("oracle/_ref not built")
+    count = 0
+    for name, ftype, fs, f0, q, n, h in golden_impulses():
+        for kind in ("generic", KIND_OF[ftype]):
+            f = O.Iir(4, kind, impl)
+            f.design(ftype, f0, fs, q)
+            f2 = f.copy()
+            x = np.zeros(n)
+            x[0] = 1.0
+            y = f.process(x)
+            assert np.abs(y - h).max() < IIR_GOLDEN_ABS, (name, kind)
+            parts = [f2.process(x[i:i + 32]) for i in range(0, n, 32)]  # 32-sample blocks + 8-sample tail
+            assert np.array_equal(np.concatenate(parts), y), (name, kind)
+            count += 1
+    assert count == 18
+
+
+def test_iir_port_matches_reference_vectors():
+    z = ref_vectors()
+    x = z["iir_in"][0]
+    for key in z["iir_cases"]:
+        key = str(key)
+        _, m, kind, t, f = key.split("_")
+        sections, ftype, f0 = int(m[1:]), int(t[1:]), float(f[1:])
+        flt = O.Iir(sections, kind, "port")
+        flt.design(ftype, f0, 100e3, 1.1, 1.0 if f0 > 1e3 else 0.75)
+        y = np.concatenate([flt.process(x[:300]), flt.process(x[300:])])
+        assert np.array_equal(y, z[key]), key
+
+
+def test_iir_gain_and_preload():
+    # reference test/testIIR.cpp:79-218
+    fs, f0, q = 100e3, 10e3, 1.1
+    x = np.zeros(1024)
+    x[0] = 1.0
+    for ftype in (1, 2, 3):
+        f1, f2 = O.Iir(4), O.Iir(4)
+        f1.design(ftype, f0, fs, q, 1.0)
+        f2.design(ftype, f0, fs, q, 2.0)
+        assert np.abs(2.0 * f1.process(x) - f2.process(x)).max() < 1e-12
+        f = O.Iir(4)
+        f.design(ftype, f0, fs, q)
+        f.preload_filter(10.0)
+        y = f.process(np.full(1024, 10.0))
+        assert np.abs(y - (10.0 if ftype == 1 else 0.0)).max() < 1e-12
+        assert np.array_equal(y, ref_vectors()[f"iir_preload_t{ftype}"])

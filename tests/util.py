@@ -1,0 +1,43 @@
+"""Shared helpers for the test-suite (checker side only)."""
+import os
+
+import numpy as np
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+# tolerances stated by BASELINE.json north_star
+FFT_TOL = {"f64": 1e-12, "f32": 1e-5}   # relative L2 error per frame
+IIR_TOL = {"f64": 1e-10, "f32": 1e-4}   # max |err| / max |ref| per channel
+IIR_GOLDEN_ABS = 1e-12                  # reference test/testIIR.cpp:59 (fp64)
+
+
+def rel_l2(obs, ref):
+    obs = np.asarray(obs).astype(np.complex128)
+    ref = np.asarray(ref).astype(np.complex128)
+    num = np.sqrt((np.abs(obs - ref) ** 2).sum(axis=-1))
+    den = np.sqrt((np.abs(ref) ** 2).sum(axis=-1))
+    return float(np.max(num / np.where(den == 0, 1, den)))
+
+
+def peak_rel(obs, ref):
+    obs = np.asarray(obs, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    num = np.abs(obs - ref).max(axis=-1)
+    den = np.abs(ref).max(axis=-1)
+    return float(np.max(num / np.where(den == 0, 1, den)))
+
+
+def golden_impulses():
+    z = np.load(os.path.join(GOLDEN, "impulse_response.npz"))
+    for name in z["names"]:
+        ftype, fs, f0, q, n = z[str(name) + "_header"]
+        yield str(name), int(ftype), float(fs), float(f0), float(q), int(n), z[str(name) + "_h"]
+
+
+def ref_vectors():
+    return np.load(os.path.join(GOLDEN, "ref_vectors.npz"))
+
+
+def f32_noise(rng, shape):
+    return rng.standard_normal(shape).astype(np.float32).astype(np.float64)
