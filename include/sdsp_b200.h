@@ -94,6 +94,11 @@ int sdsp_b200_fft_plan_describe(sdsp_b200_fft_plan plan, char *buf, size_t buf_l
 /* number of kernel launches one exec of n_frames device-resident frames issues */
 int sdsp_b200_fft_plan_launches(sdsp_b200_fft_plan plan, size_t n_frames, int *launches);
 
+/* The reference's twiddle table calc_wCoeffs<N,T>() (fft.h:197-214): out[log2(n)][n][2] doubles,
+ * W[i][j] = exp(-i * Sign * 2 pi j / 2^(i+1)).  Host only (no device needed); produced by the same
+ * octant-symmetric long-double generator that fills the device tables. */
+int sdsp_b200_twiddle_table(uint32_t n, int direction, double *out);
+
 /* Digit-reversal tables, computed on the device (reference fft.h:217-236 digit_reverse<N,base>,
  * :238-256 calc_swap_lookup<N,base>).  base 2 or 4.  half_table = 0: out[i] = rev(i);
  * half_table = 1: the reference's swap table (the higher index of every pair maps to itself).

@@ -592,6 +592,27 @@ int sdsp_b200_digit_reverse_permute(void *data, uint32_t n, uint32_t base, int p
     return SDSP_B200_OK;
 }
 
+// W[i][j] = exp(-i * Sign * 2 pi j / 2^(i+1)), i < log2(n), j < n: the table of reference fft.h:197-214,
+// produced by the generator that fills the device tables (host only, no device needed)
+int sdsp_b200_twiddle_table(uint32_t n, int direction, double *out)
+{
+    if (!out || !is_pow2(n) || n < 2)
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "twiddle_table: n=%u must be a power of 2 and out non-null", n);
+    if (direction != SDSP_B200_FORWARD && direction != SDSP_B200_REVERSE)
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "twiddle_table: bad direction %d", direction);
+    const int rows = ilog2(n);
+    for (int i = 0; i < rows; i++) {
+        const uint64_t den = 2ull << i;
+        for (uint32_t j = 0; j < n; j++) {
+            long double re, im;
+            unit_root(j, den, re, im);
+            out[2 * ((size_t)i * n + j)] = (double)re;
+            out[2 * ((size_t)i * n + j) + 1] = direction == SDSP_B200_REVERSE ? (double)-im : (double)im;
+        }
+    }
+    return SDSP_B200_OK;
+}
+
 int sdsp_b200_debug_emulate_fft(uint32_t n, int precision, int direction, void *data, size_t n_frames)
 {
     int rc = check_fft_args(n, 2, precision, direction);

@@ -1,0 +1,26 @@
+"""The reference's OWN test-suite (test/testFFT.cpp, test/testIIR.cpp), compiled unmodified against the
+drop-in headers include/sdsp/*.h + libsdsp_b200.so (oracle/Makefile target `reftests`, built in the build
+container where /root/reference exists; the binary and its CSV fixtures travel under oracle/_ref/)."""
+import os
+import subprocess
+
+import pytest
+
+from tests.util import ROOT
+
+pytestmark = pytest.mark.gpu
+BIN = os.path.join(ROOT, "oracle", "_ref", "ref_tests_dropin")
+
+
+def test_reference_test_suite_passes_through_the_gpu_dropin():
+    if not os.path.exists(BIN):
+        pytest.skip("oracle/_ref/ref_tests_dropin not built (needs /root/reference at build time)")
+    # the tests open ../../../test_data/impulse_response relative to the working directory
+    cwd = os.path.join(ROOT, "oracle", "_ref", "run", "a", "b")
+    os.makedirs(cwd, exist_ok=True)
+    r = subprocess.run([BIN, "--order", "rand", "--warn", "NoAssertions"], cwd=cwd, capture_output=True, text=True, timeout=600)
+    print(r.stdout[-4000:])
+    print(r.stderr[-2000:])
+    assert r.returncode == 0, r.stdout[-2000:]
+    assert "0 failed" in r.stdout
+    assert r.stdout.count("[ ok ]") >= 10  # 5 FFT + 5 IIR test cases
