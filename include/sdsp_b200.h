@@ -162,9 +162,12 @@ int sdsp_b200_iir_process_once(int sections, int numerator, int precision, doubl
 int sdsp_b200_debug_emulate_fft(uint32_t n, int precision, int direction, void *data, size_t n_frames);
 int sdsp_b200_debug_emulate_iir(int sections, int numerator, int precision, double gain, const double *b,
                                 const double *a, double *mem, void *data, size_t n_samples);
+/* the scan path's algorithm (iir_scan_core.cuh) played on the host: whole tiles of 32*chunk samples go
+ * through the chunked scan, the remainder through the sequential loop.  force_general != 0 takes the
+ * wait-for-predecessor carry path whatever the filter's reach. */
 int sdsp_b200_debug_emulate_iir_scan(int sections, int numerator, int precision, double gain, const double *b,
                                      const double *a, double *mem, void *data, size_t n_samples,
-                                     int chunk, int tile_chunks);
+                                     int chunk, int force_general);
 
 #ifdef __cplusplus
 }

@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libsdsp_b200.so")
+# SDSP_B200_LIB: kernel-tuning aid only (benchmarking alternative builds of the same library)
+LIB_PATH = os.environ.get("SDSP_B200_LIB") or os.path.join(HERE, "lib", "libsdsp_b200.so")
 
 # enums of include/sdsp_b200.h
 OK, ERR_INVALID_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_OOM, ERR_NO_DEVICE = range(6)

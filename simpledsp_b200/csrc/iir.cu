@@ -182,7 +182,15 @@ static void emulate_seq(double gain, const double *b, const double *a, double *m
         s.h[r][1] = (T)mem[2 * r + 1];
     }
     T *d = static_cast<T *>(data);
-    for (size_t i = 0; i < n; i++)
+    // as the TMA kernel does: whole tiles with the sections skewed, the ragged tail sample by sample
+    constexpr int TS = 2 * 128 / (int)sizeof(T);
+    size_t i = 0;
+    for (; i + TS <= n; i += TS) {
+        T *tile = d + i;
+        iir_tile_dispatch<T, M, KIND, TS>(
+            c, s, [&](int k) -> T { return tile[k]; }, [&](int k, T y) { tile[k] = y; });
+    }
+    for (; i < n; i++)
         d[i] = iir_step<T, M, KIND>(d[i], c, s);
     for (int r = 0; r <= M; r++) {
         mem[2 * r] = (double)s.h[r][0];

@@ -6,23 +6,42 @@
 // iir_step() in the same order, so SDSP_B200_IIR_AUTO only ever resolves to a sequential kernel unless
 // the caller opts into the (reassociating) scan with SDSP_B200_IIR_SCAN.
 #include <cstdio>
+#include <cstdlib>
 
 #include "iir_internal.h"
 
 namespace sdsp_b200
 {
+// Both sequential kernels produce identical bits (same iir_section() calls in the same order), so which
+// one runs may depend on the call: the TMA kernel needs a 16-byte aligned base and pitch and pays off
+// once a warp has a few stages of work.
+static bool iir_use_tma(const IirBank &b, const void *data, size_t n_samples, size_t stride)
+{
+    static const bool disabled = getenv("SDSP_B200_NO_TMA") != nullptr;
+    if (disabled || !iir_tma_built_for(b.sections))
+        return false;
+    if (n_samples < 256)
+        return false;
+    return iir_tma_applicable(b, data, n_samples, stride);
+}
+
 int iir_dispatch(IirBank &b, void *data, size_t n_samples, size_t stride, int path, cudaStream_t stream)
 {
     if (path == SDSP_B200_IIR_SCAN)
         return set_error(SDSP_B200_ERR_UNSUPPORTED, "iir: the scan path is not built yet");
+    if (iir_use_tma(b, data, n_samples, stride))
+        return iir_launch_tma(b, data, n_samples, stride, stream);
     return iir_launch_sequential(b, data, n_samples, stride, stream);
 }
 
 int iir_describe(IirBank &b, size_t n_samples, size_t stride, int path, char *buf, size_t buf_len)
 {
-    snprintf(buf, buf_len, "iir bank: %zu channels x %d sections %s numerator=%d; n_samples=%zu stride=%zu path=%s -> sequential/generic",
+    // alignment of the (unknown here) base pointer is assumed: describe() reports the kernel a 16-byte aligned call gets
+    const bool tma = path != SDSP_B200_IIR_SCAN && iir_use_tma(b, nullptr, n_samples, stride);
+    snprintf(buf, buf_len, "iir bank: %zu channels x %d sections %s numerator=%d; n_samples=%zu stride=%zu path=%s -> %s",
              b.n_channels, b.sections, b.precision == SDSP_B200_F32 ? "f32" : "f64", b.numerator, n_samples, stride,
-             path == SDSP_B200_IIR_SCAN ? "scan" : path == SDSP_B200_IIR_SEQUENTIAL ? "sequential" : "auto");
+             path == SDSP_B200_IIR_SCAN ? "scan" : path == SDSP_B200_IIR_SEQUENTIAL ? "sequential" : "auto",
+             path == SDSP_B200_IIR_SCAN ? "scan" : tma ? "sequential/tma (warp per 32 channels, skewed sections, 4-stage TMA ring)" : "sequential/generic");
     return SDSP_B200_OK;
 }
 
@@ -36,7 +55,3 @@ void iir_bank_release_aux(IirBank &b)
 }
 } // namespace sdsp_b200
 
-extern "C" int sdsp_b200_debug_emulate_iir_scan(int, int, int, double, const double *, const double *, double *, void *, size_t, int, int)
-{
-    return sdsp_b200::set_error(SDSP_B200_ERR_UNSUPPORTED, "emulate_iir_scan: the scan path is not built yet");
-}

@@ -32,6 +32,10 @@ struct IirBank {
 
 // iir.cu
 int iir_launch_sequential(const IirBank &b, void *data, size_t n_samples, size_t stride, cudaStream_t stream);
+// iir_tma.cu -- the fast sequential path (needs 16-byte aligned base and pitch, even section count)
+bool iir_tma_applicable(const IirBank &b, const void *data, size_t n_samples, size_t stride);
+bool iir_tma_built_for(int sections);
+int iir_launch_tma(const IirBank &b, void *data, size_t n_samples, size_t stride, cudaStream_t stream);
 // iir_dispatch.cu
 int iir_dispatch(IirBank &b, void *data, size_t n_samples, size_t stride, int path, cudaStream_t stream);
 int iir_describe(IirBank &b, size_t n_samples, size_t stride, int path, char *buf, size_t buf_len);

@@ -113,3 +113,55 @@ def test_emulated_iir_kernel_code_matches_golden():
                 if pname == "f64":
                     assert np.abs(x - h).max() < IIR_GOLDEN_ABS
                 assert peak_rel(x, h) < IIR_TOL[pname], (name, num, pname)
+
+
+@pytest.mark.parametrize("sections", [2, 4, 6, 8])
+def test_skewed_tiles_are_bit_identical_to_the_plain_loop(sections):
+    """The TMA kernel filters whole tiles with the sections software-skewed and ragged tails sample by
+    sample (iir_core.cuh).  Emulated on the host: a stream cut into 7-sample calls (plain loop only) must
+    reproduce the whole-buffer run (skewed tiles) bit for bit -- reference test/testIIR.cpp:61-75."""
+    L = K.lib()
+    rng = np.random.default_rng(sections)
+    for num in (0, 1, 2, 3):
+        g, b, a = S.design(num if num else 1, sections, 3000.0, 100e3, 1.1)
+        for prec, dt in ((K.F64, np.float64), (K.F32, np.float32)):
+            x = rng.standard_normal(1000).astype(dt)
+            whole, mem = x.copy(), np.zeros((sections + 1, 2))
+            K.check(L.sdsp_b200_debug_emulate_iir(sections, num, prec, g, b.ctypes.data_as(dp), a.ctypes.data_as(dp),
+                                                  mem.ctypes.data_as(dp), whole.ctypes.data, whole.size))
+            parts, mem2 = x.copy(), np.zeros((sections + 1, 2))
+            for i in range(0, 1000, 7):
+                blk = parts[i:i + 7]
+                K.check(L.sdsp_b200_debug_emulate_iir(sections, num, prec, g, b.ctypes.data_as(dp), a.ctypes.data_as(dp),
+                                                      mem2.ctypes.data_as(dp), blk.ctypes.data, blk.size))
+            assert np.array_equal(whole, parts) and np.array_equal(mem, mem2)
+
+
+@pytest.mark.parametrize("case", [(1, 10e3, 100e3), (2, 10e3, 100e3), (3, 2000.0, 39e3), (1, 200.0, 39e3)])
+def test_emulated_scan_algorithm_matches_oracle(case):
+    """The chunked state-space scan (iir_scan_core.cuh) played on the host: zero-state chunks, Kogge-Stone
+    carry over 32 lanes, look-back over tiles, natural-response correction -- against the sequential
+    reference on the same input, both carry paths, ragged length (the tail takes the sequential loop)."""
+    ftype, f0, fs = case
+    L = K.lib()
+    rng = np.random.default_rng(int(f0))
+    g, b, a = S.design(ftype, 4, f0, fs, 1.1)
+    for chunk in (16, 128):
+        n = 32 * chunk * 3 + 77
+        x = rng.standard_normal(n).astype(np.float32).astype(np.float64)
+        f = O.Iir(4)
+        f.design(ftype, f0, fs, 1.1)
+        ref = f.process(x)
+        for force_general in (0, 1):
+            for pname, prec, dt in (("f64", K.F64, np.float64), ("f32", K.F32, np.float32)):
+                y = x.astype(dt)
+                mem = np.zeros((5, 2))
+                K.check(L.sdsp_b200_debug_emulate_iir_scan(4, 0, prec, g, b.ctypes.data_as(dp), a.ctypes.data_as(dp),
+                                                           mem.ctypes.data_as(dp), y.ctypes.data, n, chunk, force_general))
+                assert peak_rel(y, ref) <= IIR_TOL[pname], (case, chunk, force_general, pname)
+                # the history handed back continues the stream: next block through the sequential emulator
+                nxt = rng.standard_normal(50).astype(dt)
+                want = f.copy().process(nxt.astype(np.float64))
+                K.check(L.sdsp_b200_debug_emulate_iir(4, 0, prec, g, b.ctypes.data_as(dp), a.ctypes.data_as(dp),
+                                                      mem.ctypes.data_as(dp), nxt.ctypes.data, nxt.size))
+                assert peak_rel(nxt, want) <= 10 * IIR_TOL[pname]

@@ -143,3 +143,34 @@ def test_bank_state_roundtrip_and_device_pointer_path():
 def test_bank_other_section_counts(sections):
     bank, x, ref = _bank_case(40, 512, "f64", sections=sections, seed=sections)
     assert peak_rel(bank.process(x.copy()), ref) <= IIR_TOL["f64"]
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_tma_and_generic_kernels_agree_bit_for_bit(prec):
+    """An unaligned base pointer forces the generic kernel; an aligned one takes the TMA kernel.  Same
+    arithmetic, same bits -- which is what lets SDSP_B200_IIR_AUTO pick by layout."""
+    torch = pytest.importorskip("torch")
+    code, dt = PREC[prec]
+    tdt = torch.float32 if prec == "f32" else torch.float64
+    n_channels, n = 70, 5000
+    bank, x, ref = _bank_case(n_channels, n, prec, seed=11)
+    stride = 5008
+    wide = torch.zeros(n_channels * stride + 8, device="cuda", dtype=tdt)
+    a = wide[: n_channels * stride].view(n_channels, stride)
+    a[:, :n] = torch.from_numpy(x).cuda()
+    bank.process_ptr(a.data_ptr(), n, stride, K.PTR_DEVICE, K.IIR_AUTO, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert "tma" in bank.describe(n, stride)
+    y_tma = a[:, :n].cpu().numpy()
+    st_tma = bank.get_state()
+    bank.reset_state()
+    wide2 = torch.zeros(n_channels * stride + 8, device="cuda", dtype=tdt)
+    b = wide2[1: n_channels * stride + 1].view(n_channels, stride)  # base off by one element
+    b[:, :n] = torch.from_numpy(x).cuda()
+    bank.process_ptr(b.data_ptr(), n, stride, K.PTR_DEVICE, K.IIR_AUTO, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    y_gen = b[:, :n].cpu().numpy()
+    assert np.array_equal(y_tma, y_gen)
+    assert np.array_equal(st_tma, bank.get_state())
+    assert peak_rel(y_tma, ref) <= IIR_TOL[prec]
+    assert float(a[:, n:].abs().max()) == 0.0 and float(wide[n_channels * stride:].abs().max()) == 0.0  # nothing outside the ranges written
