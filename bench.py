@@ -35,9 +35,11 @@ WORKLOADS = {
     # name: (kind, params)
     "fft4096_f32": dict(kind="fft", n=4096, frames=65536, precision="f32", bytes_per_sample=16),
     "fft4096_f64": dict(kind="fft", n=4096, frames=65536, precision="f64", bytes_per_sample=32),
+    "fft65536_f32": dict(kind="fft", n=65536, frames=4096, precision="f32", bytes_per_sample=16),
     "fft1024_f32": dict(kind="fft", n=1024, frames=262144, precision="f32", bytes_per_sample=16),
     "iir16384_f32": dict(kind="iir", channels=16384, samples=1 << 20, precision="f32", sections=4, bytes_per_sample=8),
     "iir4096_f32": dict(kind="iir", channels=4096, samples=1 << 22, precision="f32", sections=4, bytes_per_sample=8),
+    "iir4096_f32_scan": dict(kind="iir", channels=4096, samples=1 << 22, precision="f32", sections=4, bytes_per_sample=8, path="scan"),
     "iirscan_f64": dict(kind="iir", channels=1, samples=1 << 30, precision="f64", sections=4, bytes_per_sample=16, path="scan"),
 }
 

@@ -220,6 +220,14 @@ struct FftPlan {
     void *d_tw = nullptr;
     size_t tw_bytes = 0;
     fft_launch_fn launch = nullptr;
+    // multi-pass ("four-step") path for frames larger than one CTA can hold: n = n1 * 256
+    bool large = false;
+    int n1 = 0;
+    void *d_tw_cols = nullptr, *d_tw_rows = nullptr, *d_tw_hi = nullptr, *d_tw_lo = nullptr;
+    void *d_scratch = nullptr;
+    size_t scratch_frames = 0;
+    int large_threads_a = 0;
+    size_t large_smem_a = 0, large_smem_b = 0;
     // host staging (ptr_kind == HOST)
     void *d_stage = nullptr;
     size_t stage_bytes = 0;
@@ -287,6 +295,218 @@ static void emulate_cfg(void *frame, bool inverse)
     fft_emulate_frame<Cfg, T>(reinterpret_cast<cplx<T> *>(frame), tw.data(), inverse, (T)(1.0 / (double)Cfg::N));
 }
 
+// =================================================================================================
+// frames larger than one CTA can hold: n = n1 * 256, Cooley-Tukey with n = 256*a + b, k = k1 + n1*k2:
+//   X[k1 + n1 k2] = sum_b W_256^(b k2) [ W_n^(b k1) sum_a x[256 a + b] W_n1^(a k1) ]
+// pass A ("columns"): for 16 adjacent b at a time the n1-point transforms over a (stride 256), times the
+//   twiddle W_n^(b k1), written to a scratch frame at [k1][b] -- reads and writes are 128-byte runs;
+// pass B ("rows"): for 16 adjacent k1 at a time the 256-point transforms over b (contiguous), the results
+//   transposed through shared memory so that the 16 outputs X[k1.. + n1 k2] leave as one 128-byte run.
+// The scratch holds only a slab of frames small enough to stay in the 126 MB L2 between the two
+// passes, so HBM sees each frame once in and once out.  W_n^(b k1) is the product of two 256-/n1-entry
+// tables (W_n^x = W_n1^(x >> 8) * W_n^(x & 255)).
+constexpr int LARGE_COLS = 16; // columns / rows per CTA
+
+template <class Cfg>
+struct LargeStride { // odd frame pitch: the 16 frames a warp touches together land in different banks
+    static constexpr int value = Cfg::PADDED_N + 1;
+};
+
+template <class Cfg, typename T, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+    fft_large_cols_kernel(const cplx<T> *__restrict__ in, cplx<T> *__restrict__ out, const cplx<T> *__restrict__ tw,
+                          const cplx<T> *__restrict__ tw_hi, const cplx<T> *__restrict__ tw_lo, size_t n_frames, int inverse)
+{
+    constexpr int N1 = Cfg::N, N2 = 256;
+    static_assert(THREADS == LARGE_COLS * Cfg::TPF, "16 columns per CTA");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx<T> *smem = reinterpret_cast<cplx<T> *>(smem_raw);
+    const int col = threadIdx.x & (LARGE_COLS - 1);
+    const int t = threadIdx.x / LARGE_COLS;
+    cplx<T> *fs = smem + (size_t)col * LargeStride<Cfg>::value;
+    constexpr int TILES = N2 / LARGE_COLS; // column tiles per frame
+    const size_t work = n_frames * TILES;
+    for (size_t w = blockIdx.x; w < work; w += gridDim.x) {
+        const size_t frame = w / TILES;
+        const int c0 = (int)(w % TILES) * LARGE_COLS;
+        const cplx<T> *gp = in + frame * ((size_t)N1 * N2) + c0 + col;
+        cplx<T> v[Cfg::E];
+#pragma unroll
+        for (int e = 0; e < Cfg::E; e++)
+            v[e] = gp[(size_t)(t + Cfg::S * e) * N2];
+        if (inverse) {
+#pragma unroll
+            for (int e = 0; e < Cfg::E; e++)
+                v[e] = cplx<T>{ v[e].y, v[e].x };
+        }
+        fft_kernel_passes<Cfg, T, THREADS, 1, 0>(v, fs, tw, t);
+        cplx<T> *op = out + frame * ((size_t)N1 * N2) + c0 + col;
+        const unsigned b = (unsigned)(c0 + col);
+#pragma unroll
+        for (int e = 0; e < Cfg::E; e++) {
+            const unsigned k1 = (unsigned)(t + Cfg::S * e);
+            const unsigned x = b * k1;
+            const cplx<T> wv = cmul(tw_hi[x >> 8], tw_lo[x & 255u]);
+            op[(size_t)k1 * N2] = cmul(v[e], wv);
+        }
+        if constexpr (Cfg::NPASS > 1)
+            __syncthreads();
+    }
+}
+
+template <class Cfg, typename T, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+    fft_large_rows_kernel(const cplx<T> *__restrict__ in, cplx<T> *__restrict__ out, const cplx<T> *__restrict__ tw, size_t n_frames,
+                          int n1, int inverse, T scale)
+{
+    static_assert(Cfg::N == 256 && Cfg::TPF == 16 && THREADS == 256, "16 rows of 256 points per CTA");
+    constexpr int N2 = 256;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx<T> *smem = reinterpret_cast<cplx<T> *>(smem_raw);
+    const int fl = threadIdx.x >> 4, t = threadIdx.x & 15;
+    cplx<T> *fs = smem + (size_t)fl * LargeStride<Cfg>::value;
+    const int tiles = n1 / LARGE_COLS;
+    const size_t work = n_frames * (size_t)tiles;
+    for (size_t w = blockIdx.x; w < work; w += gridDim.x) {
+        const size_t frame = w / tiles;
+        const int r0 = (int)(w % tiles) * LARGE_COLS;
+        const cplx<T> *gp = in + frame * ((size_t)n1 * N2) + (size_t)(r0 + fl) * N2 + t;
+        cplx<T> v[Cfg::E];
+#pragma unroll
+        for (int e = 0; e < Cfg::E; e++)
+            v[e] = gp[Cfg::S * e];
+        fft_kernel_passes<Cfg, T, THREADS, 1, 0>(v, fs, tw, t);
+        if (inverse) {
+#pragma unroll
+            for (int e = 0; e < Cfg::E; e++)
+                v[e] = cplx<T>{ v[e].y * scale, v[e].x * scale };
+        }
+        __syncthreads(); // last pass has read the exchange buffer
+#pragma unroll
+        for (int e = 0; e < Cfg::E; e++)
+            fs[Cfg::pad(t + Cfg::S * e)] = v[e]; // natural order: slot e of thread t is k2 = t + 16 e
+        __syncthreads();
+        // transposed read: 16 consecutive lanes take the same k2 of 16 consecutive rows
+        const int rr = threadIdx.x & 15, q = threadIdx.x >> 4;
+        const cplx<T> *rs = smem + (size_t)rr * LargeStride<Cfg>::value;
+        cplx<T> *op = out + frame * ((size_t)n1 * N2) + r0 + rr;
+#pragma unroll
+        for (int e = 0; e < Cfg::E; e++) {
+            const int k2 = q + 16 * e;
+            op[(size_t)k2 * n1] = rs[Cfg::pad(k2)];
+        }
+        __syncthreads();
+    }
+}
+
+template <class CfgA, typename T>
+static int launch_large(const FftPlan &p, void *data, size_t n_frames, cudaStream_t stream)
+{
+    using CfgB = FftCfg<256, 16, 16, 16>;
+    constexpr int THREADS_A = LARGE_COLS * CfgA::TPF;
+    cplx<T> *d = reinterpret_cast<cplx<T> *>(data);
+    cplx<T> *scratch = reinterpret_cast<cplx<T> *>(p.d_scratch);
+    const int inverse = p.direction == SDSP_B200_REVERSE ? 1 : 0;
+    const T scale = (T)(1.0 / (double)p.n);
+    const size_t grid_cap = (size_t)p.sm_count * 8;
+    for (size_t f0 = 0; f0 < n_frames; f0 += p.scratch_frames) {
+        const size_t cnt = (n_frames - f0) < p.scratch_frames ? (n_frames - f0) : p.scratch_frames;
+        cplx<T> *slab = d + f0 * (size_t)p.n;
+        const size_t work_a = cnt * (256 / LARGE_COLS), work_b = cnt * (size_t)(p.n1 / LARGE_COLS);
+        fft_large_cols_kernel<CfgA, T, THREADS_A><<<(unsigned)(work_a < grid_cap ? work_a : grid_cap), THREADS_A, p.large_smem_a, stream>>>(
+            slab, scratch, reinterpret_cast<const cplx<T> *>(p.d_tw_cols), reinterpret_cast<const cplx<T> *>(p.d_tw_hi),
+            reinterpret_cast<const cplx<T> *>(p.d_tw_lo), cnt, inverse);
+        fft_large_rows_kernel<CfgB, T, 256><<<(unsigned)(work_b < grid_cap ? work_b : grid_cap), 256, p.large_smem_b, stream>>>(
+            scratch, slab, reinterpret_cast<const cplx<T> *>(p.d_tw_rows), cnt, p.n1, inverse, scale);
+    }
+    SDSP_CUDA(cudaGetLastError());
+    return SDSP_B200_OK;
+}
+
+template <typename T>
+static int upload_table(void **dst, const std::vector<cplx<T>> &v)
+{
+    SDSP_CUDA(cudaMalloc(dst, v.size() * sizeof(cplx<T>)));
+    SDSP_CUDA(cudaMemcpy(*dst, v.data(), v.size() * sizeof(cplx<T>), cudaMemcpyHostToDevice));
+    return SDSP_B200_OK;
+}
+
+template <class CfgA, typename T>
+static int setup_large(FftPlan &p)
+{
+    using CfgB = FftCfg<256, 16, 16, 16>;
+    constexpr int THREADS_A = LARGE_COLS * CfgA::TPF;
+    p.large = true;
+    p.n1 = CfgA::N;
+    p.npass = CfgA::NPASS + CfgB::NPASS;
+    p.e = 16;
+    p.threads = THREADS_A;
+    p.large_threads_a = THREADS_A;
+    p.large_smem_a = (size_t)LARGE_COLS * LargeStride<CfgA>::value * sizeof(cplx<T>);
+    p.large_smem_b = (size_t)LARGE_COLS * LargeStride<CfgB>::value * sizeof(cplx<T>);
+    auto ka = fft_large_cols_kernel<CfgA, T, THREADS_A>;
+    auto kb = fft_large_rows_kernel<CfgB, T, 256>;
+    if (p.large_smem_a > 48 * 1024)
+        SDSP_CUDA(cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.large_smem_a));
+    if (p.large_smem_b > 48 * 1024)
+        SDSP_CUDA(cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.large_smem_b));
+    std::vector<cplx<T>> tw;
+    int ra[4] = { CfgA::R0, CfgA::R1, CfgA::R2, CfgA::R3 }, rb[4] = { 16, 16, 1, 1 };
+    build_twiddles<T>(CfgA::N, ra, CfgA::NPASS, tw);
+    tw.push_back(cplx<T>{ 1, 0 });
+    int rc = upload_table<T>(&p.d_tw_cols, tw);
+    build_twiddles<T>(256, rb, 2, tw);
+    if (!rc)
+        rc = upload_table<T>(&p.d_tw_rows, tw);
+    std::vector<cplx<T>> hi(CfgA::N), lo(256);
+    for (int i = 0; i < CfgA::N; i++) {
+        long double re, im;
+        unit_root((uint64_t)i, (uint64_t)CfgA::N, re, im);
+        hi[i] = cplx<T>{ (T)re, (T)im };
+    }
+    for (int i = 0; i < 256; i++) {
+        long double re, im;
+        unit_root((uint64_t)i, (uint64_t)p.n, re, im);
+        lo[i] = cplx<T>{ (T)re, (T)im };
+    }
+    if (!rc)
+        rc = upload_table<T>(&p.d_tw_hi, hi);
+    if (!rc)
+        rc = upload_table<T>(&p.d_tw_lo, lo);
+    if (rc)
+        return rc;
+    // slab of frames that stays L2-resident between the two passes (about a quarter of the 126 MB L2)
+    const size_t frame_bytes = (size_t)p.n * sizeof(cplx<T>);
+    size_t slab = (32u << 20) / frame_bytes;
+    if (slab < 1)
+        slab = 1;
+    p.scratch_frames = slab;
+    if (cudaMalloc(&p.d_scratch, slab * frame_bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return set_error(SDSP_B200_ERR_OOM, "fft: cannot allocate %zu bytes of scratch", slab * frame_bytes);
+    }
+    p.launch = &launch_large<CfgA, T>;
+    p.tw_bytes = (tw.size() + hi.size() + lo.size()) * sizeof(cplx<T>);
+    return SDSP_B200_OK;
+}
+
+template <typename T>
+static int setup_large_n1(FftPlan &p)
+{
+    switch (p.n / 256) {
+    case 64: return setup_large<FftCfg<64, 16, 16, 4>, T>(p);
+    case 128: return setup_large<FftCfg<128, 16, 16, 8>, T>(p);
+    case 256: return setup_large<FftCfg<256, 16, 16, 16>, T>(p);
+    case 512: return setup_large<FftCfg<512, 16, 16, 16, 2>, T>(p);
+    case 1024:
+        if constexpr (sizeof(T) == 4)
+            return setup_large<FftCfg<1024, 16, 16, 16, 4>, T>(p);
+    default: break;
+    }
+    return set_error(SDSP_B200_ERR_UNSUPPORTED, "fft: n=%u %s exceeds the multi-pass path (up to 2^18 f32 / 2^17 f64)", p.n,
+                     p.precision == SDSP_B200_F32 ? "f32" : "f64");
+}
+
 // the factorisation table: log2(n) -> configuration.  16 points per thread wherever the frame has them.
 template <int LG>
 struct CfgFor;
@@ -343,7 +563,10 @@ static int emulate_for(int precision, bool inverse, void *frame)
 
 static int setup_plan(FftPlan &p)
 {
-    switch (ilog2(p.n)) {
+    const int lg = ilog2(p.n);
+    if (lg > (p.precision == SDSP_B200_F32 ? MAX_LOG2N_F32 : MAX_LOG2N_F64))
+        return p.precision == SDSP_B200_F32 ? setup_large_n1<float>(p) : setup_large_n1<double>(p);
+    switch (lg) {
 #define X(LG) \
     case LG: return setup_for<LG>(p);
         SDSP_FOR_EACH_LG(X)
@@ -408,8 +631,9 @@ int sdsp_b200_fft_plan_create(sdsp_b200_fft_plan *plan, uint32_t n, int radix, i
     h->p.sm_count = device_sm_count(device);
     rc = setup_plan(h->p);
     if (rc) {
-        if (h->p.d_tw)
-            cudaFree(h->p.d_tw);
+        for (void *q : { h->p.d_tw, h->p.d_tw_cols, h->p.d_tw_rows, h->p.d_tw_hi, h->p.d_tw_lo, h->p.d_scratch })
+            if (q)
+                cudaFree(q);
         delete h;
         return rc;
     }
@@ -426,6 +650,9 @@ int sdsp_b200_fft_plan_destroy(sdsp_b200_fft_plan plan)
         cudaFree(plan->p.d_tw);
     if (plan->p.d_stage)
         cudaFree(plan->p.d_stage);
+    for (void *q : { plan->p.d_tw_cols, plan->p.d_tw_rows, plan->p.d_tw_hi, plan->p.d_tw_lo, plan->p.d_scratch })
+        if (q)
+            cudaFree(q);
     delete plan;
     return SDSP_B200_OK;
 }
@@ -508,6 +735,15 @@ int sdsp_b200_fft_plan_describe(sdsp_b200_fft_plan plan, char *buf, size_t buf_l
     if (!plan || !buf || buf_len == 0)
         return set_error(SDSP_B200_ERR_INVALID_ARG, "fft_plan_describe: bad arguments");
     const FftPlan &p = plan->p;
+    if (p.large) {
+        snprintf(buf, buf_len,
+                 "fft n=%u %s %s radix-arg=%d: multi-pass, n = %d x 256: column pass (%d-point transforms, 16 columns/CTA, %d threads, "
+                 "smem %zuB) -> L2-resident scratch slab of %zu frames -> row pass (256-point transforms, transposed store, smem %zuB); "
+                 "2 launches per slab; SMs=%d",
+                 p.n, p.precision == SDSP_B200_F32 ? "f32" : "f64", p.direction == SDSP_B200_FORWARD ? "forward" : "reverse", p.radix, p.n1,
+                 p.n1, p.large_threads_a, p.large_smem_a, p.scratch_frames, p.large_smem_b, p.sm_count);
+        return SDSP_B200_OK;
+    }
     snprintf(buf, buf_len,
              "fft n=%u %s %s radix-arg=%d: single-CTA kernel, passes=%d radices=[%d,%d,%d,%d] points/thread=%d "
              "threads/CTA=%d frames/CTA=%d smem/CTA=%zuB CTAs/SM=%d SMs=%d twiddle-table=%zuB",
@@ -521,7 +757,10 @@ int sdsp_b200_fft_plan_launches(sdsp_b200_fft_plan plan, size_t n_frames, int *l
 {
     if (!plan || !launches)
         return set_error(SDSP_B200_ERR_INVALID_ARG, "fft_plan_launches: bad arguments");
-    *launches = n_frames ? 1 : 0;
+    if (plan->p.large)
+        *launches = (int)(2 * ((n_frames + plan->p.scratch_frames - 1) / plan->p.scratch_frames));
+    else
+        *launches = n_frames ? 1 : 0;
     return SDSP_B200_OK;
 }
 

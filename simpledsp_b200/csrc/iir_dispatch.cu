@@ -28,7 +28,7 @@ static bool iir_use_tma(const IirBank &b, const void *data, size_t n_samples, si
 int iir_dispatch(IirBank &b, void *data, size_t n_samples, size_t stride, int path, cudaStream_t stream)
 {
     if (path == SDSP_B200_IIR_SCAN)
-        return set_error(SDSP_B200_ERR_UNSUPPORTED, "iir: the scan path is not built yet");
+        return iir_launch_scan(b, data, n_samples, stride, stream);
     if (iir_use_tma(b, data, n_samples, stride))
         return iir_launch_tma(b, data, n_samples, stride, stream);
     return iir_launch_sequential(b, data, n_samples, stride, stream);

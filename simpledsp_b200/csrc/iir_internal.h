@@ -22,6 +22,8 @@ struct IirBank {
     size_t scan_tables_bytes = 0;
     unsigned long scan_tables_version = ~0ul;
     int scan_chunk = 0;
+    int scan_reach_max = 0;
+    unsigned scan_epoch = 0;
     void *d_scan_flags = nullptr;
     size_t scan_flags_bytes = 0;
     // host staging
@@ -36,6 +38,9 @@ int iir_launch_sequential(const IirBank &b, void *data, size_t n_samples, size_t
 bool iir_tma_applicable(const IirBank &b, const void *data, size_t n_samples, size_t stride);
 bool iir_tma_built_for(int sections);
 int iir_launch_tma(const IirBank &b, void *data, size_t n_samples, size_t stride, cudaStream_t stream);
+// iir_scan.cu -- time-parallel path
+int iir_launch_scan(IirBank &b, void *data, size_t n_samples, size_t stride, cudaStream_t stream);
+int iir_scan_chunk(int precision);
 // iir_dispatch.cu
 int iir_dispatch(IirBank &b, void *data, size_t n_samples, size_t stride, int path, cudaStream_t stream);
 int iir_describe(IirBank &b, size_t n_samples, size_t stride, int path, char *buf, size_t buf_len);

@@ -8,6 +8,7 @@
 
 #include "iir_internal.h"
 #include "iir_scan_core.cuh"
+#include "tma_ptx.cuh"
 
 namespace sdsp_b200
 {
@@ -60,6 +61,469 @@ static int emulate_scan_sections(int m, int kind, double gain, const double *b, 
     case 8: return emulate_scan_kind<T, 8>(kind, gain, b, a, mem, data, n, L, fg);
     default: return set_error(SDSP_B200_ERR_UNSUPPORTED, "scan: sections=%d not built (2, 4, 6, 8)", m);
     }
+}
+
+// =================================================================================================
+// device side
+template <typename T, int SD>
+struct alignas(16) ScanRec { // one per (channel, tile); written once per launch, tagged with the launch epoch
+    T uh[2];     // scaled-input history leaving the tile (known as soon as the tile is loaded)
+    T agg[SD];   // state leaving the tile if it had been entered with zero state
+    T incl[SD];  // true state leaving the tile
+    unsigned flag_x, flag_a, flag_i, pad;
+};
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// lane 0 polls, the warp re-converges; afterwards plain loads that bypass L1 see the published data
+__device__ __forceinline__ void warp_wait_flag(const unsigned *flag, unsigned epoch, int lane)
+{
+    if (lane == 0) {
+        while (ld_acquire_u32(flag) != epoch)
+            __nanosleep(20);
+    }
+    __syncwarp();
+}
+template <typename T>
+__device__ __forceinline__ T ld_cg(const T *p)
+{
+    return __ldcg(p);
+}
+
+// L samples per lane, 32 lanes per tile, WARPS independent warps per CTA, RG rows per TMA box
+template <typename T, int M, int KIND, int L, int WARPS, int RG>
+__global__ void __launch_bounds__(WARPS * 32)
+    iir_scan_kernel(const __grid_constant__ CUtensorMap map, const T *__restrict__ coef, T *__restrict__ state, size_t n_channels,
+                    const T *__restrict__ tables, const int *__restrict__ reach_of, ScanRec<T, 2 * M> *__restrict__ recs,
+                    unsigned *__restrict__ ticket, unsigned epoch, unsigned n_tiles, unsigned rows_per_channel)
+{
+    constexpr int SD = 2 * M;
+    constexpr int TSB = 128 / (int)sizeof(T); // samples per 128-byte box row
+    constexpr int NBOX = L / TSB;
+    constexpr int CTS = 2 * TSB; // skewed compute tile
+    static_assert(L % CTS == 0, "chunk must hold whole compute tiles");
+    constexpr int BOX_BYTES = 32 * 128;
+    constexpr int TILE_BYTES = NBOX * BOX_BYTES;
+    constexpr int VN = Vec16<T>::N;
+    constexpr int TAB = scan_table_count(M, L);
+    using V = typename Vec16<T>::type;
+
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ uint64_t bars[WARPS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char *buf = smem_raw + (size_t)warp * TILE_BYTES;
+    uint64_t *bar = &bars[warp];
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+        fence_proxy_async();
+    }
+    __syncwarp();
+    const uint32_t row_off = (uint32_t)lane * 128u;
+    const uint32_t sw = (uint32_t)(lane & 7);
+    auto elem = [&](int row, int i) -> T * { // address of sample i of chunk `row` inside the swizzled tile
+        const int box = i / TSB, chunk = (i % TSB) / VN, e = i % VN;
+        return reinterpret_cast<T *>(buf + box * BOX_BYTES + row * 128 + ((((uint32_t)chunk) ^ (uint32_t)(row & 7)) << 4)) + e;
+    };
+    const unsigned total = (unsigned)n_channels * n_tiles;
+    unsigned phase = 0;
+
+    for (;;) {
+        unsigned w = 0;
+        if (lane == 0)
+            w = atomicAdd(ticket, 1u);
+        w = __shfl_sync(0xffffffffu, w, 0);
+        if (w >= total)
+            break;
+        const unsigned ch = w / n_tiles, t = w % n_tiles;
+        const int row0 = (int)(ch * rows_per_channel + t * 32u);
+        if (lane == 0) {
+            mbar_expect_tx(bar, TILE_BYTES);
+#pragma unroll
+            for (int g = 0; g < 32 / RG; g++)
+#pragma unroll
+                for (int u = 0; u < NBOX; u++)
+                    tma_load_2d(buf + u * BOX_BYTES + g * RG * 128, &map, u * TSB, row0 + g * RG, bar);
+        }
+        // while the tile is in flight: this channel's coefficients (the same for every lane)
+        IirCoef<T, M> c;
+        c.gain = coef[ch];
+#pragma unroll
+        for (int j = 0; j < M; j++) {
+            c.b1[j] = coef[(size_t)(1 + j) * n_channels + ch];
+            c.b2[j] = coef[(size_t)(1 + M + j) * n_channels + ch];
+            c.na1[j] = coef[(size_t)(1 + 2 * M + j) * n_channels + ch];
+            c.na2[j] = coef[(size_t)(1 + 3 * M + j) * n_channels + ch];
+        }
+        const T *tab = tables + (size_t)ch * TAB;
+        const int reach = reach_of[ch];
+        ScanRec<T, SD> *rec = recs + (size_t)ch * n_tiles + t;
+
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+
+        // ---- scaled-input history entering each chunk, read before anything is overwritten
+        IirState<T, M> z;
+#pragma unroll
+        for (int r = 0; r <= M; r++)
+            z.h[r][0] = z.h[r][1] = 0;
+        if (lane > 0) {
+            z.h[0][0] = *elem(lane - 1, L - 1) * c.gain;
+            z.h[0][1] = *elem(lane - 1, L - 2) * c.gain;
+        }
+        const T out_u1 = *elem(31, L - 1) * c.gain, out_u2 = *elem(31, L - 2) * c.gain; // leaves the tile
+        if (lane == 31) {
+            rec->uh[0] = out_u1;
+            rec->uh[1] = out_u2;
+            __threadfence();
+            st_release_u32(&rec->flag_x, epoch);
+        }
+        if (t == 0) {
+            if (lane == 0) {
+                z.h[0][0] = state[(size_t)0 * n_channels + ch];
+                z.h[0][1] = state[(size_t)1 * n_channels + ch];
+            }
+        } else {
+            warp_wait_flag(&rec[-1].flag_x, epoch, lane);
+            if (lane == 0) {
+                z.h[0][0] = ld_cg(&rec[-1].uh[0]);
+                z.h[0][1] = ld_cg(&rec[-1].uh[1]);
+            }
+        }
+        __syncwarp();
+
+        // ---- zero-state pass over this lane's chunk, in place
+#pragma unroll 1
+        for (int ct = 0; ct < L / CTS; ct++) {
+            unsigned char *cbuf = buf + ct * 2 * BOX_BYTES;
+            V vin, vout;
+            iir_tile_dispatch<T, M, KIND, CTS>(
+                c, z,
+                [&](int i) -> T {
+                    if (i % VN == 0) {
+                        const int box = i / TSB, chunk = (i % TSB) / VN;
+                        vin = *reinterpret_cast<const V *>(cbuf + box * BOX_BYTES + row_off + (((uint32_t)chunk ^ sw) << 4));
+                    }
+                    return vget(vin, i % VN);
+                },
+                [&](int i, T y) {
+                    vset(vout, i % VN, y);
+                    if (i % VN == VN - 1) {
+                        const int box = i / TSB, chunk = (i % TSB) / VN;
+                        *reinterpret_cast<V *>(cbuf + box * BOX_BYTES + row_off + (((uint32_t)chunk ^ sw) << 4)) = vout;
+                    }
+                });
+        }
+        T P[SD];
+        scan_state_to_vec<T, M>(z, P);
+
+        // ---- Kogge-Stone over the 32 chunks: P = state leaving chunk `lane` had the tile been entered with zero state
+#pragma unroll
+        for (int j = 0; j < SCAN_KS_STEPS; j++) {
+            T recv[SD];
+#pragma unroll
+            for (int k = 0; k < SD; k++)
+                recv[k] = __shfl_up_sync(0xffffffffu, P[k], 1 << j);
+            if (lane >= (1 << j))
+                tri_matvec_acc<T, SD>(tab + scan_off_A(M, L, j), recv, P);
+        }
+        T agg[SD], Pprev[SD];
+#pragma unroll
+        for (int k = 0; k < SD; k++) {
+            agg[k] = __shfl_sync(0xffffffffu, P[k], 31);
+            Pprev[k] = __shfl_up_sync(0xffffffffu, P[k], 1);
+            if (lane == 0)
+                Pprev[k] = 0;
+        }
+        if (lane == 31) {
+#pragma unroll
+            for (int k = 0; k < SD; k++)
+                rec->agg[k] = agg[k];
+            __threadfence();
+            st_release_u32(&rec->flag_a, epoch);
+        }
+
+        // ---- state entering the tile (identical in every lane)
+        const T *Mt = tab + scan_off_A(M, L, SCAN_KS_STEPS);
+        T cin[SD];
+        if (t == 0) {
+#pragma unroll
+            for (int k = 0; k < SD; k++)
+                cin[k] = state[(size_t)(2 + k) * n_channels + ch];
+        } else if (reach <= SCAN_MAX_REACH) {
+            const unsigned K = (unsigned)reach < t ? (unsigned)reach : t;
+#pragma unroll
+            for (int k = 0; k < SD; k++)
+                cin[k] = (K == t) ? state[(size_t)(2 + k) * n_channels + ch] : (T)0;
+            for (unsigned kk = K; kk >= 1; kk--) {
+                const ScanRec<T, SD> *pr = rec - kk;
+                warp_wait_flag(&pr->flag_a, epoch, lane);
+                T nxt[SD];
+#pragma unroll
+                for (int k = 0; k < SD; k++)
+                    nxt[k] = ld_cg(&pr->agg[k]);
+                tri_matvec_acc<T, SD>(Mt, cin, nxt);
+#pragma unroll
+                for (int k = 0; k < SD; k++)
+                    cin[k] = nxt[k];
+            }
+        } else {
+            warp_wait_flag(&rec[-1].flag_i, epoch, lane);
+#pragma unroll
+            for (int k = 0; k < SD; k++)
+                cin[k] = ld_cg(&rec[-1].incl[k]);
+        }
+        T incl[SD];
+#pragma unroll
+        for (int k = 0; k < SD; k++)
+            incl[k] = agg[k];
+        tri_matvec_acc<T, SD>(Mt, cin, incl);
+        if (lane == 31) {
+#pragma unroll
+            for (int k = 0; k < SD; k++)
+                rec->incl[k] = incl[k];
+            __threadfence();
+            st_release_u32(&rec->flag_i, epoch);
+            if (t + 1 == n_tiles) { // the bank's history after the last whole tile
+                state[(size_t)0 * n_channels + ch] = out_u1;
+                state[(size_t)1 * n_channels + ch] = out_u2;
+#pragma unroll
+                for (int k = 0; k < SD; k++)
+                    state[(size_t)(2 + k) * n_channels + ch] = incl[k];
+            }
+        }
+
+        // ---- A_L^lane * cin by the binary digits of the lane index, plus the zero-state prefix
+        T ci[SD];
+#pragma unroll
+        for (int k = 0; k < SD; k++)
+            ci[k] = cin[k];
+#pragma unroll
+        for (int j = 0; j < SCAN_KS_STEPS; j++) {
+            T nq[SD];
+#pragma unroll
+            for (int k = 0; k < SD; k++)
+                nq[k] = 0;
+            tri_matvec_acc<T, SD>(tab + scan_off_A(M, L, j), ci, nq);
+            if (lane & (1 << j)) {
+#pragma unroll
+                for (int k = 0; k < SD; k++)
+                    ci[k] = nq[k];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < SD; k++)
+            ci[k] += Pprev[k];
+
+        // ---- natural-response correction of this lane's chunk
+#pragma unroll 4
+        for (int q = 0; q < L / VN; q++) {
+            const int box = (q * VN) / TSB, chunk = ((q * VN) % TSB) / VN;
+            V *p = reinterpret_cast<V *>(buf + box * BOX_BYTES + row_off + (((uint32_t)chunk ^ sw) << 4));
+            V v = *p;
+#pragma unroll
+            for (int e = 0; e < VN; e++) {
+                T y = vget(v, e);
+                const T *h = tab + (size_t)(q * VN + e) * SD;
+#pragma unroll
+                for (int k = 0; k < SD; k++)
+                    y = fma_t(__ldg(h + k), ci[k], y);
+                vset(v, e, y);
+            }
+            *p = v;
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+            for (int g = 0; g < 32 / RG; g++)
+#pragma unroll
+                for (int u = 0; u < NBOX; u++)
+                    tma_store_2d(&map, u * TSB, row0 + g * RG, buf + u * BOX_BYTES + g * RG * 128);
+            tma_commit();
+            tma_wait_read<0>(); // single buffer: the next tile's load must not overtake this store's reads
+        }
+        __syncwarp();
+    }
+    if (lane == 0)
+        tma_wait_all();
+}
+
+// =================================================================================================
+// host side
+template <typename T>
+struct ScanChunk; // samples per lane: 32 KiB tiles
+template <>
+struct ScanChunk<float> {
+    static constexpr int L = 256;
+};
+template <>
+struct ScanChunk<double> {
+    static constexpr int L = 128;
+};
+
+template <typename T, int M, int KIND>
+static int launch_scan(IirBank &b, void *data, size_t n_samples, size_t stride, cudaStream_t stream, size_t *done)
+{
+    constexpr int L = ScanChunk<T>::L, SD = 2 * M, WARPS = 4, RG = 8;
+    constexpr int TSB = 128 / (int)sizeof(T);
+    constexpr int TAB = scan_table_count(M, L);
+    const size_t tile = (size_t)32 * L;
+    const size_t n_tiles = n_samples / tile;
+    *done = 0;
+    if (n_tiles == 0)
+        return SDSP_B200_OK;
+    if (n_tiles * b.n_channels >= (1ull << 31))
+        return set_error(SDSP_B200_ERR_UNSUPPORTED, "iir scan: too many tiles");
+    if (b.h_gain.size() != b.n_channels)
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "iir scan: coefficients have not been set");
+
+    // per-channel propagation tables, rebuilt when the coefficients change
+    if (b.scan_tables_version != b.coef_version || b.scan_chunk != L) {
+        std::vector<T> tabs((size_t)b.n_channels * TAB);
+        std::vector<int> reach(b.n_channels);
+        std::vector<double> one;
+        for (size_t ch = 0; ch < b.n_channels; ch++) {
+            int r = 0;
+            scan_build_tables(M, KIND, b.h_gain[ch], &b.h_b[ch * 3 * M], &b.h_a[ch * 3 * M], L, one, r);
+            reach[ch] = r;
+            for (int i = 0; i < TAB; i++)
+                tabs[ch * TAB + i] = (T)one[i];
+        }
+        const size_t bytes = tabs.size() * sizeof(T) + reach.size() * sizeof(int);
+        if (b.scan_tables_bytes < bytes) {
+            if (b.d_scan_tables)
+                cudaFree(b.d_scan_tables);
+            b.d_scan_tables = nullptr;
+            b.scan_tables_bytes = 0;
+            if (cudaMalloc(&b.d_scan_tables, bytes) != cudaSuccess) {
+                cudaGetLastError();
+                return set_error(SDSP_B200_ERR_OOM, "iir scan: cannot allocate %zu bytes of tables", bytes);
+            }
+            b.scan_tables_bytes = bytes;
+        }
+        SDSP_CUDA(cudaMemcpyAsync(b.d_scan_tables, tabs.data(), tabs.size() * sizeof(T), cudaMemcpyHostToDevice, stream));
+        SDSP_CUDA(cudaMemcpyAsync(static_cast<char *>(b.d_scan_tables) + tabs.size() * sizeof(T), reach.data(), reach.size() * sizeof(int),
+                                  cudaMemcpyHostToDevice, stream));
+        SDSP_CUDA(cudaStreamSynchronize(stream)); // host vectors go out of scope
+        b.scan_tables_version = b.coef_version;
+        b.scan_chunk = L;
+        b.scan_reach_max = 0;
+        for (int r : reach)
+            b.scan_reach_max = r > b.scan_reach_max ? r : b.scan_reach_max;
+    }
+    // carry records + ticket
+    const size_t rec_bytes = sizeof(ScanRec<T, SD>) * b.n_channels * n_tiles + 256;
+    if (b.scan_flags_bytes < rec_bytes) {
+        if (b.d_scan_flags)
+            cudaFree(b.d_scan_flags);
+        b.d_scan_flags = nullptr;
+        b.scan_flags_bytes = 0;
+        if (cudaMalloc(&b.d_scan_flags, rec_bytes) != cudaSuccess) {
+            cudaGetLastError();
+            return set_error(SDSP_B200_ERR_OOM, "iir scan: cannot allocate %zu bytes of carry records", rec_bytes);
+        }
+        b.scan_flags_bytes = rec_bytes;
+        SDSP_CUDA(cudaMemsetAsync(b.d_scan_flags, 0, rec_bytes, stream));
+        b.scan_epoch = 0;
+    }
+    b.scan_epoch++;
+    unsigned *ticket = static_cast<unsigned *>(b.d_scan_flags);
+    auto *recs = reinterpret_cast<ScanRec<T, SD> *>(static_cast<char *>(b.d_scan_flags) + 256);
+    SDSP_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned), stream));
+
+    // 2-D view: rows of L samples; channel c starts at row c * (stride / L)
+    const size_t rows_per_channel = b.n_channels > 1 ? stride / L : n_tiles * 32;
+    const size_t total_rows = (b.n_channels - 1) * rows_per_channel + n_tiles * 32;
+    CUtensorMap map;
+    const cuuint64_t gdim[2] = { (cuuint64_t)L, (cuuint64_t)total_rows };
+    const cuuint64_t gstride[1] = { (cuuint64_t)L * sizeof(T) };
+    const cuuint32_t box[2] = { (cuuint32_t)TSB, (cuuint32_t)RG };
+    const cuuint32_t estr[2] = { 1, 1 };
+    CUresult r = get_encode_fn()(&map, sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, data, gdim,
+                                 gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return set_error(SDSP_B200_ERR_CUDA, "iir scan: cuTensorMapEncodeTiled failed with %d", (int)r);
+
+    auto kern = iir_scan_kernel<T, M, KIND, L, WARPS, RG>;
+    constexpr size_t smem = (size_t)WARPS * (L / TSB) * 32 * 128;
+    static bool configured = false;
+    static int occ = 1;
+    if (!configured) {
+        SDSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SDSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WARPS * 32, smem));
+        if (occ < 1)
+            occ = 1;
+        configured = true;
+    }
+    const size_t total_tiles = b.n_channels * n_tiles;
+    size_t grid = (size_t)b.sm_count * occ;
+    if (grid * WARPS > total_tiles)
+        grid = (total_tiles + WARPS - 1) / WARPS;
+    kern<<<(unsigned)grid, WARPS * 32, smem, stream>>>(map, static_cast<const T *>(b.d_coef), static_cast<T *>(b.d_state), b.n_channels,
+                                                      static_cast<const T *>(b.d_scan_tables),
+                                                      reinterpret_cast<const int *>(static_cast<char *>(b.d_scan_tables) +
+                                                                                    (size_t)b.n_channels * TAB * sizeof(T)),
+                                                      recs, ticket, b.scan_epoch, (unsigned)n_tiles, (unsigned)rows_per_channel);
+    SDSP_CUDA(cudaGetLastError());
+    *done = n_tiles * tile;
+    return SDSP_B200_OK;
+}
+
+template <typename T, int M>
+static int launch_scan_kind(IirBank &b, void *data, size_t n, size_t stride, cudaStream_t s, size_t *done)
+{
+    switch (b.numerator) {
+    case NUM_GENERIC: return launch_scan<T, M, NUM_GENERIC>(b, data, n, stride, s, done);
+    case NUM_LP: return launch_scan<T, M, NUM_LP>(b, data, n, stride, s, done);
+    case NUM_HP: return launch_scan<T, M, NUM_HP>(b, data, n, stride, s, done);
+    default: return launch_scan<T, M, NUM_BP>(b, data, n, stride, s, done);
+    }
+}
+
+template <typename T>
+static int launch_scan_sections(IirBank &b, void *data, size_t n, size_t stride, cudaStream_t s, size_t *done)
+{
+    switch (b.sections) {
+    case 2: return launch_scan_kind<T, 2>(b, data, n, stride, s, done);
+    case 4: return launch_scan_kind<T, 4>(b, data, n, stride, s, done);
+    case 6: return launch_scan_kind<T, 6>(b, data, n, stride, s, done);
+    case 8: return launch_scan_kind<T, 8>(b, data, n, stride, s, done);
+    default: return set_error(SDSP_B200_ERR_UNSUPPORTED, "iir scan path: sections=%d not built (2, 4, 6, 8)", b.sections);
+    }
+}
+
+int iir_scan_chunk(int precision)
+{
+    return precision == SDSP_B200_F32 ? ScanChunk<float>::L : ScanChunk<double>::L;
+}
+
+// whole tiles through the scan kernel, the ragged remainder through the sequential kernel (which picks the
+// bank history up where the scan left it)
+int iir_launch_scan(IirBank &b, void *data, size_t n_samples, size_t stride, cudaStream_t stream)
+{
+    const size_t es = b.precision == SDSP_B200_F32 ? 4 : 8;
+    const int L = iir_scan_chunk(b.precision);
+    if (reinterpret_cast<uintptr_t>(data) % 16 != 0 || (b.n_channels > 1 && stride % L != 0) || !get_encode_fn())
+        return set_error(SDSP_B200_ERR_UNSUPPORTED,
+                         "iir scan path needs a 16-byte aligned base and (for several channels) a channel stride that is a multiple of %d samples", L);
+    size_t done = 0;
+    int rc = b.precision == SDSP_B200_F32 ? launch_scan_sections<float>(b, data, n_samples, stride, stream, &done) :
+                                            launch_scan_sections<double>(b, data, n_samples, stride, stream, &done);
+    if (rc)
+        return rc;
+    if (done < n_samples)
+        rc = iir_launch_sequential(b, static_cast<char *>(data) + done * es, n_samples - done, stride, stream);
+    return rc;
 }
 } // namespace sdsp_b200
 

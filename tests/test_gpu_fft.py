@@ -47,11 +47,13 @@ def test_digit_reverse_permute_matches_swap_sweep(n, base):
 
 # ------------------------------------------------------------------ parity against the oracle
 @pytest.mark.parametrize("prec", ["f64", "f32"])
-@pytest.mark.parametrize("lg", range(1, 15))
+@pytest.mark.parametrize("lg", range(1, 19))
 def test_fft_matches_oracle_all_sizes(lg, prec):
+    """Single-CTA kernels up to 2^14 (f32) / 2^13 (f64); above that the multi-pass path (n = n1 x 256
+    through an L2-resident scratch), up to 2^18 (f32) / 2^17 (f64)."""
     n = 1 << lg
-    if prec == "f64" and lg > 13:
-        pytest.skip("f64 16384 needs the multi-pass path")
+    if prec == "f64" and lg > 17:
+        pytest.skip("f64 2^18 is beyond the multi-pass path")
     code, dt = PREC[prec]
     rng = np.random.default_rng(100 + lg)
     frames = 7 if n <= 4096 else 3
@@ -156,3 +158,28 @@ def test_device_f64_batch_linearity():
     assert float(err.max()) <= FFT_TOL["f64"]
     ref = oracle_fft(a[:4].cpu().numpy())
     assert rel_l2(plan(a[:4].clone()).cpu().numpy(), ref) <= FFT_TOL["f64"]
+
+
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+def test_large_frames_many_frames_and_unsupported_sizes(prec):
+    """BASELINE config 5's transform size (65536) over more frames than one scratch slab holds."""
+    torch = pytest.importorskip("torch")
+    code, dt = PREC[prec]
+    n, frames = 65536, 150 if prec == "f32" else 70
+    g = torch.Generator(device="cuda").manual_seed(9)
+    x = torch.view_as_complex(torch.randn(frames, n, 2, device="cuda", generator=g, dtype=torch.float32 if prec == "f32" else torch.float64))
+    fwd, inv = S.FftPlan(n, 4, code, K.FORWARD), S.FftPlan(n, 4, code, K.REVERSE)
+    assert "multi-pass" in fwd.describe() and fwd.launches(frames) >= 4
+    y = x.clone()
+    fwd(y)
+    torch.cuda.synchronize()
+    idx = [0, 1, frames // 2, frames - 1]
+    ref = oracle_fft(x[idx].cpu().numpy())
+    assert rel_l2(y[idx].cpu().numpy(), ref) <= FFT_TOL[prec]
+    inv(y)
+    torch.cuda.synchronize()
+    err = (y - x).abs().pow(2).sum(dim=1).sqrt() / x.abs().pow(2).sum(dim=1).sqrt()
+    assert float(err.max()) <= 2 * FFT_TOL[prec]
+    with pytest.raises(S.SdspError) as e:
+        S.FftPlan(1 << 20, 2, code, K.FORWARD)
+    assert e.value.status == K.ERR_UNSUPPORTED

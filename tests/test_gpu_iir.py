@@ -174,3 +174,71 @@ def test_tma_and_generic_kernels_agree_bit_for_bit(prec):
     assert np.array_equal(st_tma, bank.get_state())
     assert peak_rel(y_tma, ref) <= IIR_TOL[prec]
     assert float(a[:, n:].abs().max()) == 0.0 and float(wide[n_channels * stride:].abs().max()) == 0.0  # nothing outside the ranges written
+
+
+# ------------------------------------------------------------------ the time-parallel (scan) path
+def _scan_reference(ftype, f0, fs, x, sections=4):
+    f = O.Iir(sections)
+    f.design(ftype, f0, fs, 1.1)
+    return f, f.process(x)
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("case", [(1, 10e3, 100e3), (2, 10e3, 100e3), (3, 2000.0, 39e3), (1, 200.0, 39e3)])
+def test_scan_single_long_channel_matches_sequential_reference(case, prec):
+    """BASELINE config 4 in miniature: one channel, time axis split over the whole GPU."""
+    ftype, f0, fs = case
+    code, dt = PREC[prec]
+    chunk = 128 if prec == "f64" else 256
+    n = 32 * chunk * 37 + 333  # 37 whole tiles + a ragged tail (sequential kernel)
+    rng = np.random.default_rng(int(f0) + ftype)
+    x = f32_noise(rng, n)
+    f, ref = _scan_reference(ftype, f0, fs, x)
+    g, b, a = S.design(ftype, 4, f0, fs, 1.1)
+    bank = S.IirBank(4, 1, code)
+    bank.set_coeffs([g], [b], [a])
+    y = bank.process(x.astype(dt), path=K.IIR_SCAN)
+    tol = 3 * IIR_TOL[prec] if (prec == "f32" and f0 < 1e3) else IIR_TOL[prec]  # SURVEY H3, as in the CPU test
+    assert peak_rel(y, ref) <= tol
+    # the history left behind continues the stream exactly where the scan stopped
+    nxt = f32_noise(rng, 1000)
+    want = f.process(nxt)
+    got = bank.process(nxt.astype(dt), path=K.IIR_SEQUENTIAL)
+    assert peak_rel(got, want) <= 10 * tol
+    # and a second scan call on the same bank (non-zero incoming history) too
+    more = f32_noise(rng, 32 * chunk * 3)
+    want2 = f.process(more)
+    got2 = bank.process(more.astype(dt), path=K.IIR_SCAN)
+    assert peak_rel(got2, want2) <= 10 * tol
+
+
+def test_scan_general_carry_path_for_long_memory_filters():
+    """f0/fs = 2e-4: the tile-to-tile propagation matrix does not vanish within the look-back window, so
+    tiles wait for their predecessor's inclusive state.  Correctness only (this path is slow by design).
+    fp64 error is ~1e-9 of peak here because such a filter amplifies any rounding by ~1e6."""
+    n = 32 * 128 * 24
+    rng = np.random.default_rng(20)
+    x = f32_noise(rng, n)
+    f, ref = _scan_reference(1, 20.0, 100e3, x)
+    g, b, a = S.design(1, 4, 20.0, 100e3)
+    bank = S.IirBank(4, 1, K.F64)
+    bank.set_coeffs([g], [b], [a])
+    y = bank.process(x.copy(), path=K.IIR_SCAN)
+    assert peak_rel(y, ref) <= 1e-8
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_scan_few_channels_each_split_along_time(prec):
+    torch = pytest.importorskip("torch")
+    code, dt = PREC[prec]
+    chunk = 128 if prec == "f64" else 256
+    n_channels, n = 6, 32 * chunk * 5 + 100
+    stride = 32 * chunk * 6
+    bank, x, ref = _bank_case(n_channels, n, prec, seed=77)
+    tdt = torch.float32 if prec == "f32" else torch.float64
+    wide = torch.zeros(n_channels, stride, device="cuda", dtype=tdt)
+    wide[:, :n] = torch.from_numpy(x).cuda()
+    bank.process_ptr(wide.data_ptr(), n, stride, K.PTR_DEVICE, K.IIR_SCAN, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert peak_rel(wide[:, :n].cpu().numpy(), ref) <= IIR_TOL[prec]
+    assert float(wide[:, n:].abs().max()) == 0.0
