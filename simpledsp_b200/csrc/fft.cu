@@ -5,6 +5,7 @@
 // frames resident in HBM.  See fft_core.cuh for the factorisation and DESIGN.md for the roofline.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -92,29 +93,36 @@ __device__ __forceinline__ void st_stream(cplx<T> *p, cplx<T> v)
     *p = v;
 }
 
-template <class Cfg, typename T, int THREADS, int MINB, int P>
-__device__ __forceinline__ void fft_kernel_passes(cplx<T> (&v)[Cfg::E], cplx<T> *fs, const cplx<T> *__restrict__ tw, int t)
+// DB = false: one exchange buffer, a barrier after every write and after every read that is followed by a
+//   write (four per 3-pass frame).
+// DB = true: two buffers used alternately; a pass reads one and writes the other, so only the barrier after
+//   each write remains (two per 3-pass frame).  fs1 = second buffer.
+template <class Cfg, typename T, int THREADS, int MINB, int P, bool DB = false>
+__device__ __forceinline__ void fft_kernel_passes(cplx<T> (&v)[Cfg::E], cplx<T> *fs, const cplx<T> *__restrict__ tw, int t,
+                                                  cplx<T> *fs1 = nullptr)
 {
     if constexpr (P < Cfg::NPASS) {
+        cplx<T> *rd = (DB && (P % 2 == 0)) ? fs1 : fs; // pass P reads what pass P-1 wrote
+        cplx<T> *wr = (DB && (P % 2 == 1)) ? fs1 : fs;
         if constexpr (P > 0) {
 #pragma unroll
             for (int e = 0; e < Cfg::E; e++)
-                v[e] = fs[Cfg::pad(t + Cfg::S * e)];
-            if constexpr (P + 1 < Cfg::NPASS)
+                v[e] = rd[fft_read_phys<Cfg>(t, e)];
+            if constexpr (P + 1 < Cfg::NPASS && !DB)
                 __syncthreads(); // everyone has read before this pass overwrites the exchange buffer
         }
         fft_pass<Cfg, P, T>(v, t, tw);
         if constexpr (P + 1 < Cfg::NPASS) {
 #pragma unroll
             for (int e = 0; e < Cfg::E; e++)
-                fs[Cfg::pad(fft_out_pos<Cfg, P>(t, e))] = v[e];
+                wr[fft_out_phys<Cfg, P>(t, e)] = v[e];
             __syncthreads();
-            fft_kernel_passes<Cfg, T, THREADS, MINB, P + 1>(v, fs, tw, t);
+            fft_kernel_passes<Cfg, T, THREADS, MINB, P + 1, DB>(v, fs, tw, t, fs1);
         }
     }
 }
 
-template <class Cfg, typename T, int THREADS, int MINB>
+template <class Cfg, typename T, int THREADS, int MINB, bool DB = false>
 __global__ void __launch_bounds__(THREADS, MINB)
     fft_cta_kernel(cplx<T> *__restrict__ data, const cplx<T> *__restrict__ tw, size_t n_frames, int inverse, T scale)
 {
@@ -125,6 +133,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
     const int fl = threadIdx.x / Cfg::TPF;
     const int t = threadIdx.x % Cfg::TPF;
     cplx<T> *fs = smem + (size_t)fl * Cfg::PADDED_N;
+    cplx<T> *fs1 = fs + (size_t)FPC * Cfg::PADDED_N; // second exchange buffer (DB only)
     const size_t groups = (n_frames + FPC - 1) / FPC;
 
     for (size_t g = blockIdx.x; g < groups; g += gridDim.x) {
@@ -146,7 +155,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
             for (int e = 0; e < Cfg::E; e++)
                 v[e] = cplx<T>{ v[e].y, v[e].x };
         }
-        fft_kernel_passes<Cfg, T, THREADS, MINB, 0>(v, fs, tw, t);
+        fft_kernel_passes<Cfg, T, THREADS, MINB, 0, DB>(v, fs, tw, t, fs1);
         if (inverse) {
 #pragma unroll
             for (int e = 0; e < Cfg::E; e++)
@@ -157,8 +166,12 @@ __global__ void __launch_bounds__(THREADS, MINB)
             for (int e = 0; e < Cfg::E; e++)
                 st_stream(gp + Cfg::S * e, v[e]);
         }
-        if constexpr (Cfg::NPASS > 1)
-            __syncthreads(); // last pass has read the exchange buffer before the next group writes it
+        // single buffer: the last pass has read the exchange buffer before the next group writes it.  With two
+        // buffers the barriers inside the next frame already order every reuse (a buffer is rewritten only after a
+        // barrier that all readers of its previous contents have passed), except when one buffer serves both the
+        // first write and the last read (even number of exchanges)
+        if constexpr (Cfg::NPASS > 1 && (!DB || (Cfg::NPASS - 1) % 2 == 1))
+            __syncthreads();
     }
 }
 
@@ -217,6 +230,7 @@ struct FftPlan {
     int npass = 0, radices[4] = { 1, 1, 1, 1 }, e = 0, threads = 0, frames_per_cta = 0, min_blocks = 0;
     size_t smem_bytes = 0;
     int ctas_per_sm = 0, sm_count = 0;
+    bool double_buffered = false;
     void *d_tw = nullptr;
     size_t tw_bytes = 0;
     fft_launch_fn launch = nullptr;
@@ -234,7 +248,7 @@ struct FftPlan {
     std::mutex mu;
 };
 
-template <class Cfg, typename T, int THREADS, int MINB>
+template <class Cfg, typename T, int THREADS, int MINB, bool DB>
 static int launch_cta(const FftPlan &p, void *data, size_t n_frames, cudaStream_t stream)
 {
     constexpr int FPC = THREADS / Cfg::TPF;
@@ -245,14 +259,14 @@ static int launch_cta(const FftPlan &p, void *data, size_t n_frames, cudaStream_
     // persistent-style grid: a whole number of waves, each CTA strides over frame groups
     size_t grid = groups < resident * 4 ? groups : resident * 4;
     const T scale = (T)(1.0 / (double)Cfg::N);
-    fft_cta_kernel<Cfg, T, THREADS, MINB><<<(unsigned)grid, THREADS, p.smem_bytes, stream>>>(
+    fft_cta_kernel<Cfg, T, THREADS, MINB, DB><<<(unsigned)grid, THREADS, p.smem_bytes, stream>>>(
         reinterpret_cast<cplx<T> *>(data), reinterpret_cast<const cplx<T> *>(p.d_tw), n_frames,
         p.direction == SDSP_B200_REVERSE ? 1 : 0, scale);
     SDSP_CUDA(cudaGetLastError());
     return SDSP_B200_OK;
 }
 
-template <class Cfg, typename T, int THREADS, int MINB>
+template <class Cfg, typename T, int THREADS, int MINB, bool DB = false>
 static int setup_cta(FftPlan &p)
 {
     constexpr int FPC = THREADS / Cfg::TPF;
@@ -265,8 +279,9 @@ static int setup_cta(FftPlan &p)
     p.threads = THREADS;
     p.frames_per_cta = FPC;
     p.min_blocks = MINB;
-    p.smem_bytes = Cfg::NPASS > 1 ? (size_t)FPC * Cfg::PADDED_N * sizeof(cplx<T>) : 0;
-    auto kern = fft_cta_kernel<Cfg, T, THREADS, MINB>;
+    p.smem_bytes = Cfg::NPASS > 1 ? (size_t)FPC * Cfg::PADDED_N * sizeof(cplx<T>) * (DB ? 2 : 1) : 0;
+    p.double_buffered = DB;
+    auto kern = fft_cta_kernel<Cfg, T, THREADS, MINB, DB>;
     if (p.smem_bytes > 48 * 1024)
         SDSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
     int occ = 0;
@@ -274,7 +289,7 @@ static int setup_cta(FftPlan &p)
     if (occ < 1)
         return set_error(SDSP_B200_ERR_UNSUPPORTED, "fft kernel for n=%u does not fit on an SM", p.n);
     p.ctas_per_sm = occ;
-    p.launch = &launch_cta<Cfg, T, THREADS, MINB>;
+    p.launch = &launch_cta<Cfg, T, THREADS, MINB, DB>;
     std::vector<cplx<T>> tw;
     build_twiddles<T>(Cfg::N, p.radices, Cfg::NPASS, tw);
     p.tw_bytes = tw.size() * sizeof(cplx<T>);
@@ -540,6 +555,30 @@ template <int LG>
 static int setup_for(FftPlan &p)
 {
     using C = CfgFor<LG>;
+    if constexpr (LG == 12) { // SDSP_B200_FFT_TUNE: kernel-tuning aid for the headline size
+        static int tune = -1;
+        if (tune < 0) {
+            const char *e = getenv("SDSP_B200_FFT_TUNE");
+            tune = e ? atoi(e) : 0;
+        }
+        if (p.precision == SDSP_B200_F32) {
+            if (tune == 1)
+                return setup_cta<typename C::type, float, C::THREADS, 3, true>(p);
+            if (tune == 2)
+                return setup_cta<typename C::type, float, C::THREADS, 4, false>(p);
+            if (tune == 3)
+                return setup_cta<typename C::type, float, C::THREADS, 4, true>(p);
+            if (tune == 4)
+                return setup_cta<typename C::type, float, C::THREADS, 2, true>(p);
+        } else {
+            if (tune == 1)
+                return setup_cta<typename C::type, double, C::THREADS, 2, true>(p);
+            if (tune == 2)
+                return setup_cta<typename C::type, double, C::THREADS, 3, false>(p);
+            if (tune == 3)
+                return setup_cta<typename C::type, double, C::THREADS, 1, true>(p);
+        }
+    }
     if (p.precision == SDSP_B200_F32)
         return setup_cta<typename C::type, float, C::THREADS, C::MINB>(p);
     if constexpr (LG <= MAX_LOG2N_F64)
@@ -746,10 +785,10 @@ int sdsp_b200_fft_plan_describe(sdsp_b200_fft_plan plan, char *buf, size_t buf_l
     }
     snprintf(buf, buf_len,
              "fft n=%u %s %s radix-arg=%d: single-CTA kernel, passes=%d radices=[%d,%d,%d,%d] points/thread=%d "
-             "threads/CTA=%d frames/CTA=%d smem/CTA=%zuB CTAs/SM=%d SMs=%d twiddle-table=%zuB",
+             "threads/CTA=%d frames/CTA=%d smem/CTA=%zuB%s CTAs/SM=%d SMs=%d twiddle-table=%zuB",
              p.n, p.precision == SDSP_B200_F32 ? "f32" : "f64", p.direction == SDSP_B200_FORWARD ? "forward" : "reverse", p.radix,
              p.npass, p.radices[0], p.radices[1], p.radices[2], p.radices[3], p.e, p.threads, p.frames_per_cta, p.smem_bytes,
-             p.ctas_per_sm, p.sm_count, p.tw_bytes);
+             p.double_buffered ? " (double-buffered exchange)" : "", p.ctas_per_sm, p.sm_count, p.tw_bytes);
     return SDSP_B200_OK;
 }
 

@@ -61,9 +61,27 @@ SDSP_HD T iir_numpart(T in1, T in2, T b1, T b2) // b1*in1 + b2*in2
         return fma_t((T)-2, in1, in2);
     return -in2; // NUM_BP {1, 0, -1}
 }
-template <int KIND, typename T>
-SDSP_HD T iir_section(T in0, T in1, T in2, T v1, T v2, T b1, T b2, T na1, T na2)
+// fp64: four fused multiply-adds in the obvious order (accuracy is not at stake there -- 7e-15 absolute on the
+// golden fixtures -- and the FP64 pipe is what bounds the fp64 kernels, so the operation count matters)
+template <int KIND>
+SDSP_HD double iir_section(double in0, double in1, double in2, double v1, double v2, double b1, double b2, double na1, double na2)
 {
+    double acc;
+    if (KIND == NUM_GENERIC)
+        acc = fma_t(b2, in2, fma_t(b1, in1, in0));
+    else if (KIND == NUM_LP)
+        acc = fma_t(2.0, in1, in0) + in2;
+    else if (KIND == NUM_HP)
+        acc = fma_t(-2.0, in1, in0) + in2;
+    else
+        acc = in0 - in2;
+    return fma_t(na1, v1, fma_t(na2, v2, acc));
+}
+// fp32: SDSP_IIR_ORDER
+template <int KIND>
+SDSP_HD float iir_section(float in0, float in1, float in2, float v1, float v2, float b1, float b2, float na1, float na2)
+{
+    using T = float;
 #if SDSP_IIR_ORDER == 'A' // numerator chain from in0, then both feedback terms
     T acc;
     if (KIND == NUM_GENERIC)
@@ -100,7 +118,7 @@ SDSP_HD T iir_step(T x, const IirCoef<T, M> &c, IirState<T, M> &s)
 #endif
     for (int j = 0; j < M; j++) {
         const T v1 = s.h[j + 1][0], v2 = s.h[j + 1][1];
-        const T v = iir_section<KIND, T>(in0, in1, in2, v1, v2, c.b1[j], c.b2[j], c.na1[j], c.na2[j]);
+        const T v = iir_section<KIND>(in0, in1, in2, v1, v2, c.b1[j], c.b2[j], c.na1[j], c.na2[j]);
         s.h[j + 1][1] = v1;
         s.h[j + 1][0] = v;
         in0 = v;
@@ -142,7 +160,7 @@ SDSP_HD void iir_tile_skewed(const IirCoef<T, M> &c, IirState<T, M> &s, Load &&l
             const int smp = i - j;
             if (smp >= 0 && smp < TS) {
                 const T in0 = (j == 0) ? load(smp) * c.gain : pipe[j];
-                const T v = iir_section<KIND, T>(in0, inh[j][0], inh[j][1], vh[j][0], vh[j][1], c.b1[j], c.b2[j], c.na1[j], c.na2[j]);
+                const T v = iir_section<KIND>(in0, inh[j][0], inh[j][1], vh[j][0], vh[j][1], c.b1[j], c.b2[j], c.na1[j], c.na2[j]);
                 inh[j][1] = inh[j][0];
                 inh[j][0] = in0;
                 vh[j][1] = vh[j][0];
@@ -301,13 +319,13 @@ SDSP_HD void iir_tile_skewed_x2(const IirCoef<float, M> &c, IirState<float, M> &
                 if (p == P - 1)
                     store(shi, v.y);
             } else if (lo_on) { // ramp-up: only the low section of the pair has a sample
-                const float v = iir_section<KIND, float>(in0.x, inh0[p].x, inh1[p].x, vh0[p].x, vh1[p].x, b1[p].x, b2[p].x, na1[p].x, na2[p].x);
+                const float v = iir_section<KIND>(in0.x, inh0[p].x, inh1[p].x, vh0[p].x, vh1[p].x, b1[p].x, b2[p].x, na1[p].x, na2[p].x);
                 inh1[p].x = inh0[p].x;
                 inh0[p].x = in0.x;
                 vh1[p].x = vh0[p].x;
                 vh0[p].x = v;
             } else { // ramp-down: only the high section still has samples
-                const float v = iir_section<KIND, float>(in0.y, inh0[p].y, inh1[p].y, vh0[p].y, vh1[p].y, b1[p].y, b2[p].y, na1[p].y, na2[p].y);
+                const float v = iir_section<KIND>(in0.y, inh0[p].y, inh1[p].y, vh0[p].y, vh1[p].y, b1[p].y, b2[p].y, na1[p].y, na2[p].y);
                 inh1[p].y = inh0[p].y;
                 inh0[p].y = in0.y;
                 vh1[p].y = vh0[p].y;

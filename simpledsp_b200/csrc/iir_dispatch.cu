@@ -51,7 +51,9 @@ void iir_bank_release_aux(IirBank &b)
         cudaFree(b.d_scan_tables);
     if (b.d_scan_flags)
         cudaFree(b.d_scan_flags);
-    b.d_scan_tables = b.d_scan_flags = nullptr;
+    if (b.d_state_alt)
+        cudaFree(b.d_state_alt);
+    b.d_scan_tables = b.d_scan_flags = b.d_state_alt = nullptr;
 }
 } // namespace sdsp_b200
 

@@ -14,6 +14,7 @@ struct IirBank {
     size_t n_channels = 0;
     void *d_coef = nullptr;  // [1 + 4m][n_channels]   gain, b1[m], b2[m], -a1[m], -a2[m]
     void *d_state = nullptr; // [2(m + 1)][n_channels] row r: x[n-1], x[n-2]
+    void *d_state_alt = nullptr; // scan path: the launch reads d_state and writes here, then the two are swapped
     // host copy of the coefficients in double (scan tables are derived from it)
     std::vector<double> h_gain, h_b, h_a;
     unsigned long coef_version = 0;
@@ -23,6 +24,7 @@ struct IirBank {
     unsigned long scan_tables_version = ~0ul;
     int scan_chunk = 0;
     int scan_reach_max = 0;
+    int scan_chunk_request = 0;
     unsigned scan_epoch = 0;
     void *d_scan_flags = nullptr;
     size_t scan_flags_bytes = 0;

@@ -1,6 +1,8 @@
 // iir_scan.cu -- the time-parallel IIR path (chunked state-space scan), see iir_scan_core.cuh.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <utility>
 #include <vector>
 
 #include <cuda.h>
@@ -26,7 +28,7 @@ static int emulate_scan(double gain, const double *b, const double *a, double *m
     }
     std::vector<double> tab;
     int reach = 0;
-    if (scan_build_tables(M, KIND, gain, b, a, L, tab, reach) != 0)
+    if (scan_build_tables(M, KIND, gain, b, a, L, scan_negligible<T>(), tab, reach) != 0)
         return set_error(SDSP_B200_ERR_UNSUPPORTED, "scan: sections=%d not built", M);
     T *d = static_cast<T *>(data);
     const size_t done = scan_emulate_channel<T, M, KIND>(c, s, tab, reach, L, d, n, force_general);
@@ -79,6 +81,12 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p)
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v)
 {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -87,8 +95,9 @@ __device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v)
 __device__ __forceinline__ void warp_wait_flag(const unsigned *flag, unsigned epoch, int lane)
 {
     if (lane == 0) {
-        while (ld_acquire_u32(flag) != epoch)
+        while (ld_relaxed_u32(flag) != epoch)
             __nanosleep(20);
+        (void)ld_acquire_u32(flag); // one acquire after the flag has been seen (orders the data reads below)
     }
     __syncwarp();
 }
@@ -99,9 +108,11 @@ __device__ __forceinline__ T ld_cg(const T *p)
 }
 
 // L samples per lane, 32 lanes per tile, WARPS independent warps per CTA, RG rows per TMA box
-template <typename T, int M, int KIND, int L, int WARPS, int RG>
+// ONE_CH: the bank has a single channel, so one copy of its tables serves the whole CTA (more warps fit).
+template <typename T, int M, int KIND, int L, int WARPS, int RG, bool ONE_CH>
 __global__ void __launch_bounds__(WARPS * 32)
-    iir_scan_kernel(const __grid_constant__ CUtensorMap map, const T *__restrict__ coef, T *__restrict__ state, size_t n_channels,
+    iir_scan_kernel(const __grid_constant__ CUtensorMap map, const T *__restrict__ coef, const T *__restrict__ state, T *__restrict__ state_out,
+                    size_t n_channels,
                     const T *__restrict__ tables, const int *__restrict__ reach_of, ScanRec<T, 2 * M> *__restrict__ recs,
                     unsigned *__restrict__ ticket, unsigned epoch, unsigned n_tiles, unsigned rows_per_channel)
 {
@@ -116,10 +127,20 @@ __global__ void __launch_bounds__(WARPS * 32)
     constexpr int TAB = scan_table_count(M, L);
     using V = typename Vec16<T>::type;
 
+    constexpr int TABLE_BYTES = (TAB * (int)sizeof(T) + 15) / 16 * 16;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ uint64_t bars[WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char *buf = smem_raw + (size_t)warp * TILE_BYTES;
+    // this warp's copy of its channel's tables (H then the six matrices), refilled when the channel changes
+    T *tab = reinterpret_cast<T *>(smem_raw + (size_t)WARPS * TILE_BYTES + (size_t)(ONE_CH ? 0 : warp) * TABLE_BYTES);
+    unsigned tab_ch = 0xffffffffu;
+    IirCoef<T, M> c;
+    c.gain = 0;
+#pragma unroll
+    for (int j = 0; j < M; j++)
+        c.b1[j] = c.b2[j] = c.na1[j] = c.na2[j] = 0;
+    int reach = 0;
     uint64_t *bar = &bars[warp];
     if (lane == 0) {
         mbar_init(bar, 1);
@@ -133,6 +154,31 @@ __global__ void __launch_bounds__(WARPS * 32)
         const int box = i / TSB, chunk = (i % TSB) / VN, e = i % VN;
         return reinterpret_cast<T *>(buf + box * BOX_BYTES + row * 128 + ((((uint32_t)chunk) ^ (uint32_t)(row & 7)) << 4)) + e;
     };
+    // coefficients into registers, tables into shared memory.  H is re-laid for the correction loop: fp32 keeps
+    // sample pairs together, [i/2][k][2], so that one 16-byte load feeds two FFMA2; fp64 stays [i][k]
+    auto load_channel = [&](unsigned ch, int first, int step) {
+        c.gain = coef[ch];
+#pragma unroll
+        for (int j = 0; j < M; j++) {
+            c.b1[j] = coef[(size_t)(1 + j) * n_channels + ch];
+            c.b2[j] = coef[(size_t)(1 + M + j) * n_channels + ch];
+            c.na1[j] = coef[(size_t)(1 + 2 * M + j) * n_channels + ch];
+            c.na2[j] = coef[(size_t)(1 + 3 * M + j) * n_channels + ch];
+        }
+        reach = reach_of[ch];
+        const T *src = tables + (size_t)ch * TAB;
+        for (int idx = first; idx < L * SD; idx += step) {
+            const int i = idx / SD, k = idx % SD;
+            const int dst = sizeof(T) == 4 ? (((i >> 1) * SD + k) * 2 + (i & 1)) : idx;
+            tab[dst] = __ldg(src + idx);
+        }
+        for (int idx = L * SD + first; idx < TAB; idx += step)
+            tab[idx] = __ldg(src + idx);
+    };
+    if (ONE_CH) {
+        load_channel(0, threadIdx.x, WARPS * 32);
+        __syncthreads();
+    }
     const unsigned total = (unsigned)n_channels * n_tiles;
     unsigned phase = 0;
 
@@ -153,18 +199,11 @@ __global__ void __launch_bounds__(WARPS * 32)
                 for (int u = 0; u < NBOX; u++)
                     tma_load_2d(buf + u * BOX_BYTES + g * RG * 128, &map, u * TSB, row0 + g * RG, bar);
         }
-        // while the tile is in flight: this channel's coefficients (the same for every lane)
-        IirCoef<T, M> c;
-        c.gain = coef[ch];
-#pragma unroll
-        for (int j = 0; j < M; j++) {
-            c.b1[j] = coef[(size_t)(1 + j) * n_channels + ch];
-            c.b2[j] = coef[(size_t)(1 + M + j) * n_channels + ch];
-            c.na1[j] = coef[(size_t)(1 + 2 * M + j) * n_channels + ch];
-            c.na2[j] = coef[(size_t)(1 + 3 * M + j) * n_channels + ch];
+        if (!ONE_CH && ch != tab_ch) { // while the tile is in flight: this channel's coefficients and tables
+            load_channel(ch, lane, 32);
+            tab_ch = ch;
+            __syncwarp();
         }
-        const T *tab = tables + (size_t)ch * TAB;
-        const int reach = reach_of[ch];
         ScanRec<T, SD> *rec = recs + (size_t)ch * n_tiles + t;
 
         mbar_wait(bar, phase);
@@ -183,7 +222,6 @@ __global__ void __launch_bounds__(WARPS * 32)
         if (lane == 31) {
             rec->uh[0] = out_u1;
             rec->uh[1] = out_u2;
-            __threadfence();
             st_release_u32(&rec->flag_x, epoch);
         }
         if (t == 0) {
@@ -247,7 +285,6 @@ __global__ void __launch_bounds__(WARPS * 32)
 #pragma unroll
             for (int k = 0; k < SD; k++)
                 rec->agg[k] = agg[k];
-            __threadfence();
             st_release_u32(&rec->flag_a, epoch);
         }
 
@@ -287,17 +324,19 @@ __global__ void __launch_bounds__(WARPS * 32)
             incl[k] = agg[k];
         tri_matvec_acc<T, SD>(Mt, cin, incl);
         if (lane == 31) {
-#pragma unroll
-            for (int k = 0; k < SD; k++)
-                rec->incl[k] = incl[k];
-            __threadfence();
-            st_release_u32(&rec->flag_i, epoch);
-            if (t + 1 == n_tiles) { // the bank's history after the last whole tile
-                state[(size_t)0 * n_channels + ch] = out_u1;
-                state[(size_t)1 * n_channels + ch] = out_u2;
+            if (reach > SCAN_MAX_REACH) { // only the wait-for-predecessor path reads inclusive states
 #pragma unroll
                 for (int k = 0; k < SD; k++)
-                    state[(size_t)(2 + k) * n_channels + ch] = incl[k];
+                    rec->incl[k] = incl[k];
+                st_release_u32(&rec->flag_i, epoch);
+            }
+            if (t + 1 == n_tiles) { // the bank's history after the last whole tile.  It goes to a second buffer: the
+                                    // first tiles of this launch may not have read the incoming history yet
+                state_out[(size_t)0 * n_channels + ch] = out_u1;
+                state_out[(size_t)1 * n_channels + ch] = out_u2;
+#pragma unroll
+                for (int k = 0; k < SD; k++)
+                    state_out[(size_t)(2 + k) * n_channels + ch] = incl[k];
             }
         }
 
@@ -323,22 +362,48 @@ __global__ void __launch_bounds__(WARPS * 32)
         for (int k = 0; k < SD; k++)
             ci[k] += Pprev[k];
 
-        // ---- natural-response correction of this lane's chunk
-#pragma unroll 4
-        for (int q = 0; q < L / VN; q++) {
-            const int box = (q * VN) / TSB, chunk = ((q * VN) % TSB) / VN;
-            V *p = reinterpret_cast<V *>(buf + box * BOX_BYTES + row_off + (((uint32_t)chunk ^ sw) << 4));
-            V v = *p;
+        // ---- natural-response correction of this lane's chunk: y[i] += sum_k H[i][k] ci[k]
+        if constexpr (sizeof(T) == 4) {
+            f32x2 cib[SD];
 #pragma unroll
-            for (int e = 0; e < VN; e++) {
-                T y = vget(v, e);
-                const T *h = tab + (size_t)(q * VN + e) * SD;
+            for (int k = 0; k < SD; k++)
+                cib[k] = mk2(ci[k], ci[k]);
+#pragma unroll 2
+            for (int q = 0; q < L / 4; q++) {
+                const int box = (q * 4) / TSB, chunk = ((q * 4) % TSB) / 4;
+                float4 *p = reinterpret_cast<float4 *>(buf + box * BOX_BYTES + row_off + (((uint32_t)chunk ^ sw) << 4));
+                float4 v = *p;
+                f32x2 y01 = mk2(v.x, v.y), y23 = mk2(v.z, v.w);
+                const float4 *h01 = reinterpret_cast<const float4 *>(tab + (size_t)(2 * q) * SD * 2);
+                const float4 *h23 = h01 + SD / 2;
 #pragma unroll
-                for (int k = 0; k < SD; k++)
-                    y = fma_t(__ldg(h + k), ci[k], y);
-                vset(v, e, y);
+                for (int kk = 0; kk < SD / 2; kk++) {
+                    const float4 ha = h01[kk], hb = h23[kk];
+                    y01 = fma2(mk2(ha.x, ha.y), cib[2 * kk], y01);
+                    y23 = fma2(mk2(hb.x, hb.y), cib[2 * kk], y23);
+                    y01 = fma2(mk2(ha.z, ha.w), cib[2 * kk + 1], y01);
+                    y23 = fma2(mk2(hb.z, hb.w), cib[2 * kk + 1], y23);
+                }
+                *p = make_float4(y01.x, y01.y, y23.x, y23.y);
             }
-            *p = v;
+        } else {
+#pragma unroll 4
+            for (int q = 0; q < L / 2; q++) {
+                const int box = (q * 2) / TSB, chunk = ((q * 2) % TSB) / 2;
+                double2 *p = reinterpret_cast<double2 *>(buf + box * BOX_BYTES + row_off + (((uint32_t)chunk ^ sw) << 4));
+                double2 v = *p;
+                const double2 *h0 = reinterpret_cast<const double2 *>(tab + (size_t)(2 * q) * SD);
+                const double2 *h1 = h0 + SD / 2;
+#pragma unroll
+                for (int kk = 0; kk < SD / 2; kk++) {
+                    const double2 ha = h0[kk], hb = h1[kk];
+                    v.x = fma_t((T)ha.x, ci[2 * kk], (T)v.x);
+                    v.y = fma_t((T)hb.x, ci[2 * kk], (T)v.y);
+                    v.x = fma_t((T)ha.y, ci[2 * kk + 1], (T)v.x);
+                    v.y = fma_t((T)hb.y, ci[2 * kk + 1], (T)v.y);
+                }
+                *p = v;
+            }
         }
         fence_proxy_async();
         __syncwarp();
@@ -363,17 +428,17 @@ template <typename T>
 struct ScanChunk; // samples per lane: 32 KiB tiles
 template <>
 struct ScanChunk<float> {
-    static constexpr int L = 256;
+    static constexpr int L = 128;
 };
 template <>
 struct ScanChunk<double> {
-    static constexpr int L = 128;
+    static constexpr int L = 64;
 };
 
-template <typename T, int M, int KIND>
-static int launch_scan(IirBank &b, void *data, size_t n_samples, size_t stride, cudaStream_t stream, size_t *done)
+template <typename T, int M, int KIND, int L, int WARPS, bool ONE_CH>
+static int launch_scan_cfg(IirBank &b, void *data, size_t n_samples, size_t stride, cudaStream_t stream, size_t *done)
 {
-    constexpr int L = ScanChunk<T>::L, SD = 2 * M, WARPS = 4, RG = 8;
+    constexpr int SD = 2 * M, RG = 8;
     constexpr int TSB = 128 / (int)sizeof(T);
     constexpr int TAB = scan_table_count(M, L);
     const size_t tile = (size_t)32 * L;
@@ -393,7 +458,7 @@ static int launch_scan(IirBank &b, void *data, size_t n_samples, size_t stride, 
         std::vector<double> one;
         for (size_t ch = 0; ch < b.n_channels; ch++) {
             int r = 0;
-            scan_build_tables(M, KIND, b.h_gain[ch], &b.h_b[ch * 3 * M], &b.h_a[ch * 3 * M], L, one, r);
+            scan_build_tables(M, KIND, b.h_gain[ch], &b.h_b[ch * 3 * M], &b.h_a[ch * 3 * M], L, scan_negligible<T>(), one, r);
             reach[ch] = r;
             for (int i = 0; i < TAB; i++)
                 tabs[ch * TAB + i] = (T)one[i];
@@ -454,8 +519,8 @@ static int launch_scan(IirBank &b, void *data, size_t n_samples, size_t stride, 
     if (r != CUDA_SUCCESS)
         return set_error(SDSP_B200_ERR_CUDA, "iir scan: cuTensorMapEncodeTiled failed with %d", (int)r);
 
-    auto kern = iir_scan_kernel<T, M, KIND, L, WARPS, RG>;
-    constexpr size_t smem = (size_t)WARPS * (L / TSB) * 32 * 128;
+    auto kern = iir_scan_kernel<T, M, KIND, L, WARPS, RG, ONE_CH>;
+    constexpr size_t smem = (size_t)WARPS * (size_t)(L / TSB) * 32 * 128 + (size_t)(ONE_CH ? 1 : WARPS) * (((size_t)TAB * sizeof(T) + 15) / 16 * 16);
     static bool configured = false;
     static int occ = 1;
     if (!configured) {
@@ -469,14 +534,51 @@ static int launch_scan(IirBank &b, void *data, size_t n_samples, size_t stride, 
     size_t grid = (size_t)b.sm_count * occ;
     if (grid * WARPS > total_tiles)
         grid = (total_tiles + WARPS - 1) / WARPS;
-    kern<<<(unsigned)grid, WARPS * 32, smem, stream>>>(map, static_cast<const T *>(b.d_coef), static_cast<T *>(b.d_state), b.n_channels,
+    // outgoing history is written to the bank's second state buffer, which then becomes the current one
+    const size_t state_bytes = (size_t)(2 + SD) * b.n_channels * sizeof(T);
+    if (!b.d_state_alt) {
+        if (cudaMalloc(&b.d_state_alt, state_bytes) != cudaSuccess) {
+            cudaGetLastError();
+            return set_error(SDSP_B200_ERR_OOM, "iir scan: cannot allocate %zu bytes of state", state_bytes);
+        }
+    }
+    kern<<<(unsigned)grid, WARPS * 32, smem, stream>>>(map, static_cast<const T *>(b.d_coef), static_cast<const T *>(b.d_state),
+                                                      static_cast<T *>(b.d_state_alt), b.n_channels,
                                                       static_cast<const T *>(b.d_scan_tables),
                                                       reinterpret_cast<const int *>(static_cast<char *>(b.d_scan_tables) +
                                                                                     (size_t)b.n_channels * TAB * sizeof(T)),
                                                       recs, ticket, b.scan_epoch, (unsigned)n_tiles, (unsigned)rows_per_channel);
     SDSP_CUDA(cudaGetLastError());
+    std::swap(b.d_state, b.d_state_alt);
     *done = n_tiles * tile;
     return SDSP_B200_OK;
+}
+
+// chunk length / warps per CTA: SDSP_B200_SCAN_TUNE=<0|1> is a kernel-tuning aid (alternative built for the
+// headline instantiations only)
+template <typename T, int M, int KIND>
+static int launch_scan(IirBank &b, void *data, size_t n_samples, size_t stride, cudaStream_t stream, size_t *done)
+{
+    static int alt = -1;
+    if (alt < 0) {
+        const char *e = getenv("SDSP_B200_SCAN_TUNE");
+        alt = e ? atoi(e) : 0;
+    }
+    constexpr int L = ScanChunk<T>::L;
+    // 16 KiB tiles; warps per CTA = what 227 KB of shared memory holds next to the table copies
+    constexpr int TABB = (scan_table_count(M, L) * (int)sizeof(T) + 15) / 16 * 16;
+    constexpr int W_ONE = (220 * 1024 - TABB) / (16 * 1024) > 12 ? 12 : (220 * 1024 - TABB) / (16 * 1024);
+    constexpr int W_MANY = (220 * 1024) / (16 * 1024 + TABB) > 12 ? 12 : (220 * 1024) / (16 * 1024 + TABB);
+    if constexpr (M == 4 && KIND == NUM_GENERIC) {
+        if (alt == 1 && b.scan_chunk_request == 2 * L) {
+            if (b.n_channels == 1)
+                return launch_scan_cfg<T, M, KIND, 2 * L, 6, true>(b, data, n_samples, stride, stream, done);
+            return launch_scan_cfg<T, M, KIND, 2 * L, 5, false>(b, data, n_samples, stride, stream, done);
+        }
+    }
+    if (b.n_channels == 1)
+        return launch_scan_cfg<T, M, KIND, L, W_ONE, true>(b, data, n_samples, stride, stream, done);
+    return launch_scan_cfg<T, M, KIND, L, W_MANY, false>(b, data, n_samples, stride, stream, done);
 }
 
 template <typename T, int M>
@@ -504,7 +606,13 @@ static int launch_scan_sections(IirBank &b, void *data, size_t n, size_t stride,
 
 int iir_scan_chunk(int precision)
 {
-    return precision == SDSP_B200_F32 ? ScanChunk<float>::L : ScanChunk<double>::L;
+    static int alt = -1;
+    if (alt < 0) {
+        const char *e = getenv("SDSP_B200_SCAN_TUNE");
+        alt = e ? atoi(e) : 0;
+    }
+    const int L = precision == SDSP_B200_F32 ? ScanChunk<float>::L : ScanChunk<double>::L;
+    return alt == 1 ? 2 * L : L;
 }
 
 // whole tiles through the scan kernel, the ragged remainder through the sequential kernel (which picks the
@@ -513,6 +621,7 @@ int iir_launch_scan(IirBank &b, void *data, size_t n_samples, size_t stride, cud
 {
     const size_t es = b.precision == SDSP_B200_F32 ? 4 : 8;
     const int L = iir_scan_chunk(b.precision);
+    b.scan_chunk_request = L;
     if (reinterpret_cast<uintptr_t>(data) % 16 != 0 || (b.n_channels > 1 && stride % L != 0) || !get_encode_fn())
         return set_error(SDSP_B200_ERR_UNSUPPORTED,
                          "iir scan path needs a 16-byte aligned base and (for several channels) a channel stride that is a multiple of %d samples", L);

@@ -18,9 +18,9 @@
 //   tiles:   a warp owns 32 consecutive chunks; tiles of one channel are chained through small
 //            records in global memory (decoupled look-back).  With Mt = A_L^32:
 //              c_in(tile t) = sum_{k>=1} Mt^(k-1) agg(t-k)
-//            For every stable filter Mt^K underflows to exactly zero after a few tiles (K = "reach",
-//            found on the host); the sum is then cut after K terms without changing a bit and tiles do
-//            not wait for one another's final result.  Filters whose reach exceeds the window fall back
+//            For every stable filter Mt^K falls below 2^-80 (fp64) / 2^-50 (fp32) after a few tiles
+//            (K = "reach", found on the host); the sum is then cut after K terms -- orders of magnitude
+//            below one ulp -- and tiles do not wait for one another's final result.  Filters whose reach exceeds the window fall back
 //            to waiting for the predecessor's inclusive state (correct for any filter, slower).
 //
 // All matrices are block lower-triangular (section j never feeds back into sections < j); only those
@@ -35,6 +35,11 @@ namespace sdsp_b200
 constexpr int SCAN_LANES = 32;
 constexpr int SCAN_KS_STEPS = 5;   // log2(32)
 constexpr int SCAN_MAX_REACH = 8;  // look-back window of the fast path
+template <typename T>
+constexpr double scan_negligible()
+{
+    return sizeof(T) == 4 ? 8.8817841970012523e-16 /* 2^-50 */ : 8.2718061255302767e-25 /* 2^-80 */;
+}
 
 SDSP_HD constexpr int scan_sd(int m) // dimension of the carried state
 {
@@ -83,7 +88,7 @@ SDSP_HD void scan_state_to_vec(const IirState<T, M> &s, T (&c)[2 * M])
 
 // ---- host: tables ---------------------------------------------------------------------------------
 template <int M, int KIND>
-inline void scan_build_tables_mk(double gain, const double *b, const double *a, int L, std::vector<double> &out, int &reach)
+inline void scan_build_tables_mk(double gain, const double *b, const double *a, int L, double negligible, std::vector<double> &out, int &reach)
 {
     constexpr int SD = 2 * M;
     IirCoef<double, M> c;
@@ -114,14 +119,15 @@ inline void scan_build_tables_mk(double gain, const double *b, const double *a, 
     };
     for (int j = 1; j <= SCAN_KS_STEPS; j++) // A_(2L), A_(4L), ... A_(32L) = Mt
         square(out.data() + scan_off_A(M, L, j - 1), out.data() + scan_off_A(M, L, j));
-    // reach: smallest K with Mt^K == 0 exactly
+    // reach: smallest K with max |Mt^K| <= negligible (2^-80 for fp64 data, 2^-50 for fp32: eight and more
+    // decimal orders below one ulp of anything the carried state is added to)
     const double *Mt = out.data() + scan_off_A(M, L, SCAN_KS_STEPS);
     std::vector<double> pw(Mt, Mt + SD * SD), nx(SD * SD);
     reach = 1 << 30;
     for (int K = 1; K <= 64; K++) {
         bool zero = true;
         for (double v : pw)
-            zero = zero && (v == 0.0);
+            zero = zero && (v <= negligible && v >= -negligible);
         if (zero) {
             reach = K;
             break;
@@ -137,15 +143,16 @@ inline void scan_build_tables_mk(double gain, const double *b, const double *a, 
     }
 }
 
-inline int scan_build_tables(int m, int kind, double gain, const double *b, const double *a, int L, std::vector<double> &out, int &reach)
+inline int scan_build_tables(int m, int kind, double gain, const double *b, const double *a, int L, double negligible, std::vector<double> &out,
+                             int &reach)
 {
 #define SDSP_SCAN_CASE(MM)                                                                \
     case MM:                                                                              \
         switch (kind) {                                                                   \
-        case NUM_GENERIC: scan_build_tables_mk<MM, NUM_GENERIC>(gain, b, a, L, out, reach); break; \
-        case NUM_LP: scan_build_tables_mk<MM, NUM_LP>(gain, b, a, L, out, reach); break;  \
-        case NUM_HP: scan_build_tables_mk<MM, NUM_HP>(gain, b, a, L, out, reach); break;  \
-        default: scan_build_tables_mk<MM, NUM_BP>(gain, b, a, L, out, reach); break;      \
+        case NUM_GENERIC: scan_build_tables_mk<MM, NUM_GENERIC>(gain, b, a, L, negligible, out, reach); break; \
+        case NUM_LP: scan_build_tables_mk<MM, NUM_LP>(gain, b, a, L, negligible, out, reach); break;  \
+        case NUM_HP: scan_build_tables_mk<MM, NUM_HP>(gain, b, a, L, negligible, out, reach); break;  \
+        default: scan_build_tables_mk<MM, NUM_BP>(gain, b, a, L, negligible, out, reach); break;      \
         }                                                                                 \
         return 0;
     switch (m) {
