@@ -41,6 +41,11 @@ WORKLOADS = {
     "iir4096_f32": dict(kind="iir", channels=4096, samples=1 << 22, precision="f32", sections=4, bytes_per_sample=8),
     "iir4096_f32_scan": dict(kind="iir", channels=4096, samples=1 << 22, precision="f32", sections=4, bytes_per_sample=8, path="scan"),
     "iirscan_f64": dict(kind="iir", channels=1, samples=1 << 30, precision="f64", sections=4, bytes_per_sample=16, path="scan"),
+    "iirscan_f32": dict(kind="iir", channels=1, samples=1 << 30, precision="f32", sections=4, bytes_per_sample=8, path="scan"),
+    "iirscan_f64_lookback": dict(kind="iir", channels=1, samples=1 << 30, precision="f64", sections=4, bytes_per_sample=16, path="lookback"),
+    "iir4096_f32_lookback": dict(kind="iir", channels=4096, samples=1 << 22, precision="f32", sections=4, bytes_per_sample=8, path="lookback"),
+    "iir16384_f32_scan": dict(kind="iir", channels=16384, samples=1 << 20, precision="f32", sections=4, bytes_per_sample=8, path="scan"),
+    "iir16384_f64": dict(kind="iir", channels=16384, samples=1 << 19, precision="f64", sections=4, bytes_per_sample=16),
 }
 
 
@@ -235,7 +240,7 @@ class IirWorkload:
         self.ch, self.n, self.m = spec["channels"], spec["samples"], spec["sections"]
         self.prec = K.F32 if spec["precision"] == "f32" else K.F64
         self.rdtype = torch.float32 if self.prec == K.F32 else torch.float64
-        self.path = K.IIR_SCAN if spec.get("path") == "scan" else K.IIR_AUTO
+        self.path = {"scan": K.IIR_SCAN, "lookback": K.IIR_SCAN_LOOKBACK}.get(spec.get("path"), K.IIR_AUTO)
         self.bank = S.IirBank(self.m, self.ch, self.prec, K.NUM_GENERIC, device)
         fs = 100e3
         ftype = np.where(np.arange(self.ch) % 2 == 0, K.LOW_PASS, K.HIGH_PASS)

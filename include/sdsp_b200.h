@@ -57,7 +57,10 @@ enum sdsp_b200_numerator { SDSP_B200_NUM_GENERIC = 0, SDSP_B200_NUM_LP = 1, SDSP
 enum sdsp_b200_iir_path {
     SDSP_B200_IIR_AUTO = 0,       /* pure function of the bank configuration, never of call length alone */
     SDSP_B200_IIR_SEQUENTIAL = 1, /* lane per channel, samples in order; bit-identical however a stream is cut into calls */
-    SDSP_B200_IIR_SCAN = 2        /* chunked state-space scan along time (reassociates; fp64 error ~1e-13 of peak) */
+    SDSP_B200_IIR_SCAN = 2,       /* time axis split into chunks that carry boundary state (reassociates; fp64 error ~1e-13 of peak):
+                                     the time-split kernel when the filter's memory fits a segment, else the look-back scan */
+    SDSP_B200_IIR_SCAN_LOOKBACK = 3, /* force the look-back scan kernel (any stable filter) */
+    SDSP_B200_IIR_SCAN_SPLIT = 4     /* force the time-split kernel (error if the filter's memory is too long for the call) */
 };
 
 typedef struct sdsp_b200_fft_plan_s *sdsp_b200_fft_plan;

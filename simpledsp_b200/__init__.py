@@ -9,7 +9,7 @@ Nothing here computes: every call goes through the C ABI to the CUDA kernels and
 library or the device is missing.
 """
 from . import _capi
-from ._capi import (BAND_PASS, F32, F64, FORWARD, HIGH_PASS, IIR_AUTO, IIR_SCAN, IIR_SEQUENTIAL, LOW_PASS,
+from ._capi import (BAND_PASS, F32, F64, FORWARD, HIGH_PASS, IIR_AUTO, IIR_SCAN, IIR_SCAN_LOOKBACK, IIR_SCAN_SPLIT, IIR_SEQUENTIAL, LOW_PASS,
                     NUM_BP, NUM_GENERIC, NUM_HP, NUM_LP, REVERSE, SdspError)
 from .fft import FftPlan, digit_reverse_permute, digit_reverse_table, fft_radix2, fft_radix4
 from .iir import IirBank, casc_2o_iir, casc_2o_iir_bp, casc_2o_iir_hp, casc_2o_iir_lp, design
@@ -18,5 +18,5 @@ __all__ = [
     "FftPlan", "fft_radix2", "fft_radix4", "digit_reverse_table", "digit_reverse_permute",
     "IirBank", "casc_2o_iir", "casc_2o_iir_lp", "casc_2o_iir_hp", "casc_2o_iir_bp", "design",
     "SdspError", "F32", "F64", "FORWARD", "REVERSE", "LOW_PASS", "HIGH_PASS", "BAND_PASS",
-    "NUM_GENERIC", "NUM_LP", "NUM_HP", "NUM_BP", "IIR_AUTO", "IIR_SEQUENTIAL", "IIR_SCAN",
+    "NUM_GENERIC", "NUM_LP", "NUM_HP", "NUM_BP", "IIR_AUTO", "IIR_SEQUENTIAL", "IIR_SCAN", "IIR_SCAN_LOOKBACK", "IIR_SCAN_SPLIT",
 ]

@@ -19,7 +19,7 @@ FORWARD, REVERSE = 0, 1
 PTR_HOST, PTR_DEVICE = 0, 1
 FILTER_NONE, LOW_PASS, HIGH_PASS, BAND_PASS = 0, 1, 2, 3
 NUM_GENERIC, NUM_LP, NUM_HP, NUM_BP = 0, 1, 2, 3
-IIR_AUTO, IIR_SEQUENTIAL, IIR_SCAN = 0, 1, 2
+IIR_AUTO, IIR_SEQUENTIAL, IIR_SCAN, IIR_SCAN_LOOKBACK, IIR_SCAN_SPLIT = 0, 1, 2, 3, 4
 
 _vp, _dp, _u32p, _sz = C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint32), C.c_size_t
 

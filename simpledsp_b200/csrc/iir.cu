@@ -521,7 +521,7 @@ int sdsp_b200_iir_bank_process(sdsp_b200_iir_bank bank, void *data, size_t n_sam
     IirBank &b = bank->b;
     if (channel_stride < n_samples && b.n_channels > 1)
         return set_error(SDSP_B200_ERR_INVALID_ARG, "iir_bank_process: channel_stride %zu < n_samples %zu", channel_stride, n_samples);
-    if (path < SDSP_B200_IIR_AUTO || path > SDSP_B200_IIR_SCAN)
+    if (path < SDSP_B200_IIR_AUTO || path > SDSP_B200_IIR_SCAN_SPLIT)
         return set_error(SDSP_B200_ERR_INVALID_ARG, "iir_bank_process: bad path %d", path);
     const size_t es = elem_size(b.precision);
     if (reinterpret_cast<uintptr_t>(data) % es)

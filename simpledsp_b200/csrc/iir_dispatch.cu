@@ -27,8 +27,18 @@ static bool iir_use_tma(const IirBank &b, const void *data, size_t n_samples, si
 
 int iir_dispatch(IirBank &b, void *data, size_t n_samples, size_t stride, int path, cudaStream_t stream)
 {
+    // time-parallel: the time-split path when the filter's memory fits a segment, else the look-back scan
     if (path == SDSP_B200_IIR_SCAN)
+        return iir_segment_applicable(b, data, n_samples, stride) ? iir_launch_segmented(b, data, n_samples, stride, stream) :
+                                                                    iir_launch_scan(b, data, n_samples, stride, stream);
+    if (path == SDSP_B200_IIR_SCAN_LOOKBACK)
         return iir_launch_scan(b, data, n_samples, stride, stream);
+    if (path == SDSP_B200_IIR_SCAN_SPLIT) {
+        if (!iir_segment_applicable(b, data, n_samples, stride))
+            return set_error(SDSP_B200_ERR_UNSUPPORTED, "iir time-split path needs a 16-byte aligned layout, a filter whose natural response "
+                                                        "vanishes within a segment, and fewer channels than the GPU has lanes");
+        return iir_launch_segmented(b, data, n_samples, stride, stream);
+    }
     if (iir_use_tma(b, data, n_samples, stride))
         return iir_launch_tma(b, data, n_samples, stride, stream);
     return iir_launch_sequential(b, data, n_samples, stride, stream);
@@ -37,11 +47,20 @@ int iir_dispatch(IirBank &b, void *data, size_t n_samples, size_t stride, int pa
 int iir_describe(IirBank &b, size_t n_samples, size_t stride, int path, char *buf, size_t buf_len)
 {
     // alignment of the (unknown here) base pointer is assumed: describe() reports the kernel a 16-byte aligned call gets
-    const bool tma = path != SDSP_B200_IIR_SCAN && iir_use_tma(b, nullptr, n_samples, stride);
-    snprintf(buf, buf_len, "iir bank: %zu channels x %d sections %s numerator=%d; n_samples=%zu stride=%zu path=%s -> %s",
-             b.n_channels, b.sections, b.precision == SDSP_B200_F32 ? "f32" : "f64", b.numerator, n_samples, stride,
-             path == SDSP_B200_IIR_SCAN ? "scan" : path == SDSP_B200_IIR_SEQUENTIAL ? "sequential" : "auto",
-             path == SDSP_B200_IIR_SCAN ? "scan" : tma ? "sequential/tma (warp per 32 channels, skewed sections, 4-stage TMA ring)" : "sequential/generic");
+    const bool timepar = path == SDSP_B200_IIR_SCAN || path == SDSP_B200_IIR_SCAN_LOOKBACK || path == SDSP_B200_IIR_SCAN_SPLIT;
+    const bool tma = !timepar && iir_use_tma(b, nullptr, n_samples, stride);
+    char how[512];
+    snprintf(how, sizeof how, "%s", tma ? "sequential/tma (warp per 32 channels, skewed sections, 6-stage TMA ring per warp)" : "sequential/generic");
+    if (timepar) {
+        const bool split = path != SDSP_B200_IIR_SCAN_LOOKBACK && b.h_gain.size() == b.n_channels && iir_use_tma(b, nullptr, n_samples, stride) &&
+                           iir_segment_describe(b, n_samples, how, sizeof how) == 0;
+        if (!split)
+            snprintf(how, sizeof how, "look-back scan (warp per 32 chunks of %d samples, Kogge-Stone over lanes, decoupled look-back between tiles)",
+                     iir_scan_chunk(b.precision));
+    }
+    snprintf(buf, buf_len, "iir bank: %zu channels x %d sections %s numerator=%d; n_samples=%zu stride=%zu path=%s -> %s", b.n_channels,
+             b.sections, b.precision == SDSP_B200_F32 ? "f32" : "f64", b.numerator, n_samples, stride,
+             timepar ? "time-parallel" : path == SDSP_B200_IIR_SEQUENTIAL ? "sequential" : "auto", how);
     return SDSP_B200_OK;
 }
 
@@ -53,7 +72,10 @@ void iir_bank_release_aux(IirBank &b)
         cudaFree(b.d_scan_flags);
     if (b.d_state_alt)
         cudaFree(b.d_state_alt);
-    b.d_scan_tables = b.d_scan_flags = b.d_state_alt = nullptr;
+    if (b.d_seg_state)
+        cudaFree(b.d_seg_state);
+    b.d_scan_tables = b.d_scan_flags = b.d_state_alt = b.d_seg_state = nullptr;
+    b.seg_state_bytes = 0;
 }
 } // namespace sdsp_b200
 

@@ -28,6 +28,12 @@ struct IirBank {
     unsigned scan_epoch = 0;
     void *d_scan_flags = nullptr;
     size_t scan_flags_bytes = 0;
+    // time-split path (iir_segment.cu): filter memory in samples (0 = never decays) and per-segment history
+    unsigned long long decay_len = 0;
+    unsigned long decay_version = ~0ul;
+    bool decay_len_valid = false;
+    void *d_seg_state = nullptr;
+    size_t seg_state_bytes = 0;
     // host staging
     void *d_stage = nullptr;
     size_t stage_bytes = 0;
@@ -40,7 +46,16 @@ int iir_launch_sequential(const IirBank &b, void *data, size_t n_samples, size_t
 bool iir_tma_applicable(const IirBank &b, const void *data, size_t n_samples, size_t stride);
 bool iir_tma_built_for(int sections);
 int iir_launch_tma(const IirBank &b, void *data, size_t n_samples, size_t stride, cudaStream_t stream);
-// iir_scan.cu -- time-parallel path
+// rows = segments of channels (see iir_segment.cu)
+int iir_launch_tma_rows(const IirBank &b, void *data, size_t seg_len, size_t segs, size_t stride, void *row_state, size_t n_samples,
+                        bool accumulate, cudaStream_t stream);
+int iir_tma_rows_slots_per_sm(const IirBank &b);
+// iir_segment.cu -- time-parallel path for filters whose memory is shorter than a segment
+bool iir_segment_applicable(IirBank &b, const void *data, size_t n_samples, size_t stride);
+int iir_launch_segmented(IirBank &b, void *data, size_t n_samples, size_t stride, cudaStream_t stream);
+int iir_segment_describe(IirBank &b, size_t n_samples, char *buf, size_t buf_len);
+unsigned long long iir_decay_length(IirBank &b);
+// iir_scan.cu -- time-parallel path, general (look-back carry of the propagation term)
 int iir_launch_scan(IirBank &b, void *data, size_t n_samples, size_t stride, cudaStream_t stream);
 int iir_scan_chunk(int precision);
 // iir_dispatch.cu

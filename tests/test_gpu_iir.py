@@ -183,21 +183,28 @@ def _scan_reference(ftype, f0, fs, x, sections=4):
     return f, f.process(x)
 
 
+TIME_PARALLEL = {"auto": K.IIR_SCAN, "lookback": K.IIR_SCAN_LOOKBACK, "split": K.IIR_SCAN_SPLIT}
+
+
+@pytest.mark.parametrize("how", ["split", "lookback"])
 @pytest.mark.parametrize("prec", ["f64", "f32"])
 @pytest.mark.parametrize("case", [(1, 10e3, 100e3), (2, 10e3, 100e3), (3, 2000.0, 39e3), (1, 200.0, 39e3)])
-def test_scan_single_long_channel_matches_sequential_reference(case, prec):
-    """BASELINE config 4 in miniature: one channel, time axis split over the whole GPU."""
+def test_scan_single_long_channel_matches_sequential_reference(case, prec, how):
+    """BASELINE config 4 in miniature: one channel, time axis split over the whole GPU -- by the time-split
+    kernel (segments as rows of the lane-per-row kernel + natural-response correction) and by the look-back scan."""
     ftype, f0, fs = case
     code, dt = PREC[prec]
+    tp = TIME_PARALLEL[how]
     chunk = 128 if prec == "f64" else 256
-    n = 32 * chunk * 37 + 333  # 37 whole tiles + a ragged tail (sequential kernel)
+    n = 32 * chunk * 150 + 333  # whole tiles / segments + a ragged tail (sequential kernel)
     rng = np.random.default_rng(int(f0) + ftype)
     x = f32_noise(rng, n)
     f, ref = _scan_reference(ftype, f0, fs, x)
     g, b, a = S.design(ftype, 4, f0, fs, 1.1)
     bank = S.IirBank(4, 1, code)
     bank.set_coeffs([g], [b], [a])
-    y = bank.process(x.astype(dt), path=K.IIR_SCAN)
+    assert ("time-split" in bank.describe(n, n, tp)) == (how == "split")
+    y = bank.process(x.astype(dt), path=tp)
     tol = 3 * IIR_TOL[prec] if (prec == "f32" and f0 < 1e3) else IIR_TOL[prec]  # SURVEY H3, as in the CPU test
     assert peak_rel(y, ref) <= tol
     # the history left behind continues the stream exactly where the scan stopped
@@ -208,7 +215,7 @@ def test_scan_single_long_channel_matches_sequential_reference(case, prec):
     # and a second scan call on the same bank (non-zero incoming history) too
     more = f32_noise(rng, 32 * chunk * 3)
     want2 = f.process(more)
-    got2 = bank.process(more.astype(dt), path=K.IIR_SCAN)
+    got2 = bank.process(more.astype(dt), path=K.IIR_SCAN if how == "split" else tp)  # (short: auto may pick either)
     assert peak_rel(got2, want2) <= 10 * tol
 
 
@@ -223,22 +230,32 @@ def test_scan_general_carry_path_for_long_memory_filters():
     g, b, a = S.design(1, 4, 20.0, 100e3)
     bank = S.IirBank(4, 1, K.F64)
     bank.set_coeffs([g], [b], [a])
+    assert "look-back" in bank.describe(n, n, K.IIR_SCAN)  # filter memory (~3e5 samples) exceeds any segment of this call
+    with pytest.raises(RuntimeError):
+        bank.process(x.copy(), path=K.IIR_SCAN_SPLIT)
     y = bank.process(x.copy(), path=K.IIR_SCAN)
     assert peak_rel(y, ref) <= 1e-8
 
 
+@pytest.mark.parametrize("how", ["auto", "lookback"])
 @pytest.mark.parametrize("prec", ["f64", "f32"])
-def test_scan_few_channels_each_split_along_time(prec):
+def test_scan_few_channels_each_split_along_time(prec, how):
     torch = pytest.importorskip("torch")
     code, dt = PREC[prec]
+    tp = TIME_PARALLEL[how]
     chunk = 128 if prec == "f64" else 256
-    n_channels, n = 6, 32 * chunk * 5 + 100
-    stride = 32 * chunk * 6
+    n_channels, n = 6, 32 * chunk * 100 + 100
+    stride = 32 * chunk * 101
     bank, x, ref = _bank_case(n_channels, n, prec, seed=77)
     tdt = torch.float32 if prec == "f32" else torch.float64
     wide = torch.zeros(n_channels, stride, device="cuda", dtype=tdt)
     wide[:, :n] = torch.from_numpy(x).cuda()
-    bank.process_ptr(wide.data_ptr(), n, stride, K.PTR_DEVICE, K.IIR_SCAN, torch.cuda.current_stream().cuda_stream)
+    if how == "auto":
+        assert "time-split" in bank.describe(n, stride, tp)
+    bank.process_ptr(wide.data_ptr(), n, stride, K.PTR_DEVICE, tp, torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     assert peak_rel(wide[:, :n].cpu().numpy(), ref) <= IIR_TOL[prec]
     assert float(wide[:, n:].abs().max()) == 0.0
+    # the bank history continues the stream: next block through the sequential kernel
+    st = bank.get_state()
+    assert np.isfinite(st).all()
