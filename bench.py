@@ -44,6 +44,10 @@ WORKLOADS = {
     "iirscan_f32": dict(kind="iir", channels=1, samples=1 << 30, precision="f32", sections=4, bytes_per_sample=8, path="scan"),
     "iirscan_f64_lookback": dict(kind="iir", channels=1, samples=1 << 30, precision="f64", sections=4, bytes_per_sample=16, path="lookback"),
     "iir4096_f32_lookback": dict(kind="iir", channels=4096, samples=1 << 22, precision="f32", sections=4, bytes_per_sample=8, path="lookback"),
+    # BASELINE config 5, one GPU's share at 8 GPUs: 512 channels x 64 frames of 65536 real samples (32768 frames):
+    # IIR along every channel (time-split path), then every frame transformed (real in, spectrum out)
+    "pipeline65536_f32": dict(kind="pipeline", channels=512, frames_per_channel=64, n=65536, precision="f32", sections=4,
+                              bytes_per_sample=20),
     "iir16384_f32_scan": dict(kind="iir", channels=16384, samples=1 << 20, precision="f32", sections=4, bytes_per_sample=8, path="scan"),
     "iir16384_f64": dict(kind="iir", channels=16384, samples=1 << 19, precision="f64", sections=4, bytes_per_sample=16),
 }
@@ -281,12 +285,77 @@ class IirWorkload:
         pass
 
 
+class PipelineWorkload:
+    """IIR bank over [channels][frames*n] real samples in place, then a real-input FFT of every n-sample frame into
+    a spectrum buffer.  Algorithmic bytes per sample: 8 (filter, read + write) + 4 + 8 (transform, real in, complex out)."""
+
+    def __init__(self, spec, device):
+        import torch
+
+        import simpledsp_b200 as S
+        from simpledsp_b200 import _capi as K
+
+        self.spec, self.S, self.K, self.torch = spec, S, K, torch
+        self.ch, self.fpc, self.n, self.m = spec["channels"], spec["frames_per_channel"], spec["n"], spec["sections"]
+        self.prec = K.F32
+        self.len = self.fpc * self.n
+        self.bank = S.IirBank(self.m, self.ch, self.prec, K.NUM_GENERIC, device)
+        g_, b_, a_ = S.design(K.LOW_PASS, self.m, 10e3, 100e3)
+        self.bank.set_coeffs(np.full(self.ch, g_), np.tile(b_, (self.ch, 1, 1)), np.tile(a_, (self.ch, 1, 1)))
+        self.plan = S.FftPlan(self.n, 4, self.prec, K.FORWARD, device)
+        g = torch.Generator(device="cuda").manual_seed(1234 + device)
+        self.signal = torch.empty(self.ch, self.len, device="cuda", dtype=torch.float32)
+        rows = max(1, (1 << 28) // self.len)
+        for lo in range(0, self.ch, rows):
+            self.signal[lo:lo + rows].normal_(generator=g)
+        self.spectra = torch.empty(self.ch * self.fpc, self.n, device="cuda", dtype=torch.complex64)
+        self.samples_per_step = self.ch * self.len
+        self.stream = torch.cuda.current_stream().cuda_stream
+
+    def describe(self):
+        return self.bank.describe(self.len, self.len, self.K.IIR_SCAN) + " | then real-input " + self.plan.describe()
+
+    def launches_per_step(self):
+        return 1
+
+    def step(self):
+        K = self.K
+        self.bank.process_ptr(self.signal.data_ptr(), self.len, self.len, K.PTR_DEVICE, K.IIR_SCAN, self.stream)
+        self.plan.exec_real_ptr(self.signal.data_ptr(), self.spectra.data_ptr(), self.ch * self.fpc, K.PTR_DEVICE, self.stream)
+
+    def self_check(self):
+        """A sampled frame of the spectrum buffer equals the transform of the filtered signal it was made from."""
+        torch = self.torch
+        torch.cuda.synchronize()
+        worst = 0.0
+        for c, f in ((0, 0), (self.ch // 2, self.fpc // 2), (self.ch - 1, self.fpc - 1)):
+            x = self.signal[c, f * self.n:(f + 1) * self.n].double()
+            ref = torch.fft.fft(x)
+            got = self.spectra[c * self.fpc + f].to(torch.complex128)
+            worst = max(worst, float((got - ref).abs().pow(2).sum().sqrt() / ref.abs().pow(2).sum().sqrt()))
+        return worst
+
+    def e2e_prepare(self):
+        return None
+
+    def e2e_release(self):
+        pass
+
+
 # --------------------------------------------------------------------------------------------------
 def cpu_reference_rate(spec, threads: int, target_seconds: float = 6.0):
     """The reference's own CPU implementation on a bounded sample of the workload.
     -> (Msamples/s, kind, cores, sample description, single-thread Msamples/s)"""
     from oracle import oracle as O
 
+    if spec["kind"] == "pipeline":  # filter then transform: per-sample times add
+        a = cpu_reference_rate(dict(kind="iir", channels=spec["channels"], samples=spec["frames_per_channel"] * spec["n"],
+                                    sections=spec["sections"]), threads, target_seconds / 2)
+        b = cpu_reference_rate(dict(kind="fft", n=spec["n"]), threads, target_seconds / 2)
+        rate = 1.0 / (1.0 / a[0] + 1.0 / b[0])
+        single = 1.0 / (1.0 / a[4] + 1.0 / b[4])
+        kind = "reference" if a[1] == b[1] == "reference" else "port"
+        return rate, kind, max(a[2], b[2]), f"filter: {a[3]} | transform: {b[3]}", single
     kind = "reference" if O.have_ref() else "port"
     rng = np.random.default_rng(1234)
     if spec["kind"] == "fft":
@@ -388,7 +457,7 @@ def main():
     warmup = max(args.warmup, 3)
     steps = max(args.steps, 1)
     rank, local, world = dist_setup(args.gpus)
-    wl = (FftWorkload if spec["kind"] == "fft" else IirWorkload)(spec, local)
+    wl = {"fft": FftWorkload, "iir": IirWorkload, "pipeline": PipelineWorkload}[spec["kind"]](spec, local)
 
     for _ in range(warmup):
         wl.step()
@@ -453,7 +522,7 @@ def main():
                          "traffic": None, "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0,
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kernel_ms},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches * steps), "clocks": clocks,
-            "self_check": {"roundtrip_rel_err" if spec["kind"] == "fft" else "nonfinite": check},
+            "self_check": {{"fft": "roundtrip_rel_err", "iir": "nonfinite", "pipeline": "spectrum_vs_torch_fft_rel_err"}[spec["kind"]]: check},
             "step_ms": {"min": float(per_step.min()), "median": float(np.median(per_step)), "max": float(per_step.max())},
         }
         print(json.dumps(out))

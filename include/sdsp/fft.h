@@ -107,6 +107,21 @@ namespace detail
         }
         check(sdsp_b200_fft_exec(h->plan, frames, n_frames, ptr_kind, stream), "sdsp_b200_fft_exec");
     }
+
+    template <class T, int RADIX, typename S>
+    void run_real(const S *real_frames, std::complex<S> *spectra, uint32_t n, size_t n_frames, int ptr_kind, void *stream)
+    {
+        thread_local std::vector<std::pair<uint32_t, plan_holder *>> cache;
+        plan_holder *h = nullptr;
+        for (auto &e : cache)
+            if (e.first == n)
+                h = e.second;
+        if (!h) {
+            h = new plan_holder(n, RADIX, precision_of<S>(), T::Direction());
+            cache.emplace_back(n, h);
+        }
+        check(sdsp_b200_fft_exec_real(h->plan, real_frames, spectra, n_frames, ptr_kind, stream), "sdsp_b200_fft_exec_real");
+    }
 } // namespace detail
 
 // ---- direction policies: reference fft.h:121-146 ---------------------------------------------
@@ -236,5 +251,23 @@ template <class T = forward_fft, typename S>
 void fft_radix2_device(std::complex<S> *frames, size_t n, size_t n_frames, void *stream = nullptr)
 {
     detail::run<T, 2, S>(frames, static_cast<uint32_t>(n), n_frames, SDSP_B200_PTR_DEVICE, stream);
+}
+// real frames in, spectra out (out of place): what the reference's callers do by hand -- real part = signal, imaginary
+// part = 0 (test/testFFT.cpp:24, :86) -- folded into the transform's first load.  Device-resident buffers.
+template <class T = forward_fft, typename S>
+void fft_radix4_real_device(const S *real_frames, std::complex<S> *spectra, size_t n, size_t n_frames, void *stream = nullptr)
+{
+    detail::run_real<T, 4, S>(real_frames, spectra, static_cast<uint32_t>(n), n_frames, SDSP_B200_PTR_DEVICE, stream);
+}
+template <class T = forward_fft, typename S>
+void fft_radix2_real_device(const S *real_frames, std::complex<S> *spectra, size_t n, size_t n_frames, void *stream = nullptr)
+{
+    detail::run_real<T, 2, S>(real_frames, spectra, static_cast<uint32_t>(n), n_frames, SDSP_B200_PTR_DEVICE, stream);
+}
+// the same on host buffers (staged through the device)
+template <class T = forward_fft, typename S>
+void fft_radix4_real(const S *real_frames, std::complex<S> *spectra, size_t n, size_t n_frames)
+{
+    detail::run_real<T, 4, S>(real_frames, spectra, static_cast<uint32_t>(n), n_frames, SDSP_B200_PTR_HOST, nullptr);
 }
 } // namespace sdsp

@@ -92,6 +92,11 @@ int sdsp_b200_device_synchronize(int device);
 int sdsp_b200_fft_plan_create(sdsp_b200_fft_plan *plan, uint32_t n, int radix, int precision, int direction, int device);
 int sdsp_b200_fft_plan_destroy(sdsp_b200_fft_plan plan);
 int sdsp_b200_fft_exec(sdsp_b200_fft_plan plan, void *data, size_t n_frames, int ptr_kind, void *stream);
+/* Real frames in (n scalars each), spectra out (n complex each), out of place.  The reference has no real-input
+ * entry point; its callers place real signals in the real part of a complex_array and leave the imaginary part
+ * zero (test/testFFT.cpp:24, :86).  This does that placement inside the first load of the transform, so the input
+ * costs half the bytes.  Built for n <= 16384 and n = 65536. */
+int sdsp_b200_fft_exec_real(sdsp_b200_fft_plan plan, const void *real_in, void *spectrum_out, size_t n_frames, int ptr_kind, void *stream);
 /* human-readable description of the factorisation / launch geometry the plan chose */
 int sdsp_b200_fft_plan_describe(sdsp_b200_fft_plan plan, char *buf, size_t buf_len);
 /* number of kernel launches one exec of n_frames device-resident frames issues */

@@ -10,6 +10,8 @@
 #include <mutex>
 #include <vector>
 
+#include <cooperative_groups.h>
+
 #include <cuda_runtime.h>
 
 #include "fft_core.cuh"
@@ -124,7 +126,8 @@ __device__ __forceinline__ void fft_kernel_passes(cplx<T> (&v)[Cfg::E], cplx<T> 
 
 template <class Cfg, typename T, int THREADS, int MINB, bool DB = false>
 __global__ void __launch_bounds__(THREADS, MINB)
-    fft_cta_kernel(cplx<T> *__restrict__ data, const cplx<T> *__restrict__ tw, size_t n_frames, int inverse, T scale)
+    fft_cta_kernel(cplx<T> *__restrict__ data, const T *__restrict__ real_in, const cplx<T> *__restrict__ tw, size_t n_frames, int inverse,
+                   T scale)
 {
     constexpr int FPC = THREADS / Cfg::TPF;
     static_assert(THREADS % Cfg::TPF == 0 && FPC >= 1, "block must hold whole frames");
@@ -141,7 +144,12 @@ __global__ void __launch_bounds__(THREADS, MINB)
         const bool active = frame < n_frames;
         cplx<T> *gp = data + frame * (size_t)Cfg::N + t;
         cplx<T> v[Cfg::E];
-        if (active) {
+        if (active && real_in) { // real samples (imaginary part zero, as the reference's callers fill their arrays), out of place
+            const T *rp = real_in + frame * (size_t)Cfg::N + t;
+#pragma unroll
+            for (int e = 0; e < Cfg::E; e++)
+                v[e] = cplx<T>{ rp[Cfg::S * e], (T)0 };
+        } else if (active) {
 #pragma unroll
             for (int e = 0; e < Cfg::E; e++)
                 v[e] = ld_stream(gp + Cfg::S * e);
@@ -221,7 +229,7 @@ __global__ void digit_reverse_permute_kernel(cplx<T> *data, uint32_t n, int log2
 // =================================================================================================
 // plans
 struct FftPlan;
-typedef int (*fft_launch_fn)(const FftPlan &, void *data, size_t n_frames, cudaStream_t stream);
+typedef int (*fft_launch_fn)(const FftPlan &, void *data, const void *real_in, size_t n_frames, cudaStream_t stream);
 typedef void (*fft_emulate_fn)(void *frame, const void *tw, bool inverse);
 
 struct FftPlan {
@@ -236,6 +244,8 @@ struct FftPlan {
     fft_launch_fn launch = nullptr;
     // multi-pass ("four-step") path for frames larger than one CTA can hold: n = n1 * 256
     bool large = false;
+    bool cluster = false; // n = 65536: one frame per 8-CTA cluster, single pass over HBM
+    int cluster_slots = 0, cluster_ctas = 0;
     int n1 = 0;
     void *d_tw_cols = nullptr, *d_tw_rows = nullptr, *d_tw_hi = nullptr, *d_tw_lo = nullptr;
     void *d_scratch = nullptr;
@@ -249,7 +259,7 @@ struct FftPlan {
 };
 
 template <class Cfg, typename T, int THREADS, int MINB, bool DB>
-static int launch_cta(const FftPlan &p, void *data, size_t n_frames, cudaStream_t stream)
+static int launch_cta(const FftPlan &p, void *data, const void *real_in, size_t n_frames, cudaStream_t stream)
 {
     constexpr int FPC = THREADS / Cfg::TPF;
     const size_t groups = (n_frames + FPC - 1) / FPC;
@@ -260,7 +270,7 @@ static int launch_cta(const FftPlan &p, void *data, size_t n_frames, cudaStream_
     size_t grid = groups < resident * 4 ? groups : resident * 4;
     const T scale = (T)(1.0 / (double)Cfg::N);
     fft_cta_kernel<Cfg, T, THREADS, MINB, DB><<<(unsigned)grid, THREADS, p.smem_bytes, stream>>>(
-        reinterpret_cast<cplx<T> *>(data), reinterpret_cast<const cplx<T> *>(p.d_tw), n_frames,
+        reinterpret_cast<cplx<T> *>(data), static_cast<const T *>(real_in), reinterpret_cast<const cplx<T> *>(p.d_tw), n_frames,
         p.direction == SDSP_B200_REVERSE ? 1 : 0, scale);
     SDSP_CUDA(cudaGetLastError());
     return SDSP_B200_OK;
@@ -322,6 +332,33 @@ static void emulate_cfg(void *frame, bool inverse)
 // tables (W_n^x = W_n1^(x >> 8) * W_n^(x & 255)).
 constexpr int LARGE_COLS = 16; // columns / rows per CTA
 
+// The 16 inter-transform twiddles a thread needs, W_n^(b*k1) with k1 = t + S*e, form a geometric sequence in e:
+// W_n^(b t) * (W_n^(b S))^e.  Looking each one up costs two table loads whose addresses diverge across the warp
+// (b varies by lane) -- 32 divergent loads per thread.  Instead seven terms are looked up (each exact to one
+// rounding) and the rest are one product away:  w_e = qh[e / 4] * ql[e % 4],
+//   qh[i] = W^(b (t + 4 i S)),  ql[j] = W^(j b S).
+template <typename T>
+struct TwiddleSeq {
+    cplx<T> qh[4], ql[3];
+    __device__ __forceinline__ TwiddleSeq(unsigned x0, unsigned step, const cplx<T> *__restrict__ hi, const cplx<T> *__restrict__ lo)
+    {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const unsigned x = x0 + 4u * (unsigned)i * step;
+            qh[i] = cmul(hi[x >> 8], lo[x & 255u]);
+        }
+#pragma unroll
+        for (int j = 1; j < 4; j++) {
+            const unsigned x = (unsigned)j * step;
+            ql[j - 1] = cmul(hi[x >> 8], lo[x & 255u]);
+        }
+    }
+    __device__ __forceinline__ cplx<T> get(int e) const // e is a compile-time constant after unrolling
+    {
+        return (e & 3) == 0 ? qh[e >> 2] : cmul(qh[e >> 2], ql[(e & 3) - 1]);
+    }
+};
+
 template <class Cfg>
 struct LargeStride { // odd frame pitch: the 16 frames a warp touches together land in different banks
     static constexpr int value = Cfg::PADDED_N + 1;
@@ -357,12 +394,12 @@ __global__ void __launch_bounds__(THREADS)
         fft_kernel_passes<Cfg, T, THREADS, 1, 0>(v, fs, tw, t);
         cplx<T> *op = out + frame * ((size_t)N1 * N2) + c0 + col;
         const unsigned b = (unsigned)(c0 + col);
+        static_assert(Cfg::E == 16, "TwiddleSeq covers 16 points per thread");
+        const TwiddleSeq<T> wseq(b * (unsigned)t, b * (unsigned)Cfg::S, tw_hi, tw_lo);
 #pragma unroll
         for (int e = 0; e < Cfg::E; e++) {
             const unsigned k1 = (unsigned)(t + Cfg::S * e);
-            const unsigned x = b * k1;
-            const cplx<T> wv = cmul(tw_hi[x >> 8], tw_lo[x & 255u]);
-            op[(size_t)k1 * N2] = cmul(v[e], wv);
+            op[(size_t)k1 * N2] = cmul(v[e], wseq.get(e));
         }
         if constexpr (Cfg::NPASS > 1)
             __syncthreads();
@@ -415,8 +452,10 @@ __global__ void __launch_bounds__(THREADS)
 }
 
 template <class CfgA, typename T>
-static int launch_large(const FftPlan &p, void *data, size_t n_frames, cudaStream_t stream)
+static int launch_large(const FftPlan &p, void *data, const void *real_in, size_t n_frames, cudaStream_t stream)
 {
+    if (real_in)
+        return set_error(SDSP_B200_ERR_UNSUPPORTED, "fft: real-input frames are built for n <= 16384 and n = 65536 (n=%u)", p.n);
     using CfgB = FftCfg<256, 16, 16, 16>;
     constexpr int THREADS_A = LARGE_COLS * CfgA::TPF;
     cplx<T> *d = reinterpret_cast<cplx<T> *>(data);
@@ -505,9 +544,272 @@ static int setup_large(FftPlan &p)
     return SDSP_B200_OK;
 }
 
+// =================================================================================================
+// 65536-point frames in ONE pass over HBM: a thread-block cluster of 8 CTAs holds the frame in its
+// distributed shared memory (the same n = 256 a + b, k = k1 + 256 k2 split as above, but the [k1][b]
+// intermediate never leaves the chip).
+//   phase 1: CTA r owns columns b in [32r, 32r+32): 256-point transforms over a, read straight from HBM
+//            (128-byte runs), times W_N^(b k1); result (k1, b) is written into the shared memory of CTA
+//            k1 / 32 (st through the cluster's shared window), at row k1 % 32, position b;
+//   phase 2: CTA r owns rows k1 in [32r, 32r+32): 256-point transforms over b out of its own shared
+//            memory, stored to X[k1 + 256 k2] as 128-byte runs over k1.
+// Each phase runs as two halves of 16 columns / rows (256 threads x 16 points), so a CTA needs one
+// 16-transform exchange buffer plus the 32-row receive buffer (105 KB fp32: two clusters per SM overlap
+// one another's load, exchange and store phases).  Two cluster barriers per frame, split into
+// arrive/wait so that they cost nothing when CTAs are in step: "receive buffers are free" (arrive after
+// the last read of phase 2, wait before the first remote write) and "all rows have arrived".
+// Arithmetic is that of the two-kernel path above, operation for operation.
+namespace cg = cooperative_groups;
+
+__device__ __forceinline__ void cluster_arrive_release()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_wait_acquire()
+{
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive without a fence: used where the only thing to order is this thread's own completed shared-memory READS (their
+// values have been consumed by arithmetic before the call) against peers' later writes -- a release here would also wait
+// for the global stores of the previous batch to drain (11 % of all stall samples in the first profile)
+__device__ __forceinline__ void cluster_arrive_relaxed()
+{
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void prefetch_l2_bulk(const void *p, unsigned bytes) // bytes: multiple of 16
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ uint32_t cluster_map_shared(uint32_t local_addr, uint32_t rank) // same offset in CTA `rank` of the cluster
+{
+    uint32_t a;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(a) : "r"(local_addr), "r"(rank));
+    return a;
+}
+__device__ __forceinline__ void st_cluster(uint32_t addr, cplx<float> v)
+{
+    asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
+}
+__device__ __forceinline__ void st_cluster(uint32_t addr, cplx<double> v)
+{
+    asm volatile("st.shared::cluster.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(v.x), "d"(v.y) : "memory");
+}
+
+// CL = CTAs per cluster: 8 (portable; two halves of 16 columns / rows per phase) or 16 (opt-in size; one
+// transform batch per phase, 70 KB of shared memory in fp32, so three CTAs share an SM like the 4096-point kernel)
+template <typename T, int CL, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+    fft_cluster64k_kernel(cplx<T> *__restrict__ data, const T *__restrict__ real_in, const cplx<T> *__restrict__ tw,
+                          const cplx<T> *__restrict__ tw_hi, const cplx<T> *__restrict__ tw_lo, size_t n_frames, int inverse, T scale)
+{
+    using Cfg = FftCfg<256, 16, 16, 16>;
+    constexpr int PITCH = LargeStride<Cfg>::value;
+    constexpr int N2 = 256;
+    constexpr int OWN = N2 / CL;     // columns (phase 1) and rows (phase 2) this CTA owns
+    constexpr int HALVES = OWN / 16; // batches of 16 transforms
+    static_assert(CL == 8 || CL == 16, "cluster of 8 or 16 CTAs");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx<T> *xbuf = reinterpret_cast<cplx<T> *>(smem_raw); // exchange buffer of the 16 transforms in flight
+    cplx<T> *rbuf = xbuf + 16 * PITCH;                     // OWN rows received from the whole cluster
+    cplx<T> *s_hi = rbuf + OWN * PITCH, *s_lo = s_hi + 256; // the two 256-entry factors of W_N^x, read with lane-divergent indices
+    s_hi[threadIdx.x] = tw_hi[threadIdx.x];
+    s_lo[threadIdx.x] = tw_lo[threadIdx.x];
+    __syncthreads();
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned r = cluster.block_rank();
+    const size_t n_clusters = gridDim.x / CL, cid = blockIdx.x / CL;
+    const int lo16 = threadIdx.x & 15, t = threadIdx.x >> 4; // column (phase 1) / row (phase 2) within the batch; thread in transform
+    cplx<T> *fs = xbuf + (size_t)lo16 * PITCH;
+
+    cluster_arrive_release(); // "my receive buffer is free" for the first frame
+    for (size_t f = cid; f < n_frames; f += n_clusters) {
+        cplx<T> *frame = data + f * ((size_t)N2 * N2);
+        if (f + n_clusters < n_frames) { // the columns this CTA reads in the next frame: one row piece per thread, into L2
+            const size_t nf = f + n_clusters;
+            if (real_in)
+                prefetch_l2_bulk(real_in + nf * ((size_t)N2 * N2) + (size_t)threadIdx.x * N2 + OWN * r, OWN * (unsigned)sizeof(T));
+            else
+                prefetch_l2_bulk(data + nf * ((size_t)N2 * N2) + (size_t)threadIdx.x * N2 + OWN * r, OWN * (unsigned)sizeof(cplx<T>));
+        }
+        // ---- phase 1: columns
+#pragma unroll 1
+        for (int h = 0; h < HALVES; h++) {
+            const unsigned b = (unsigned)OWN * r + 16u * (unsigned)h + (unsigned)lo16;
+            const cplx<T> *gp = frame + b;
+            cplx<T> v[Cfg::E];
+            if (real_in) { // real samples, imaginary part zero; the spectrum goes to `data`
+                const T *rp = real_in + f * ((size_t)N2 * N2) + b;
+#pragma unroll
+                for (int e = 0; e < Cfg::E; e++)
+                    v[e] = cplx<T>{ rp[(size_t)(t + Cfg::S * e) * N2], (T)0 };
+            } else {
+#pragma unroll
+                for (int e = 0; e < Cfg::E; e++)
+                    v[e] = ld_stream(gp + (size_t)(t + Cfg::S * e) * N2);
+            }
+            if (inverse) {
+#pragma unroll
+                for (int e = 0; e < Cfg::E; e++)
+                    v[e] = cplx<T>{ v[e].y, v[e].x };
+            }
+            __syncthreads(); // the previous transforms have read the exchange buffer
+            fft_kernel_passes<Cfg, T, 256, MINB, 0>(v, fs, tw, t);
+            if (h == 0)
+                cluster_wait_acquire(); // every CTA has finished reading its receive buffer (previous frame)
+            const uint32_t slot = (uint32_t)__cvta_generic_to_shared(rbuf) + (uint32_t)((t * PITCH + (int)(b + (b >> 4))) * (int)sizeof(cplx<T>));
+            const TwiddleSeq<T> wseq(b * (unsigned)t, b * (unsigned)Cfg::S, s_hi, s_lo); // W_N^(b k1), k1 = t + 16 e
+#pragma unroll
+            for (int e = 0; e < Cfg::E; e++) { // k1 = t + 16 e lives in CTA k1 / OWN, row k1 % OWN
+                constexpr int EPC = OWN / 16; // values of e per destination CTA
+                const cplx<T> w = cmul(v[e], wseq.get(e));
+                st_cluster(cluster_map_shared(slot + (uint32_t)(16 * (e % EPC) * PITCH * (int)sizeof(cplx<T>)), (unsigned)(e / EPC)), w);
+            }
+        }
+        cluster_arrive_release(); // my share of every row has been written
+        cluster_wait_acquire();   // all 256 columns of my rows are here
+        // ---- phase 2: rows
+#pragma unroll 1
+        for (int g = 0; g < HALVES; g++) {
+            const int row = 16 * g + lo16;
+            const cplx<T> *rs = rbuf + (size_t)row * PITCH;
+            cplx<T> v[Cfg::E];
+#pragma unroll
+            for (int e = 0; e < Cfg::E; e++)
+                v[e] = rs[Cfg::pad(t + Cfg::S * e)];
+            __syncthreads();
+            if (g == HALVES - 1) {
+                // nothing more to read from my receive buffer: free for the next frame.  The barrier above sits behind the
+                // shared-memory loads of every thread of the CTA, so they have all returned.
+                cluster_arrive_relaxed();
+            }
+            fft_kernel_passes<Cfg, T, 256, MINB, 0>(v, fs, tw, t);
+            if (inverse) {
+#pragma unroll
+                for (int e = 0; e < Cfg::E; e++)
+                    v[e] = cplx<T>{ v[e].y * scale, v[e].x * scale };
+            }
+            cplx<T> *op = frame + (unsigned)OWN * r + (unsigned)row;
+#pragma unroll
+            for (int e = 0; e < Cfg::E; e++)
+                st_stream(op + (size_t)(t + Cfg::S * e) * N2, v[e]);
+        }
+    }
+    cluster_wait_acquire(); // pairs with the last arrive; nobody leaves while a peer may still write to it
+}
+
+template <typename T, int CL, int MINB>
+static int launch_cluster64k(const FftPlan &p, void *data, const void *real_in, size_t n_frames, cudaStream_t stream)
+{
+    if (n_frames == 0)
+        return SDSP_B200_OK;
+    const size_t clusters = (size_t)p.cluster_slots < n_frames ? (size_t)p.cluster_slots : n_frames;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(clusters * CL), 1, 1);
+    cfg.blockDim = dim3(256, 1, 1);
+    cfg.dynamicSmemBytes = p.smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = CL;
+    attr.val.clusterDim.y = attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    SDSP_CUDA(cudaLaunchKernelEx(&cfg, fft_cluster64k_kernel<T, CL, MINB>, reinterpret_cast<cplx<T> *>(data), static_cast<const T *>(real_in),
+                                 reinterpret_cast<const cplx<T> *>(p.d_tw_rows), reinterpret_cast<const cplx<T> *>(p.d_tw_hi),
+                                 reinterpret_cast<const cplx<T> *>(p.d_tw_lo), n_frames, p.direction == SDSP_B200_REVERSE ? 1 : 0,
+                                 (T)(1.0 / 65536.0)));
+    return SDSP_B200_OK;
+}
+
+template <typename T, int CL, int MINB>
+static int setup_cluster64k(FftPlan &p)
+{
+    using Cfg = FftCfg<256, 16, 16, 16>;
+    p.smem_bytes = ((size_t)(16 + 256 / CL) * LargeStride<Cfg>::value + 512) * sizeof(cplx<T>);
+    auto kern = fft_cluster64k_kernel<T, CL, MINB>;
+    SDSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
+    if (CL > 8 && cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+        cudaGetLastError();
+        return SDSP_B200_ERR_UNSUPPORTED;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(p.sm_count * MINB / CL * CL), 1, 1);
+    cfg.blockDim = dim3(256, 1, 1);
+    cfg.dynamicSmemBytes = p.smem_bytes;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = CL;
+    attr.val.clusterDim.y = attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    int slots = 0;
+    if (cudaOccupancyMaxActiveClusters(&slots, kern, &cfg) != cudaSuccess || slots < 1) {
+        cudaGetLastError();
+        return SDSP_B200_ERR_UNSUPPORTED;
+    }
+    p.cluster = true;
+    p.cluster_ctas = CL;
+    p.cluster_slots = slots;
+    p.n1 = 256;
+    p.npass = 4;
+    p.e = 16;
+    p.threads = 256;
+    if (!p.d_tw_rows) {
+        std::vector<cplx<T>> tw;
+        int rb[4] = { 16, 16, 1, 1 };
+        build_twiddles<T>(256, rb, 2, tw);
+        int rc = upload_table<T>(&p.d_tw_rows, tw);
+        std::vector<cplx<T>> hi(256), lo(256);
+        for (int i = 0; i < 256; i++) {
+            long double re, im;
+            unit_root((uint64_t)i, (uint64_t)256, re, im);
+            hi[i] = cplx<T>{ (T)re, (T)im };
+            unit_root((uint64_t)i, (uint64_t)65536, re, im);
+            lo[i] = cplx<T>{ (T)re, (T)im };
+        }
+        if (!rc)
+            rc = upload_table<T>(&p.d_tw_hi, hi);
+        if (!rc)
+            rc = upload_table<T>(&p.d_tw_lo, lo);
+        if (rc)
+            return rc;
+        p.tw_bytes = (tw.size() + hi.size() + lo.size()) * sizeof(cplx<T>);
+    }
+    p.launch = &launch_cluster64k<T, CL, MINB>;
+    return SDSP_B200_OK;
+}
+
+// cluster size 8 (portable, measured best: profiles/r01_fft65536_cluster_sweep.txt); SDSP_B200_FFT_CLUSTER=16|162 selects the
+// 16-CTA variants (tuning aid)
+template <typename T>
+static int setup_cluster64k_auto(FftPlan &p)
+{
+    static int pin = -1;
+    if (pin < 0) {
+        const char *e = getenv("SDSP_B200_FFT_CLUSTER");
+        pin = e ? atoi(e) : 0;
+    }
+    int rc = SDSP_B200_ERR_UNSUPPORTED;
+    if constexpr (sizeof(T) == 4) {
+        if (pin == 162) // 16-CTA clusters, two CTAs per SM (128 registers, no spills)
+            return setup_cluster64k<T, 16, 2>(p);
+    }
+    if (pin == 16)
+        rc = setup_cluster64k<T, 16, sizeof(T) == 4 ? 3 : 1>(p);
+    else
+        rc = setup_cluster64k<T, 8, sizeof(T) == 4 ? 2 : 1>(p);
+    if (rc == SDSP_B200_ERR_UNSUPPORTED)
+        return set_error(SDSP_B200_ERR_UNSUPPORTED, "fft: the thread-block-cluster kernel for n=65536 cannot be scheduled on this device");
+    return rc;
+}
+
 template <typename T>
 static int setup_large_n1(FftPlan &p)
 {
+    static const bool two_kernels = getenv("SDSP_B200_FFT_TWO_KERNEL") != nullptr; // comparison aid: the two-kernel path for n = 65536
+    if (p.n == 65536 && !two_kernels)
+        return setup_cluster64k_auto<T>(p);
     switch (p.n / 256) {
     case 64: return setup_large<FftCfg<64, 16, 16, 4>, T>(p);
     case 128: return setup_large<FftCfg<128, 16, 16, 8>, T>(p);
@@ -711,7 +1013,7 @@ int sdsp_b200_fft_exec(sdsp_b200_fft_plan plan, void *data, size_t n_frames, int
     if ((reinterpret_cast<uintptr_t>(data) % elem) != 0)
         return set_error(SDSP_B200_ERR_INVALID_ARG, "fft_exec: data must be aligned to one complex element (%zu bytes)", elem);
     if (ptr_kind == SDSP_B200_PTR_DEVICE)
-        return p.launch(p, data, n_frames, s);
+        return p.launch(p, data, nullptr, n_frames, s);
     if (ptr_kind != SDSP_B200_PTR_HOST)
         return set_error(SDSP_B200_ERR_INVALID_ARG, "fft_exec: bad ptr_kind %d", ptr_kind);
 
@@ -753,7 +1055,7 @@ int sdsp_b200_fft_exec(sdsp_b200_fft_plan plan, void *data, size_t n_frames, int
         if (cudaMemcpyAsync(d, h, cnt * frame_bytes, cudaMemcpyHostToDevice, cs) != cudaSuccess)
             rc = cuda_fail((int)cudaGetLastError(), "H2D", __FILE__, __LINE__);
         if (rc == SDSP_B200_OK)
-            rc = p.launch(p, d, cnt, cs);
+            rc = p.launch(p, d, nullptr, cnt, cs);
         if (rc == SDSP_B200_OK && cudaMemcpyAsync(h, d, cnt * frame_bytes, cudaMemcpyDeviceToHost, cs) != cudaSuccess)
             rc = cuda_fail((int)cudaGetLastError(), "D2H", __FILE__, __LINE__);
         done += cnt;
@@ -769,11 +1071,70 @@ int sdsp_b200_fft_exec(sdsp_b200_fft_plan plan, void *data, size_t n_frames, int
     return rc;
 }
 
+// real frames in, spectra out (out of place): the imaginary part of the input is zero, as in every call site of
+// the reference (test/testFFT.cpp:24,86 fill only the real part) -- half the input bytes of fft_exec
+int sdsp_b200_fft_exec_real(sdsp_b200_fft_plan plan, const void *real_in, void *spectrum_out, size_t n_frames, int ptr_kind, void *stream)
+{
+    if (!plan)
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "fft_exec_real: null plan");
+    if (n_frames == 0)
+        return SDSP_B200_OK;
+    if (!real_in || !spectrum_out)
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "fft_exec_real: null data");
+    FftPlan &p = plan->p;
+    SDSP_CUDA(cudaSetDevice(p.device));
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const size_t es = p.precision == SDSP_B200_F32 ? sizeof(float) : sizeof(double);
+    if ((reinterpret_cast<uintptr_t>(real_in) % es) != 0 || (reinterpret_cast<uintptr_t>(spectrum_out) % (2 * es)) != 0)
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "fft_exec_real: buffers must be aligned to their element size");
+    if (ptr_kind == SDSP_B200_PTR_DEVICE)
+        return p.launch(p, spectrum_out, real_in, n_frames, s);
+    if (ptr_kind != SDSP_B200_PTR_HOST)
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "fft_exec_real: bad ptr_kind %d", ptr_kind);
+    // host buffers: slabs through the plan's staging memory (spectrum slab first, real slab behind it)
+    std::lock_guard<std::mutex> lock(p.mu);
+    const size_t in_bytes = (size_t)p.n * es, out_bytes = 2 * in_bytes;
+    size_t slab = (64u << 20) / out_bytes;
+    slab = slab < 1 ? 1 : slab > n_frames ? n_frames : slab;
+    const size_t need = slab * (in_bytes + out_bytes);
+    if (p.stage_bytes < need) {
+        if (p.d_stage)
+            cudaFree(p.d_stage);
+        p.d_stage = nullptr;
+        p.stage_bytes = 0;
+        if (cudaMalloc(&p.d_stage, need) != cudaSuccess) {
+            cudaGetLastError();
+            return set_error(SDSP_B200_ERR_OOM, "fft_exec_real: cannot allocate %zu bytes of staging memory", need);
+        }
+        p.stage_bytes = need;
+    }
+    char *d_out = static_cast<char *>(p.d_stage), *d_in = d_out + slab * out_bytes;
+    for (size_t done = 0; done < n_frames; done += slab) {
+        const size_t cnt = (n_frames - done) < slab ? (n_frames - done) : slab;
+        SDSP_CUDA(cudaMemcpyAsync(d_in, static_cast<const char *>(real_in) + done * in_bytes, cnt * in_bytes, cudaMemcpyHostToDevice, s));
+        const int rc = p.launch(p, d_out, d_in, cnt, s);
+        if (rc)
+            return rc;
+        SDSP_CUDA(cudaMemcpyAsync(static_cast<char *>(spectrum_out) + done * out_bytes, d_out, cnt * out_bytes, cudaMemcpyDeviceToHost, s));
+        SDSP_CUDA(cudaStreamSynchronize(s));
+    }
+    return SDSP_B200_OK;
+}
+
 int sdsp_b200_fft_plan_describe(sdsp_b200_fft_plan plan, char *buf, size_t buf_len)
 {
     if (!plan || !buf || buf_len == 0)
         return set_error(SDSP_B200_ERR_INVALID_ARG, "fft_plan_describe: bad arguments");
     const FftPlan &p = plan->p;
+    if (p.cluster) {
+        snprintf(buf, buf_len,
+                 "fft n=%u %s %s radix-arg=%d: one frame per %d-CTA thread-block cluster, single pass over HBM: 256 column transforms "
+                 "(%d per CTA, read from HBM) -> twiddle -> rows exchanged through distributed shared memory -> 256 row transforms "
+                 "(%d per CTA) -> HBM; 256 threads/CTA, smem/CTA=%zuB, %d clusters resident, SMs=%d",
+                 p.n, p.precision == SDSP_B200_F32 ? "f32" : "f64", p.direction == SDSP_B200_FORWARD ? "forward" : "reverse", p.radix,
+                 p.cluster_ctas, 256 / p.cluster_ctas, 256 / p.cluster_ctas, p.smem_bytes, p.cluster_slots, p.sm_count);
+        return SDSP_B200_OK;
+    }
     if (p.large) {
         snprintf(buf, buf_len,
                  "fft n=%u %s %s radix-arg=%d: multi-pass, n = %d x 256: column pass (%d-point transforms, 16 columns/CTA, %d threads, "

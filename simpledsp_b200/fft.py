@@ -43,6 +43,28 @@ class FftPlan:
     def exec_ptr(self, ptr: int, n_frames: int, ptr_kind: int, stream=None) -> None:
         K.check(K.lib().sdsp_b200_fft_exec(self._h, ptr, n_frames, ptr_kind, stream))
 
+    def exec_real_ptr(self, real_ptr: int, out_ptr: int, n_frames: int, ptr_kind: int, stream=None) -> None:
+        """n_frames real frames of n scalars at real_ptr -> n_frames spectra of n complex at out_ptr (out of place)."""
+        K.check(K.lib().sdsp_b200_fft_exec_real(self._h, real_ptr, out_ptr, n_frames, ptr_kind, stream))
+
+    def real(self, real_in, out=None):
+        """Transform of real frames (imaginary part zero, the way the reference's callers fill their complex arrays,
+        test/testFFT.cpp:24): numpy in -> numpy out, torch CUDA tensor in -> torch CUDA tensor out."""
+        n = self.n
+        if isinstance(real_in, np.ndarray):
+            want = np.float32 if self.precision == K.F32 else np.float64
+            x = np.ascontiguousarray(real_in, dtype=want)
+            if out is None:
+                out = np.empty(x.shape, dtype=np.complex64 if self.precision == K.F32 else np.complex128)
+            self.exec_real_ptr(x.ctypes.data, out.ctypes.data, x.size // n, K.PTR_HOST, None)
+            return out
+        import torch
+
+        if out is None:
+            out = torch.empty(real_in.shape, device=real_in.device, dtype=torch.complex64 if self.precision == K.F32 else torch.complex128)
+        self.exec_real_ptr(real_in.data_ptr(), out.data_ptr(), real_in.numel() // n, K.PTR_DEVICE, torch.cuda.current_stream().cuda_stream)
+        return out
+
     def __call__(self, data):
         """Transform every length-n row of ``data`` in place (numpy: staged through the device;
         torch CUDA tensor: in place on the current stream, asynchronously).  Returns ``data``."""

@@ -1,0 +1,7 @@
+mkdir -p gpurun_out; rm -f gpurun_out/bench_r18.log
+timeout 900 python -m pytest tests/test_gpu_fft.py -m gpu -q --timeout 300 > gpurun_out/pytest_fft.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_fft.log
+tail -n 5 gpurun_out/pytest_fft.log
+run() { echo -n "$1 " >> gpurun_out/bench_r18.log; timeout 300 python bench.py --steps $3 --warmup 3 --no-e2e --no-cpu --workload $2 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['config']['workload'], round(d['ms_per_step'],3), round(d['value']), round(d['roofline']['achieved'],1), round(d['roofline']['frac'],4), d['self_check'], d['config']['plan'][-90:])" >> gpurun_out/bench_r18.log 2>&1; }
+for c in 16 162 8; do SDSP_B200_FFT_CLUSTER=$c run cluster=$c fft65536_f32 20; done
+SDSP_B200_FFT_TWO_KERNEL=1 run twokernel fft65536_f32 20
+cat gpurun_out/bench_r18.log
