@@ -53,6 +53,16 @@ WORKLOADS = {
 }
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, one launch at the workload's full size, from the
+# committed `ncu --set full` summaries (profiles/); None where no capture at that size exists
+NCU_TRAFFIC = {
+    "fft4096_f32": (4.263e9, "profiles/r01_ncu_fft4096_f32_v1.txt"),
+    "fft4096_f64": (8.813e9, "profiles/r01_ncu_fft4096_f64_v1.txt"),
+    "iir16384_f32": (1.3739e11, "profiles/r01_ncu_iir16384_f32_tma_v3.txt"),
+    "iirscan_f64": (1.7122e10, "profiles/r01_launches_iir_split_v1.txt"),
+}
+
+
 def hbm_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -269,7 +279,11 @@ class IirWorkload:
         return self.bank.describe(self.n, self.n, self.path)
 
     def launches_per_step(self):
-        return 1
+        return 1  # the bandwidth-bound pass: all the algorithmic bytes go through one launch
+
+    def gpu_launches_per_step(self):
+        # time-split: gather, row pass, carry, correction pass (leftover rounds, if any, not counted); else one kernel
+        return 4 if "time-split" in self.describe() else 1
 
     def step(self):
         self.bank.process_ptr(self.data.data_ptr(), self.n, self.n, self.K.PTR_DEVICE, self.path, self.stream)
@@ -317,6 +331,9 @@ class PipelineWorkload:
 
     def launches_per_step(self):
         return 1
+
+    def gpu_launches_per_step(self):
+        return 5  # filter: gather, row pass, carry, correction pass; transform: one cluster kernel
 
     def step(self):
         K = self.K
@@ -368,9 +385,9 @@ def cpu_reference_rate(spec, threads: int, target_seconds: float = 6.0):
         t0 = time.perf_counter()
         O.fft(probe, radix, False, impl, threads=1)
         one = (time.perf_counter() - t0) / 64
-        frames = int(min(65536, max(threads * 16, target_seconds * threads / one)))
-        x = np.ascontiguousarray(np.tile(probe, (frames // 64 + 1, 1))[:frames])
         use_threads = threads if impl == "reference" else 1
+        frames = int(min(65536, max(use_threads * 4, target_seconds * use_threads / one)))
+        x = np.ascontiguousarray(np.tile(probe, (frames // 64 + 1, 1))[:frames])
         t0 = time.perf_counter()
         O.fft(x, radix, False, impl, threads=use_threads)
         dt = time.perf_counter() - t0
@@ -442,6 +459,7 @@ def main():
     ap.add_argument("--workload", default="fft4096_f32", choices=sorted(WORKLOADS))
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="default workload only: skip the IIR (config 3) lines measured beside it")
     ap.add_argument("--frames", type=int, default=0, help="override frames (fft) for quick runs")
     args = ap.parse_args()
     spec = dict(WORKLOADS[args.workload])
@@ -457,34 +475,47 @@ def main():
     warmup = max(args.warmup, 3)
     steps = max(args.steps, 1)
     rank, local, world = dist_setup(args.gpus)
-    wl = {"fft": FftWorkload, "iir": IirWorkload, "pipeline": PipelineWorkload}[spec["kind"]](spec, local)
-
-    for _ in range(warmup):
-        wl.step()
-    barrier(world)
-
-    sampler = ClockSampler(local)
-    evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
-    sampler.start()
-    barrier(world)
-    evs[0].record()
-    for i in range(steps):
-        wl.step()
-        evs[i + 1].record()
-    barrier(world)
-    clocks = sampler.stop()
-    total_ms = evs[0].elapsed_time(evs[-1])
-    per_step = np.array([evs[i].elapsed_time(evs[i + 1]) for i in range(steps)])
-    total_ms_max = max_over_ranks(total_ms, world)
-    check = wl.self_check()
-
-    samples = wl.samples_per_step * steps * world
-    value = samples / (total_ms_max * 1e-3) / 1e6
     peak, peak_src = hbm_peak()
-    launches = wl.launches_per_step()
-    kernel_ms = float(per_step.mean()) / max(1, launches)
-    alg_bytes = wl.samples_per_step * spec["bytes_per_sample"] / max(1, launches)
-    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+
+    def measure(name, spec, steps):
+        """W warm-up steps, then `steps` timed steps between barriers; CUDA events on the launching stream, max over ranks."""
+        wl = {"fft": FftWorkload, "iir": IirWorkload, "pipeline": PipelineWorkload}[spec["kind"]](spec, local)
+        for _ in range(warmup):
+            wl.step()
+        barrier(world)
+        sampler = ClockSampler(local)
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        sampler.start()
+        barrier(world)
+        evs[0].record()
+        for i in range(steps):
+            wl.step()
+            evs[i + 1].record()
+        barrier(world)
+        clocks = sampler.stop()
+        total_ms = evs[0].elapsed_time(evs[-1])
+        per_step = np.array([evs[i].elapsed_time(evs[i + 1]) for i in range(steps)])
+        total_ms_max = max_over_ranks(total_ms, world)
+        check = wl.self_check()
+        launches = wl.launches_per_step()
+        kernel_ms = float(per_step.mean()) / max(1, launches)
+        alg_bytes = wl.samples_per_step * spec["bytes_per_sample"] / max(1, launches)
+        achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+        res = {
+            "value": wl.samples_per_step * steps * world / (total_ms_max * 1e-3) / 1e6, "ms_per_step": total_ms_max / steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": NCU_TRAFFIC.get(name, (None, None))[0], "traffic_source": NCU_TRAFFIC.get(name, (None, None))[1],
+                         "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0, "algorithmic_bytes_per_launch": alg_bytes,
+                         "kernel_ms": kernel_ms},
+            "gpu_launches": int(getattr(wl, "gpu_launches_per_step", wl.launches_per_step)() * steps), "clocks": clocks,
+            "self_check": {{"fft": "roundtrip_rel_err", "iir": "nonfinite", "pipeline": "spectrum_vs_torch_fft_rel_err"}[spec["kind"]]: check},
+            "step_ms": {"min": float(per_step.min()), "median": float(np.median(per_step)), "max": float(per_step.max())},
+            "plan": wl.describe(),
+        }
+        return wl, res
+
+    wl, res = measure(args.workload, spec, steps)
+    value, launches = res["value"], wl.launches_per_step()
 
     # ---- end to end (host buffers through the public API), rank-local, max over ranks
     e2e = None
@@ -510,20 +541,33 @@ def main():
         r = cpu_reference_rate(spec, os.cpu_count() or 1)
         cpu = {"value": r[0], "unit": "Msamples/s", "cores": r[2], "kind": r[1], "sample": r[3], "single_thread": r[4]}
 
+    # ---- the other half of the metric ("batched FFT & biquad IIR"): BASELINE config 3 measured in the same run
+    secondary = []
+    if args.workload == "fft4096_f32" and not args.no_secondary:
+        wl.data = None
+        del wl
+        torch.cuda.empty_cache()
+        for name in ("iir16384_f32", "iir16384_f32_scan"):
+            sp = dict(WORKLOADS[name])
+            w2, r2 = measure(name, sp, 5)
+            secondary.append({"workload": name, "metric": "Msamples/s", "value": r2["value"], "ms_per_step": r2["ms_per_step"],
+                              "steps": 5, "dtype": sp["precision"], "roofline": r2["roofline"], "gpu_launches": r2["gpu_launches"],
+                              "self_check": r2["self_check"], "plan": r2["plan"],
+                              "config": {k: v for k, v in sp.items() if k != "kind"}})
+            w2.data = None
+            del w2
+            torch.cuda.empty_cache()
+
     if rank == 0:
         out = {
             "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": steps, "warmup": warmup,
-            "ms_per_step": total_ms_max / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": spec["precision"], "data": "synthetic",
             "config": {"workload": args.workload, **{k: v for k, v in spec.items() if k != "kind"},
                        "per_gpu": True, "in_place": True, "l2": "working set per step is far larger than the 126 MB L2",
-                       "steps_alternate": "forward/reverse" if spec["kind"] == "fft" else "n/a", "plan": wl.describe()},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0,
-                         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kernel_ms},
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches * steps), "clocks": clocks,
-            "self_check": {{"fft": "roundtrip_rel_err", "iir": "nonfinite", "pipeline": "spectrum_vs_torch_fft_rel_err"}[spec["kind"]]: check},
-            "step_ms": {"min": float(per_step.min()), "median": float(np.median(per_step)), "max": float(per_step.max())},
+                       "steps_alternate": "forward/reverse" if spec["kind"] == "fft" else "n/a", "plan": res["plan"]},
+            "roofline": res["roofline"], "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": res["gpu_launches"], "clocks": res["clocks"],
+            "self_check": res["self_check"], "step_ms": res["step_ms"], "secondary": secondary,
         }
         print(json.dumps(out))
     if world > 1:

@@ -95,6 +95,11 @@ __device__ __forceinline__ void st_stream(cplx<T> *p, cplx<T> v)
     *p = v;
 }
 
+__device__ __forceinline__ void prefetch_l2_bulk(const void *p, unsigned bytes) // bytes: multiple of 16
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 // DB = false: one exchange buffer, a barrier after every write and after every read that is followed by a
 //   write (four per 3-pass frame).
 // DB = true: two buffers used alternately; a pass reads one and writes the other, so only the barrier after
@@ -127,7 +132,7 @@ __device__ __forceinline__ void fft_kernel_passes(cplx<T> (&v)[Cfg::E], cplx<T> 
 template <class Cfg, typename T, int THREADS, int MINB, bool DB = false>
 __global__ void __launch_bounds__(THREADS, MINB)
     fft_cta_kernel(cplx<T> *__restrict__ data, const T *__restrict__ real_in, const cplx<T> *__restrict__ tw, size_t n_frames, int inverse,
-                   T scale)
+                   T scale, int prefetch)
 {
     constexpr int FPC = THREADS / Cfg::TPF;
     static_assert(THREADS % Cfg::TPF == 0 && FPC >= 1, "block must hold whole frames");
@@ -142,6 +147,15 @@ __global__ void __launch_bounds__(THREADS, MINB)
     for (size_t g = blockIdx.x; g < groups; g += gridDim.x) {
         const size_t frame = g * FPC + fl;
         const bool active = frame < n_frames;
+        // the frames this CTA takes next: pulled into L2 while this group is transformed (one bulk prefetch, no registers)
+        if (prefetch && threadIdx.x == 0 && g + gridDim.x < groups) {
+            const size_t nf = (g + gridDim.x) * FPC;
+            const size_t cnt = (n_frames - nf) < (size_t)FPC ? (n_frames - nf) : (size_t)FPC;
+            if (real_in)
+                prefetch_l2_bulk(real_in + nf * (size_t)Cfg::N, (unsigned)(cnt * Cfg::N * sizeof(T)));
+            else
+                prefetch_l2_bulk(data + nf * (size_t)Cfg::N, (unsigned)(cnt * Cfg::N * sizeof(cplx<T>)));
+        }
         cplx<T> *gp = data + frame * (size_t)Cfg::N + t;
         cplx<T> v[Cfg::E];
         if (active && real_in) { // real samples (imaginary part zero, as the reference's callers fill their arrays), out of place
@@ -258,6 +272,16 @@ struct FftPlan {
     std::mutex mu;
 };
 
+static bool fft_prefetch_enabled() // SDSP_B200_FFT_PREFETCH=0 switches the L2 prefetch of the next frames off (comparison aid)
+{
+    static int on = -1;
+    if (on < 0) {
+        const char *e = getenv("SDSP_B200_FFT_PREFETCH");
+        on = e ? atoi(e) : 1;
+    }
+    return on != 0;
+}
+
 template <class Cfg, typename T, int THREADS, int MINB, bool DB>
 static int launch_cta(const FftPlan &p, void *data, const void *real_in, size_t n_frames, cudaStream_t stream)
 {
@@ -271,7 +295,10 @@ static int launch_cta(const FftPlan &p, void *data, const void *real_in, size_t 
     const T scale = (T)(1.0 / (double)Cfg::N);
     fft_cta_kernel<Cfg, T, THREADS, MINB, DB><<<(unsigned)grid, THREADS, p.smem_bytes, stream>>>(
         reinterpret_cast<cplx<T> *>(data), static_cast<const T *>(real_in), reinterpret_cast<const cplx<T> *>(p.d_tw), n_frames,
-        p.direction == SDSP_B200_REVERSE ? 1 : 0, scale);
+        p.direction == SDSP_B200_REVERSE ? 1 : 0, scale, fft_prefetch_enabled() && (Cfg::N * sizeof(T)) % 16 == 0 && reinterpret_cast<uintptr_t>(data) % 16 == 0 &&
+                reinterpret_cast<uintptr_t>(real_in) % 16 == 0 ?
+            1 :
+            0);
     SDSP_CUDA(cudaGetLastError());
     return SDSP_B200_OK;
 }
@@ -575,10 +602,6 @@ __device__ __forceinline__ void cluster_wait_acquire()
 __device__ __forceinline__ void cluster_arrive_relaxed()
 {
     asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void prefetch_l2_bulk(const void *p, unsigned bytes) // bytes: multiple of 16
-{
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
 __device__ __forceinline__ uint32_t cluster_map_shared(uint32_t local_addr, uint32_t rank) // same offset in CTA `rank` of the cluster
