@@ -259,6 +259,9 @@ struct FftPlan {
     // multi-pass ("four-step") path for frames larger than one CTA can hold: n = n1 * 256
     bool large = false;
     bool cluster = false; // n = 65536: one frame per 8-CTA cluster, single pass over HBM
+    bool fused = false;   // n = 65536: column and row tiles in one persistent kernel, intermediate in an L2-resident ring
+    void *d_fused_counters = nullptr;
+    size_t fused_counter_bytes = 0;
     int cluster_slots = 0, cluster_ctas = 0;
     int n1 = 0;
     void *d_tw_cols = nullptr, *d_tw_rows = nullptr, *d_tw_hi = nullptr, *d_tw_lo = nullptr;
@@ -648,7 +651,8 @@ __global__ void __launch_bounds__(256, MINB)
     cluster_arrive_release(); // "my receive buffer is free" for the first frame
     for (size_t f = cid; f < n_frames; f += n_clusters) {
         cplx<T> *frame = data + f * ((size_t)N2 * N2);
-        if (f + n_clusters < n_frames) { // the columns this CTA reads in the next frame: one row piece per thread, into L2
+        if (f + n_clusters < n_frames && reinterpret_cast<uintptr_t>(data) % 16 == 0 && reinterpret_cast<uintptr_t>(real_in) % 16 == 0) {
+            // the columns this CTA reads in the next frame: one row piece per thread, into L2
             const size_t nf = f + n_clusters;
             if (real_in)
                 prefetch_l2_bulk(real_in + nf * ((size_t)N2 * N2) + (size_t)threadIdx.x * N2 + OWN * r, OWN * (unsigned)sizeof(T));
@@ -803,6 +807,307 @@ static int setup_cluster64k(FftPlan &p)
     return SDSP_B200_OK;
 }
 
+// =================================================================================================
+// 65536-point frames, third design: ONE persistent kernel runs the column tiles and the row tiles of the two-kernel
+// path as a dependency-ordered work queue, so the [k1][b] intermediate lives in a small ring of scratch frames that
+// stays in the 126 MB L2 and HBM sees each frame once in and once out -- with the occupancy of the 4096-point kernel
+// (256 threads, 35 KB of shared memory, three CTAs per SM) instead of a cluster's.
+//   work item q -> slot q / 16, tile q % 16.  Slots: the column tiles of frames 0 .. LAG-1, then alternately the
+//   column tiles of frame f + LAG and the row tiles of frame f.  A row tile waits until the 16 column tiles of its
+//   frame have been counted in col_done[f]; a column tile of frame f waits until the row tiles of frame f - RING have
+//   released their scratch slot (row_done).  Items are handed out in order by an atomic ticket, and every wait points
+//   at items with smaller tickets, which are held by CTAs that are already running: no deadlock, whatever the residency.
+template <typename T>
+struct FusedRing {
+    static constexpr int LAG = sizeof(T) == 4 ? 32 : 16;  // frames between a frame's column tiles and its row tiles
+    static constexpr int RING = 2 * LAG;                   // scratch frames (32 MB)
+};
+
+__device__ __forceinline__ cplx<float> ld_l2(const cplx<float> *p)
+{
+    const float2 v = __ldcg(reinterpret_cast<const float2 *>(p));
+    return { v.x, v.y };
+}
+__device__ __forceinline__ cplx<double> ld_l2(const cplx<double> *p)
+{
+    const double2 v = __ldcg(reinterpret_cast<const double2 *>(p));
+    return { v.x, v.y };
+}
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void spin_until(const unsigned *ctr, unsigned target, unsigned seen) // one thread
+{
+    while (seen < target) {
+        __nanosleep(64);
+        seen = ld_acquire_gpu(ctr);
+    }
+}
+
+// decode work item q -> (column tile?, frame, tile); frame >= n_frames marks an empty slot
+template <int LAG, int TILES>
+__device__ __forceinline__ void fused_decode(size_t q, bool &cols, size_t &f, int &tile)
+{
+    const size_t slot = q / TILES;
+    tile = (int)(q % TILES);
+    if (slot < (size_t)LAG) {
+        cols = true;
+        f = slot;
+    } else {
+        const size_t u = slot - LAG;
+        cols = (u & 1) == 0;
+        f = cols ? LAG + u / 2 : u / 2;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256, sizeof(T) == 4 ? 3 : 1)
+    fft_fused64k_kernel(cplx<T> *__restrict__ data, const T *__restrict__ real_in, cplx<T> *__restrict__ scratch,
+                        const cplx<T> *__restrict__ tw, const cplx<T> *__restrict__ tw_hi, const cplx<T> *__restrict__ tw_lo,
+                        unsigned *__restrict__ ticket, unsigned *__restrict__ col_done, unsigned *__restrict__ row_done, size_t n_frames,
+                        int inverse, T scale, int prefetch)
+{
+    using Cfg = FftCfg<256, 16, 16, 16>;
+    constexpr int PITCH = LargeStride<Cfg>::value;
+    constexpr int N2 = 256, TILES = 16, LAG = FusedRing<T>::LAG, RING = FusedRing<T>::RING;
+    constexpr int MINB = sizeof(T) == 4 ? 3 : 1;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx<T> *xbuf = reinterpret_cast<cplx<T> *>(smem_raw);
+    cplx<T> *s_hi = xbuf + 16 * PITCH, *s_lo = s_hi + 256;
+    __shared__ unsigned s_ticket, s_ready;
+    s_hi[threadIdx.x] = tw_hi[threadIdx.x];
+    s_lo[threadIdx.x] = tw_lo[threadIdx.x];
+    const int lo16 = threadIdx.x & 15, hi16 = threadIdx.x >> 4;
+    const size_t total = ((size_t)LAG + 2 * n_frames) * TILES;
+
+    // Latency of the queue itself is kept off the critical path: thread 0 draws the NEXT ticket at the start of an item
+    // (the atomic's round trip overlaps the item), looks at the counter that item will depend on as soon as the ticket is
+    // back, and publishes both with the barrier that ends the item.
+    if (threadIdx.x == 0) {
+        const unsigned q0 = atomicAdd(ticket, 1u);
+        s_ticket = q0;
+        bool c0;
+        size_t f0;
+        int t0;
+        fused_decode<LAG, TILES>(q0, c0, f0, t0);
+        if (q0 < total && f0 < n_frames && !c0)
+            spin_until(col_done + f0, TILES, 0);
+    }
+    __syncthreads();
+    for (;;) {
+        const size_t q = s_ticket;
+        if (q >= total)
+            break;
+        unsigned nxt = 0;
+        if (threadIdx.x == 0)
+            nxt = atomicAdd(ticket, 1u);
+        bool cols;
+        size_t f;
+        int tile;
+        fused_decode<LAG, TILES>(q, cols, f, tile);
+        {   // whoever draws the item one round ahead will find its input in L2 (column tiles read HBM; row tiles read the ring)
+            bool pc;
+            size_t pf;
+            int pt;
+            fused_decode<LAG, TILES>(q + gridDim.x, pc, pf, pt);
+            if (prefetch && pc && pf < n_frames) {
+                const size_t off = pf * ((size_t)N2 * N2) + (size_t)threadIdx.x * N2 + 16 * pt;
+                if (real_in)
+                    prefetch_l2_bulk(real_in + off, 16 * (unsigned)sizeof(T));
+                else
+                    prefetch_l2_bulk(data + off, 16 * (unsigned)sizeof(cplx<T>));
+            }
+        }
+        cplx<T> *sc = scratch + (f % RING) * ((size_t)N2 * N2);
+        cplx<T> v[Cfg::E];
+        unsigned *done = nullptr;
+        if (f >= n_frames) {
+            __syncthreads(); // empty slot (column tiles past the last frame): everyone has read s_ticket before it is rewritten
+        } else if (cols) {
+            // ---- 16 columns b = 16 tile + lo16: 256-point transforms over a, times W_N^(b k1), to scratch [k1][b]
+            const int t = hi16;
+            const unsigned b = 16u * (unsigned)tile + (unsigned)lo16;
+            unsigned seen = TILES;
+            if (threadIdx.x == 0 && f >= (size_t)RING)
+                seen = ld_acquire_gpu(row_done + (f - RING)); // has the scratch slot's previous tenant been read out?
+            if (real_in) {
+                const T *rp = real_in + f * ((size_t)N2 * N2) + b;
+#pragma unroll
+                for (int e = 0; e < Cfg::E; e++)
+                    v[e] = cplx<T>{ __ldcs(rp + (size_t)(t + Cfg::S * e) * N2), (T)0 };
+            } else {
+                const cplx<T> *gp = data + f * ((size_t)N2 * N2) + b;
+#pragma unroll
+                for (int e = 0; e < Cfg::E; e++)
+                    v[e] = ld_stream(gp + (size_t)(t + Cfg::S * e) * N2);
+            }
+            if (inverse) {
+#pragma unroll
+                for (int e = 0; e < Cfg::E; e++)
+                    v[e] = cplx<T>{ v[e].y, v[e].x };
+            }
+            if (threadIdx.x == 0 && f >= (size_t)RING)
+                spin_until(row_done + (f - RING), TILES, seen);
+            // (the barrier inside the passes sits between thread 0's check above and every thread's stores below)
+            fft_kernel_passes<Cfg, T, 256, MINB, 0>(v, xbuf + (size_t)lo16 * PITCH, tw, t);
+            const TwiddleSeq<T> wseq(b * (unsigned)t, b * (unsigned)Cfg::S, s_hi, s_lo);
+            cplx<T> *op = sc + b;
+#pragma unroll
+            for (int e = 0; e < Cfg::E; e++)
+                op[(size_t)(t + Cfg::S * e) * N2] = cmul(v[e], wseq.get(e));
+            done = col_done + f;
+        } else {
+            // ---- 16 rows k1 = 16 tile + hi16: 256-point transforms over b out of scratch, stored to X[k1 + 256 k2]
+            // (col_done[f] was checked by thread 0 before the barrier that published this ticket)
+            const int t = lo16, row = hi16;
+            const cplx<T> *gp = sc + (size_t)(16 * tile + row) * N2 + t;
+#pragma unroll
+            for (int e = 0; e < Cfg::E; e++)
+                v[e] = ld_l2(gp + Cfg::S * e); // written by other SMs: read at L2, never from this SM's L1
+            cplx<T> *fs = xbuf + (size_t)row * PITCH;
+            fft_kernel_passes<Cfg, T, 256, MINB, 0>(v, fs, tw, t);
+            if (inverse) {
+#pragma unroll
+                for (int e = 0; e < Cfg::E; e++)
+                    v[e] = cplx<T>{ v[e].y * scale, v[e].x * scale };
+            }
+            __syncthreads(); // last pass has read the exchange buffer
+#pragma unroll
+            for (int e = 0; e < Cfg::E; e++)
+                fs[Cfg::pad(t + Cfg::S * e)] = v[e]; // natural order: slot e of thread t is k2 = t + 16 e
+            __syncthreads();
+            // transposed read: 16 consecutive lanes take the same k2 of 16 consecutive rows -> 128-byte runs over k1
+            const cplx<T> *rs = xbuf + (size_t)lo16 * PITCH;
+            cplx<T> *op = data + f * ((size_t)N2 * N2) + 16 * tile + lo16;
+#pragma unroll
+            for (int e = 0; e < Cfg::E; e++) {
+                const int k2 = hi16 + 16 * e;
+                st_stream(op + (size_t)k2 * N2, rs[Cfg::pad(k2)]);
+            }
+            done = row_done + f;
+        }
+        // ---- end of item: publish the next ticket (and that its dependency is met) with the barrier that also orders
+        // this item's stores before the completion count
+        const unsigned *dep = nullptr;
+        if (threadIdx.x == 0) {
+            s_ticket = nxt;
+            bool nc;
+            size_t nf;
+            int nt;
+            fused_decode<LAG, TILES>(nxt, nc, nf, nt);
+            if (nxt < total && nf < n_frames && !nc)
+                dep = col_done + nf;
+            s_ready = dep == nullptr || ld_acquire_gpu(dep) >= TILES; // (never spin here: this item is not counted yet)
+        }
+        __syncthreads();
+        if (threadIdx.x == 0 && done) {
+            __threadfence();
+            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(done) : "memory");
+        }
+        if (!s_ready) { // rare: the next item's column tiles are still running somewhere
+            if (threadIdx.x == 0)
+                spin_until(dep, TILES, 0);
+            __syncthreads();
+        }
+    }
+}
+
+// Prefetching the column tile one round ahead (256 bulk requests of 128 bytes per item) measured 5 % SLOWER here
+// (profiles/r01_fft65536_variants.txt): off unless SDSP_B200_FFT_FUSED_PREFETCH=1
+static bool fused_prefetch_enabled()
+{
+    static int on = -1;
+    if (on < 0) {
+        const char *e = getenv("SDSP_B200_FFT_FUSED_PREFETCH");
+        on = e ? atoi(e) : 0;
+    }
+    return on != 0;
+}
+
+template <typename T>
+static int launch_fused64k(const FftPlan &p, void *data, const void *real_in, size_t n_frames, cudaStream_t stream)
+{
+    if (n_frames == 0)
+        return SDSP_B200_OK;
+    // counters: [0] ticket, then col_done[n], row_done[n]; zeroed for every launch
+    const size_t need = (1 + 2 * n_frames) * sizeof(unsigned);
+    FftPlan &mp = const_cast<FftPlan &>(p);
+    if (mp.fused_counter_bytes < need) {
+        if (mp.d_fused_counters)
+            cudaFree(mp.d_fused_counters);
+        mp.d_fused_counters = nullptr;
+        mp.fused_counter_bytes = 0;
+        if (cudaMalloc(&mp.d_fused_counters, need) != cudaSuccess) {
+            cudaGetLastError();
+            return set_error(SDSP_B200_ERR_OOM, "fft: cannot allocate %zu bytes of work-queue counters", need);
+        }
+        mp.fused_counter_bytes = need;
+    }
+    SDSP_CUDA(cudaMemsetAsync(mp.d_fused_counters, 0, need, stream));
+    unsigned *ctr = static_cast<unsigned *>(mp.d_fused_counters);
+    const size_t items = ((size_t)FusedRing<T>::LAG + 2 * n_frames) * 16;
+    size_t grid = (size_t)p.sm_count * (size_t)p.ctas_per_sm;
+    if (grid > items)
+        grid = items;
+    fft_fused64k_kernel<T><<<(unsigned)grid, 256, p.smem_bytes, stream>>>(
+        reinterpret_cast<cplx<T> *>(data), static_cast<const T *>(real_in), reinterpret_cast<cplx<T> *>(p.d_scratch),
+        reinterpret_cast<const cplx<T> *>(p.d_tw_rows), reinterpret_cast<const cplx<T> *>(p.d_tw_hi), reinterpret_cast<const cplx<T> *>(p.d_tw_lo),
+        ctr, ctr + 1, ctr + 1 + n_frames, n_frames, p.direction == SDSP_B200_REVERSE ? 1 : 0, (T)(1.0 / 65536.0),
+        fused_prefetch_enabled() && reinterpret_cast<uintptr_t>(data) % 16 == 0 && reinterpret_cast<uintptr_t>(real_in) % 16 == 0 ? 1 : 0);
+    SDSP_CUDA(cudaGetLastError());
+    return SDSP_B200_OK;
+}
+
+template <typename T>
+static int setup_fused64k(FftPlan &p)
+{
+    using Cfg = FftCfg<256, 16, 16, 16>;
+    p.smem_bytes = ((size_t)16 * LargeStride<Cfg>::value + 512) * sizeof(cplx<T>);
+    auto kern = fft_fused64k_kernel<T>;
+    if (p.smem_bytes > 48 * 1024)
+        SDSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
+    int occ = 0;
+    SDSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, p.smem_bytes));
+    if (occ < 1)
+        return set_error(SDSP_B200_ERR_UNSUPPORTED, "fft: the fused 65536-point kernel does not fit on an SM");
+    p.ctas_per_sm = occ;
+    p.fused = true;
+    p.n1 = 256;
+    p.npass = 4;
+    p.e = 16;
+    p.threads = 256;
+    p.scratch_frames = FusedRing<T>::RING;
+    const size_t frame_bytes = (size_t)65536 * sizeof(cplx<T>);
+    if (cudaMalloc(&p.d_scratch, p.scratch_frames * frame_bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return set_error(SDSP_B200_ERR_OOM, "fft: cannot allocate %zu bytes of scratch", p.scratch_frames * frame_bytes);
+    }
+    std::vector<cplx<T>> tw;
+    int rb[4] = { 16, 16, 1, 1 };
+    build_twiddles<T>(256, rb, 2, tw);
+    int rc = upload_table<T>(&p.d_tw_rows, tw);
+    std::vector<cplx<T>> hi(256), lo(256);
+    for (int i = 0; i < 256; i++) {
+        long double re, im;
+        unit_root((uint64_t)i, (uint64_t)256, re, im);
+        hi[i] = cplx<T>{ (T)re, (T)im };
+        unit_root((uint64_t)i, (uint64_t)65536, re, im);
+        lo[i] = cplx<T>{ (T)re, (T)im };
+    }
+    if (!rc)
+        rc = upload_table<T>(&p.d_tw_hi, hi);
+    if (!rc)
+        rc = upload_table<T>(&p.d_tw_lo, lo);
+    if (rc)
+        return rc;
+    p.tw_bytes = (tw.size() + hi.size() + lo.size()) * sizeof(cplx<T>);
+    p.launch = &launch_fused64k<T>;
+    return SDSP_B200_OK;
+}
+
 // cluster size 8 (portable, measured best: profiles/r01_fft65536_cluster_sweep.txt); SDSP_B200_FFT_CLUSTER=16|162 selects the
 // 16-CTA variants (tuning aid)
 template <typename T>
@@ -830,8 +1135,15 @@ static int setup_cluster64k_auto(FftPlan &p)
 template <typename T>
 static int setup_large_n1(FftPlan &p)
 {
-    static const bool two_kernels = getenv("SDSP_B200_FFT_TWO_KERNEL") != nullptr; // comparison aid: the two-kernel path for n = 65536
-    if (p.n == 65536 && !two_kernels)
+    // n = 65536: SDSP_B200_FFT_65536=fused|cluster|twokernel (comparison aid)
+    static int which = -1;
+    if (which < 0) {
+        const char *e = getenv("SDSP_B200_FFT_65536");
+        which = !e ? 0 : !strcmp(e, "cluster") ? 1 : !strcmp(e, "twokernel") ? 2 : 0;
+    }
+    if (p.n == 65536 && which == 0)
+        return setup_fused64k<T>(p);
+    if (p.n == 65536 && which == 1)
         return setup_cluster64k_auto<T>(p);
     switch (p.n / 256) {
     case 64: return setup_large<FftCfg<64, 16, 16, 4>, T>(p);
@@ -995,7 +1307,7 @@ int sdsp_b200_fft_plan_create(sdsp_b200_fft_plan *plan, uint32_t n, int radix, i
     h->p.sm_count = device_sm_count(device);
     rc = setup_plan(h->p);
     if (rc) {
-        for (void *q : { h->p.d_tw, h->p.d_tw_cols, h->p.d_tw_rows, h->p.d_tw_hi, h->p.d_tw_lo, h->p.d_scratch })
+        for (void *q : { h->p.d_tw, h->p.d_tw_cols, h->p.d_tw_rows, h->p.d_tw_hi, h->p.d_tw_lo, h->p.d_scratch, h->p.d_fused_counters })
             if (q)
                 cudaFree(q);
         delete h;
@@ -1014,7 +1326,7 @@ int sdsp_b200_fft_plan_destroy(sdsp_b200_fft_plan plan)
         cudaFree(plan->p.d_tw);
     if (plan->p.d_stage)
         cudaFree(plan->p.d_stage);
-    for (void *q : { plan->p.d_tw_cols, plan->p.d_tw_rows, plan->p.d_tw_hi, plan->p.d_tw_lo, plan->p.d_scratch })
+    for (void *q : { plan->p.d_tw_cols, plan->p.d_tw_rows, plan->p.d_tw_hi, plan->p.d_tw_lo, plan->p.d_scratch, plan->p.d_fused_counters })
         if (q)
             cudaFree(q);
     delete plan;
@@ -1149,6 +1461,16 @@ int sdsp_b200_fft_plan_describe(sdsp_b200_fft_plan plan, char *buf, size_t buf_l
     if (!plan || !buf || buf_len == 0)
         return set_error(SDSP_B200_ERR_INVALID_ARG, "fft_plan_describe: bad arguments");
     const FftPlan &p = plan->p;
+    if (p.fused) {
+        snprintf(buf, buf_len,
+                 "fft n=%u %s %s radix-arg=%d: one persistent kernel, single pass over HBM: per frame 16 column tiles (16 columns x 256-point "
+                 "transforms, twiddle) -> ring of %zu scratch frames resident in L2 -> 16 row tiles (16 rows x 256-point transforms, "
+                 "transposed store), ordered by an atomic work queue with per-frame completion counters; 256 threads/CTA, smem/CTA=%zuB, "
+                 "CTAs/SM=%d, SMs=%d",
+                 p.n, p.precision == SDSP_B200_F32 ? "f32" : "f64", p.direction == SDSP_B200_FORWARD ? "forward" : "reverse", p.radix,
+                 p.scratch_frames, p.smem_bytes, p.ctas_per_sm, p.sm_count);
+        return SDSP_B200_OK;
+    }
     if (p.cluster) {
         snprintf(buf, buf_len,
                  "fft n=%u %s %s radix-arg=%d: one frame per %d-CTA thread-block cluster, single pass over HBM: 256 column transforms "
