@@ -259,3 +259,37 @@ def test_scan_few_channels_each_split_along_time(prec, how):
     # the bank history continues the stream: next block through the sequential kernel
     st = bank.get_state()
     assert np.isfinite(st).all()
+
+
+def test_config4_scale_single_channel_time_split_against_the_sequential_kernel():
+    """BASELINE config 4 at 1/16 scale (one fp64 channel of 2^26 samples): the time-split path against the
+    sequential kernel on the same stream (the oracle pins the sequential kernel; a 2^26-sample stream through the
+    scalar CPU oracle would dominate the suite), plus the oracle itself on windows of the stream re-run from the
+    history the GPU left at their start."""
+    torch = pytest.importorskip("torch")
+    n = 1 << 26
+    g, b, a = S.design(1, 4, 10e3, 100e3)
+    gen = torch.Generator(device="cuda").manual_seed(4)
+    x = torch.randn(1, n, device="cuda", dtype=torch.float64, generator=gen)
+    seq = S.IirBank(4, 1, K.F64)
+    seq.set_coeffs([g], [b], [a])
+    split = S.IirBank(4, 1, K.F64)
+    split.set_coeffs([g], [b], [a])
+    assert "time-split" in split.describe(n, n, K.IIR_SCAN)
+    y_seq, y_split = x.clone(), x.clone()
+    seq.process_ptr(y_seq.data_ptr(), n, n, K.PTR_DEVICE, K.IIR_SEQUENTIAL, torch.cuda.current_stream().cuda_stream)
+    split.process_ptr(y_split.data_ptr(), n, n, K.PTR_DEVICE, K.IIR_SCAN, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    peak = float(y_seq.abs().max())
+    assert float((y_seq - y_split).abs().max()) / peak <= IIR_TOL["f64"]
+    assert np.abs(seq.get_state() - split.get_state()).max() / peak <= IIR_TOL["f64"]
+    # oracle on two windows: the head of the stream, and a window deep inside it warmed up over 4096 samples
+    f = O.Iir(4)
+    f.design(1, 10e3, 100e3, 1.1)
+    head = f.process(x[0, :65536].cpu().numpy())
+    assert peak_rel(y_split[0, :65536].cpu().numpy(), head) <= IIR_TOL["f64"]
+    lo = (n // 2) + 12345
+    f2 = O.Iir(4)
+    f2.design(1, 10e3, 100e3, 1.1)
+    mid = f2.process(x[0, lo - 4096: lo + 65536].cpu().numpy())[4096:]  # 4096 samples >> the filter's memory (~450)
+    assert peak_rel(y_split[0, lo: lo + 65536].cpu().numpy(), mid) <= IIR_TOL["f64"]

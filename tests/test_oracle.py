@@ -159,3 +159,23 @@ def test_iir_gain_and_preload():
         y = f.process(np.full(1024, 10.0))
         assert np.abs(y - (10.0 if ftype == 1 else 0.0)).max() < 1e-12
         assert np.array_equal(y, ref_vectors()[f"iir_preload_t{ftype}"])
+
+
+def test_scipy_fixture_generator_reproduces_the_reference_fixtures():
+    """tools/make_fixtures.py restates the reference's Octave recipe (test_data/WriteImpulse.m, findIIRCutoffFreq.m) with
+    scipy; it must regenerate the nine golden impulse responses, and its CSV writer / parser must round-trip the
+    reference's one-line wire format (test/testIIR.cpp:7-28)."""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+    from tools import make_fixtures as M
+
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "impulse_response.npz"))
+    for name in z["names"]:
+        hd, h = z[str(name) + "_header"], z[str(name) + "_h"]
+        kind = {1: "lp", 2: "hp", 3: "bp"}[int(hd[0])]
+        got = M.impulse_response(kind, hd[1], hd[2], hd[3], 8, int(hd[4]))
+        assert np.abs(got - h).max() <= 1e-12 * np.abs(h).max(), name
+        t, fs, f0, q, back = M.parse_csv_line(M.csv_line(kind, hd[1], hd[2], hd[3], got))
+        assert (t, fs, f0, q) == (int(hd[0]), hd[1], hd[2], hd[3]) and np.allclose(back, got, rtol=1e-14, atol=0)
