@@ -49,6 +49,11 @@ WORKLOADS = {
     "pipeline65536_f32": dict(kind="pipeline", channels=512, frames_per_channel=64, n=65536, precision="f32", sections=4,
                               bytes_per_sample=20),
     "iir16384_f32_scan": dict(kind="iir", channels=16384, samples=1 << 20, precision="f32", sections=4, bytes_per_sample=8, path="scan"),
+    # same bank, channel pitch not a power of two (2^20 + 8256 samples): separates DRAM channel effects from kernel effects
+    "iir16384_f32_pitch": dict(kind="iir", channels=16384, samples=1 << 20, pitch=(1 << 20) + 8256, precision="f32", sections=4,
+                               bytes_per_sample=8),
+    # 18944 channels = 592 warps = exactly four row-warps on every one of the 148 SMs (16384 channels leave 3 or 4 per SM)
+    "iir18944_f32": dict(kind="iir", channels=18944, samples=1 << 20, precision="f32", sections=4, bytes_per_sample=8),
     "iir16384_f64": dict(kind="iir", channels=16384, samples=1 << 19, precision="f64", sections=4, bytes_per_sample=16),
 }
 
@@ -136,10 +141,35 @@ def dist_setup(n_gpus: int):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     else:
         torch.cuda.set_device(local)
+    bind_to_gpu_numa_node(local)
     if n_gpus != world:
         if rank == 0:
             print(f"warning: --gpus {n_gpus} but WORLD_SIZE={world}; using {world}", file=sys.stderr)
     return rank, local, world
+
+
+_ORIGINAL_AFFINITY = None
+
+
+def bind_to_gpu_numa_node(index: int):
+    """Pin this rank to the CPUs NVML reports as local to its GPU, before any pinned host memory is allocated or
+    touched: the end-to-end leg moves 4 GiB per step over PCIe per rank, and with 8 ranks the staging buffers must
+    not all land on one socket."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            global _ORIGINAL_AFFINITY
+            _ORIGINAL_AFFINITY = os.sched_getaffinity(0)
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass  # no NVML / not permitted: keep the inherited affinity
 
 
 def barrier(world):
@@ -268,15 +298,16 @@ class IirWorkload:
             gains[c], bs[c], as_[c] = uniq[key]
         self.bank.set_coeffs(gains, bs, as_)
         g = torch.Generator(device="cuda").manual_seed(1234 + device)
-        self.data = torch.empty(self.ch, self.n, device="cuda", dtype=self.rdtype)
-        rows = max(1, (1 << 28) // self.n)
+        self.pitch = spec.get("pitch", self.n)
+        self.data = torch.empty(self.ch, self.pitch, device="cuda", dtype=self.rdtype)
+        rows = max(1, (1 << 28) // self.pitch)
         for lo in range(0, self.ch, rows):
             self.data[lo:lo + rows].normal_(generator=g)
         self.samples_per_step = self.ch * self.n
         self.stream = torch.cuda.current_stream().cuda_stream
 
     def describe(self):
-        return self.bank.describe(self.n, self.n, self.path)
+        return self.bank.describe(self.n, self.pitch, self.path)
 
     def launches_per_step(self):
         return 1  # the bandwidth-bound pass: all the algorithmic bytes go through one launch
@@ -286,7 +317,7 @@ class IirWorkload:
         return 4 if "time-split" in self.describe() else 1
 
     def step(self):
-        self.bank.process_ptr(self.data.data_ptr(), self.n, self.n, self.K.PTR_DEVICE, self.path, self.stream)
+        self.bank.process_ptr(self.data.data_ptr(), self.n, self.pitch, self.K.PTR_DEVICE, self.path, self.stream)
 
     def self_check(self):
         self.torch.cuda.synchronize()
@@ -538,6 +569,8 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
+        if _ORIGINAL_AFFINITY:
+            os.sched_setaffinity(0, _ORIGINAL_AFFINITY)  # the CPU baseline uses every host core
         r = cpu_reference_rate(spec, os.cpu_count() or 1)
         cpu = {"value": r[0], "unit": "Msamples/s", "cores": r[2], "kind": r[1], "sample": r[3], "single_thread": r[4]}
 

@@ -31,6 +31,10 @@ namespace
     {
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
     }
+    __device__ __forceinline__ void mbar_arrive(uint64_t *bar) // release at CTA scope: orders this thread's earlier writes
+    {
+        asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+    }
     __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
     {
         asm volatile(

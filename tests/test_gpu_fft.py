@@ -130,7 +130,7 @@ def test_device_pointer_path_and_full_size_properties():
     fwd(y)
     torch.cuda.synchronize()
     # sampled frames against the oracle
-    idx = torch.linspace(0, frames - 1, 64).long()
+    idx = torch.linspace(0, frames - 1, 256).long()  # parity on >= 256 frames spread across the batch
     ref = oracle_fft(xc[idx].cpu().numpy())
     assert rel_l2(y[idx].cpu().numpy(), ref) <= FFT_TOL["f32"]
     # Parseval on every frame: sum |X|^2 = N sum |x|^2

@@ -293,3 +293,84 @@ def test_config4_scale_single_channel_time_split_against_the_sequential_kernel()
     f2.design(1, 10e3, 100e3, 1.1)
     mid = f2.process(x[0, lo - 4096: lo + 65536].cpu().numpy())[4096:]  # 4096 samples >> the filter's memory (~450)
     assert peak_rel(y_split[0, lo: lo + 65536].cpu().numpy(), mid) <= IIR_TOL["f64"]
+
+
+def test_config3_full_size_sampled_parity_both_paths():
+    """BASELINE config 3 at full size -- 16384 channels x 2^20 fp32 samples, planar, in place (64 GiB): even channels
+    low-pass, odd channels high-pass, f0 log-spaced 1-20 kHz at fs = 100 kHz.  Parity against the oracle on channels
+    spread across the bank: the head of 64 channels, 8 whole channels, and the history left behind (the stream is
+    continued on both sides).  First the bit-exact-streaming path, then the time-split path over the same buffer again
+    (its input is the first pass's output)."""
+    torch = pytest.importorskip("torch")
+    torch.cuda.empty_cache()
+    free, _ = torch.cuda.mem_get_info()
+    ch, n, fs, head = 16384, 1 << 20, 100e3, 1 << 16
+    if free < (ch * n * 4) * 1.05:
+        pytest.skip("needs 68 GB of free device memory")
+    ftype = np.where(np.arange(ch) % 2 == 0, 1, 2)
+    f0 = np.geomspace(1e3, 20e3, ch)
+    coef = [S.design(int(t), 4, float(f), fs) for t, f in zip(ftype, f0)]
+    bank = S.IirBank(4, ch, K.F32)
+    bank.set_coeffs(np.array([c[0] for c in coef]), np.array([c[1] for c in coef]), np.array([c[2] for c in coef]))
+    gen = torch.Generator(device="cuda").manual_seed(1234)
+    data = torch.empty(ch, n, device="cuda", dtype=torch.float32)
+    for lo in range(0, ch, 256):
+        data[lo:lo + 256].normal_(generator=gen)
+    idx = np.linspace(0, ch - 1, 64).astype(int)
+    whole = idx[::8]
+    d_idx, d_whole = torch.from_numpy(idx).cuda(), torch.from_numpy(whole).cuda()
+    x_head = data[d_idx, :head].cpu().numpy().astype(np.float64)
+    x_whole = data[d_whole].cpu().numpy().astype(np.float64)
+    stream = torch.cuda.current_stream().cuda_stream
+    filters = None
+    for path, want_plan in ((K.IIR_AUTO, "sequential/tma"), (K.IIR_SCAN, "time-split")):
+        assert want_plan in bank.describe(n, n, path)
+        bank.reset_state()
+        bank.process_ptr(data.data_ptr(), n, n, K.PTR_DEVICE, path, stream)
+        torch.cuda.synchronize()
+        got_head = data[d_idx, :head].cpu().numpy()
+        assert peak_rel(got_head, O.iir_bank_port(x_head, ftype[idx], f0[idx], fs)) <= IIR_TOL["f32"], path
+        filters = []
+        got_whole = data[d_whole].cpu().numpy()
+        for j, c in enumerate(whole):
+            f = O.Iir(4)
+            f.design(int(ftype[c]), float(f0[c]), fs, 1.1)
+            assert peak_rel(got_whole[j], f.process(x_whole[j])) <= IIR_TOL["f32"], (path, c)
+            filters.append(f)  # keeps the history of this pass
+        x_head, x_whole = got_head.astype(np.float64), got_whole.astype(np.float64)  # what the next pass filters
+    # the history the time-split pass left in the bank continues the stream like the oracle's
+    tail = f32_noise(np.random.default_rng(8), (len(whole), 4096))
+    block = torch.zeros(ch, 4096, device="cuda", dtype=torch.float32)
+    block[d_whole] = torch.from_numpy(tail.astype(np.float32)).cuda()
+    bank.process_ptr(block.data_ptr(), 4096, 4096, K.PTR_DEVICE, K.IIR_AUTO, stream)
+    torch.cuda.synchronize()
+    got_tail = block[d_whole].cpu().numpy()
+    for j in range(len(whole)):
+        assert peak_rel(got_tail[j], filters[j].process(tail[j])) <= 10 * IIR_TOL["f32"], whole[j]
+
+
+def test_config4_full_size_windows_against_the_oracle():
+    """BASELINE config 4 at full size: one fp64 channel of 2^30 samples (8 GiB) through the time-split path; windows
+    of the output against the oracle run from 8192 samples before each window (18 x the filter's memory of ~450
+    samples, so the oracle's zero start has decayed below 1e-70 of its state by the time the window begins)."""
+    torch = pytest.importorskip("torch")
+    torch.cuda.empty_cache()
+    n, win, warm = 1 << 30, 1 << 16, 8192
+    g, b, a = S.design(1, 4, 10e3, 100e3)
+    gen = torch.Generator(device="cuda").manual_seed(1234)
+    x = torch.empty(1, n, device="cuda", dtype=torch.float64)
+    for lo in range(0, n, 1 << 27):
+        x[:, lo:lo + (1 << 27)].normal_(generator=gen)
+    starts = [0, (n // 3) + 777, n - win]
+    x_win = [x[0, max(0, s0 - warm): s0 + win].cpu().numpy() for s0 in starts]
+    bank = S.IirBank(4, 1, K.F64)
+    bank.set_coeffs([g], [b], [a])
+    assert "time-split" in bank.describe(n, n, K.IIR_SCAN)
+    bank.process_ptr(x.data_ptr(), n, n, K.PTR_DEVICE, K.IIR_SCAN, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(x[0, :: 4099]).all())
+    for s0, xin in zip(starts, x_win):
+        f = O.Iir(4)
+        f.design(1, 10e3, 100e3, 1.1)
+        ref = f.process(xin)[-win:]
+        assert peak_rel(x[0, s0: s0 + win].cpu().numpy(), ref) <= IIR_TOL["f64"], s0
