@@ -353,11 +353,15 @@ SDSP_HD void iir_tile_skewed_x2(const IirCoef<float, M> &c, IirState<float, M> &
     }
 }
 
-template <typename T, int M, int KIND, int TS, typename Load, typename Store>
+// PACK (fp32 only): two sections per instruction with fma.rn.f32x2.  Same operations, same bits either way; which is
+// faster depends on what bounds the kernel -- packed halves the instruction count (wins when many warps share an SM
+// and issue slots are the limit), scalar has twice the independent instructions in flight per warp (wins when a warp
+// is alone on its scheduler and latency is the limit).  profiles/r01_iir_pack_vs_scalar.txt
+template <typename T, int M, int KIND, int TS, bool PACK = true, typename Load, typename Store>
 SDSP_HD void iir_tile_dispatch(const IirCoef<T, M> &c, IirState<T, M> &s, Load &&load, Store &&store)
 {
 #ifndef SDSP_IIR_NOPACK
-    if constexpr (sizeof(T) == 4 && M % 2 == 0)
+    if constexpr (sizeof(T) == 4 && M % 2 == 0 && PACK)
         iir_tile_skewed_x2<M, KIND, TS>(c, s, load, store);
     else
 #endif

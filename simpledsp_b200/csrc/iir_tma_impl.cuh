@@ -35,7 +35,7 @@ namespace sdsp_b200
 //                ADDED to the samples already there (the natural-response correction of a segment)
 enum : int { ROWS_PLAIN = 0, ROWS_SEG = 1, ROWS_SEG_ACC = 2 };
 
-template <typename T, int M, int KIND, int SUB, int CSUB, int NST, int PF, int WARPS, int RG, int MODE>
+template <typename T, int M, int KIND, int SUB, int CSUB, int NST, int PF, int WARPS, int RG, int MODE, bool PACK = true>
 __global__ void __launch_bounds__(WARPS * 32)
     iir_tma_kernel(const __grid_constant__ CUtensorMap map, int n_samples, const T *__restrict__ coef, T *__restrict__ state,
                    size_t n_channels, size_t n_coef_channels, unsigned seg_per_ch)
@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(WARPS * 32)
             const int rem = remaining - ct * CTS;
             if (rem >= CTS) {
                 V vin, vout;
-                iir_tile_dispatch<T, M, KIND, CTS>(
+                iir_tile_dispatch<T, M, KIND, CTS, PACK>(
                     c, st,
                     [&](int i) -> T {
                         if constexpr (MODE == ROWS_SEG_ACC)
@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(WARPS * 32)
     }
 }
 
-template <typename T, int M, int KIND, int SUB, int CSUB, int NST, int PF, int WARPS, int RG>
+template <typename T, int M, int KIND, int SUB, int CSUB, int NST, int PF, int WARPS, int RG, bool PACK = true>
 static int launch_tma_cfg(const IirBank &b, void *data, size_t n_samples, size_t stride, cudaStream_t stream, int promo)
 {
     constexpr int TSB = 128 / (int)sizeof(T);
@@ -239,7 +239,7 @@ static int launch_tma_cfg(const IirBank &b, void *data, size_t n_samples, size_t
     if (r != CUDA_SUCCESS)
         return set_error(SDSP_B200_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d (n_samples=%zu channels=%zu pitch=%llu)", (int)r, n_samples,
                          b.n_channels, (unsigned long long)pitch);
-    auto kern = iir_tma_kernel<T, M, KIND, SUB, CSUB, NST, PF, WARPS, RG, ROWS_PLAIN>;
+    auto kern = iir_tma_kernel<T, M, KIND, SUB, CSUB, NST, PF, WARPS, RG, ROWS_PLAIN, PACK>;
     constexpr size_t smem = (size_t)WARPS * NST * SUB * 32 * 128;
     static bool configured = false;
     if (!configured) {
@@ -617,8 +617,20 @@ static int launch_tma(const IirBank &b, void *data, size_t n_samples, size_t str
                 return launch_tma_pipe<T, M, KIND, 4, 2, 4>(b, data, n_samples, stride, stream);
         }
     }
-    // single-warp CTAs, 8-row boxes (measured best of the sweep in profiles/r01_iir_tma_config_sweep.txt)
-    return launch_tma_cfg<T, M, KIND, 2, 2, 6, 3, 1, 8>(b, data, n_samples, stride, stream, promo);
+    // single-warp CTAs, 8-row boxes (measured best of the sweep in profiles/r01_iir_tma_config_sweep.txt).  fp32: scalar
+    // arithmetic while the bank leaves schedulers to spare (a warp alone on its scheduler is latency-bound), packed once
+    // every SM holds its four warps; SDSP_B200_IIR_PACK=0|1 pins the choice (comparison aid).  Same bits either way.
+    if constexpr (sizeof(T) == 4) {
+        static int pin = -2;
+        if (pin == -2) {
+            const char *e = getenv("SDSP_B200_IIR_PACK");
+            pin = e ? atoi(e) : -1;
+        }
+        const bool pack = pin >= 0 ? pin != 0 : (b.n_channels + 31) / 32 >= (size_t)b.sm_count * 4;
+        if (!pack)
+            return launch_tma_cfg<T, M, KIND, 2, 2, 6, 3, 1, 8, false>(b, data, n_samples, stride, stream, promo);
+    }
+    return launch_tma_cfg<T, M, KIND, 2, 2, 6, 3, 1, 8, true>(b, data, n_samples, stride, stream, promo);
 }
 
 template <typename T, int M>
