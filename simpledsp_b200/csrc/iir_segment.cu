@@ -8,8 +8,8 @@
 // (row 0 of the reference's m_mem), c the two last outputs of every section (rows 1..m) --
 //       response(x; u, c) = response(x; u, 0)  +  response(0; 0, c).
 // The second term is the filter's natural response: it decays like |pole|^n.  Let K be the number of samples
-// after which the one-step transition matrix of the cascade, raised to the n-th power, is below 2^-70 (fp64) /
-// 2^-40 (fp32) in every entry -- five decimal orders below one ulp of anything it is added to.  Cut each
+// after which the one-step transition matrix of the cascade, raised to the n-th power, is below 2^-62 (fp64) /
+// 2^-32 (fp32) in every entry -- 2^-9 (fp64) / 2^-8 (fp32) of one ulp of a value as large as the state it multiplies.  Cut each
 // channel into `segs` segments of seg_len >= K samples.  Then
 //   1. seg_gather: every segment learns its incoming scaled-input history u from the two samples before it
 //      (read before anything is overwritten: the filter runs in place); segment 0 takes the bank's history;
@@ -125,7 +125,7 @@ unsigned long long iir_decay_length(IirBank &b)
 {
     if (b.decay_version == b.coef_version && b.decay_len_valid)
         return b.decay_len;
-    const double negligible = b.precision == SDSP_B200_F32 ? 9.0949470177292824e-13 /* 2^-40 */ : 8.4703294725430034e-22 /* 2^-70 */;
+    const double negligible = b.precision == SDSP_B200_F32 ? 2.3283064365386963e-10 /* 2^-32 */ : 2.1684043449710089e-19 /* 2^-62 */;
     unsigned long long worst = 1;
     const int m = b.sections;
     // identical coefficient sets are common in a bank (bench: a few thousand distinct designs): memoise the last one
