@@ -24,7 +24,6 @@ struct IirBank {
     unsigned long scan_tables_version = ~0ul;
     int scan_chunk = 0;
     int scan_reach_max = 0;
-    int scan_chunk_request = 0;
     unsigned scan_epoch = 0;
     void *d_scan_flags = nullptr;
     size_t scan_flags_bytes = 0;

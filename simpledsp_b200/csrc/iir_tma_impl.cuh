@@ -518,13 +518,7 @@ static int launch_rows_ring(const IirBank &b, void *data, size_t seg_len, size_t
     if constexpr (M == 4 && KIND == NUM_GENERIC) { // alternatives exist for the headline instantiations only
         switch (rows_tune()) { //                                         SUB CSUB NST PF   ring per warp
         case 1: return launch_rows_cfg<T, M, KIND, MODE, 2, 2, 4, 2>(b, data, seg_len, segs, stride, row_state, n_samples, stream, slots); // 32 KB
-        case 2: return launch_rows_cfg<T, M, KIND, MODE, 1, 1, 8, 4>(b, data, seg_len, segs, stride, row_state, n_samples, stream, slots); // 32 KB
-        case 3: return launch_rows_cfg<T, M, KIND, MODE, 1, 1, 6, 3>(b, data, seg_len, segs, stride, row_state, n_samples, stream, slots); // 24 KB
-        case 4: return launch_rows_cfg<T, M, KIND, MODE, 2, 2, 5, 2>(b, data, seg_len, segs, stride, row_state, n_samples, stream, slots); // 40 KB
         case 5: return launch_rows_cfg<T, M, KIND, MODE, 2, 2, 6, 3>(b, data, seg_len, segs, stride, row_state, n_samples, stream, slots); // 48 KB
-        case 6: return launch_rows_cfg<T, M, KIND, MODE, 2, 2, 2, 1>(b, data, seg_len, segs, stride, row_state, n_samples, stream, slots); // 16 KB
-        case 7: return launch_rows_cfg<T, M, KIND, MODE, 4, 2, 3, 1>(b, data, seg_len, segs, stride, row_state, n_samples, stream, slots); // 48 KB
-        case 8: return launch_rows_cfg<T, M, KIND, MODE, 4, 2, 2, 1>(b, data, seg_len, segs, stride, row_state, n_samples, stream, slots); // 32 KB
         default: break;
         }
     }
@@ -567,39 +561,11 @@ static int launch_rows_sections(const IirBank &b, void *data, size_t seg_len, si
     }
 }
 
-// SDSP_B200_IIR_TUNE="<config>,<l2 promotion bytes>": kernel-tuning aid; the extra configurations exist only for
-// the headline instantiation (fp32, 4 sections, generic numerator)
-static void tma_tune(int &cfg, int &promo)
-{
-    static int c = -1, p = 128;
-    if (c < 0) {
-        c = 0;
-        if (const char *e = getenv("SDSP_B200_IIR_TUNE"))
-            sscanf(e, "%d,%d", &c, &p);
-    }
-    cfg = c;
-    promo = p;
-}
-
 template <typename T, int M, int KIND>
 static int launch_tma(const IirBank &b, void *data, size_t n_samples, size_t stride, cudaStream_t stream)
 {
-    int cfg, promo;
-    tma_tune(cfg, promo);
-    if constexpr (sizeof(T) == 4 && M == 4 && KIND == NUM_GENERIC) {
-        switch (cfg) { //                                       SUB CSUB NST PF WARPS RG
-        case 1: return launch_tma_cfg<T, M, KIND, 2, 2, 6, 3, 4, 8>(b, data, n_samples, stride, stream, promo);
-        case 2: return launch_tma_cfg<T, M, KIND, 4, 2, 3, 2, 4, 8>(b, data, n_samples, stride, stream, promo);
-        case 3: return launch_tma_cfg<T, M, KIND, 4, 2, 4, 2, 1, 8>(b, data, n_samples, stride, stream, promo);
-        case 4: return launch_tma_cfg<T, M, KIND, 4, 2, 3, 2, 1, 8>(b, data, n_samples, stride, stream, promo);
-        case 5: return launch_tma_cfg<T, M, KIND, 8, 2, 3, 2, 1, 8>(b, data, n_samples, stride, stream, promo);
-        case 6: return launch_tma_cfg<T, M, KIND, 4, 2, 3, 2, 1, 32>(b, data, n_samples, stride, stream, promo);
-        case 7: return launch_tma_cfg<T, M, KIND, 2, 2, 6, 3, 4, 32>(b, data, n_samples, stride, stream, promo);
-        case 8: return launch_tma_cfg<T, M, KIND, 8, 2, 2, 1, 1, 8>(b, data, n_samples, stride, stream, promo);
-        default: break;
-        }
-    }
-    if constexpr (M >= 4) { // SDSP_B200_IIR_PIPE=1..4: the section-pipelined kernel (bit-identical output).  Measured slower than the
+    const int promo = 128; // TMA L2 promotion bytes (64 / 256 measured equal, profiles/r01_iir_tma_config_sweep.txt)
+    if constexpr (M >= 4) { // SDSP_B200_IIR_PIPE=1: the section-pipelined kernel (bit-identical output).  Measured slower than the
                             // single-warp kernel once the recurrence was shortened to one FMA (profiles/r01_iir_pipe_vs_single.txt): off.
         static int pipe = -1;
         if (pipe < 0) {
@@ -608,14 +574,6 @@ static int launch_tma(const IirBank &b, void *data, size_t n_samples, size_t str
         }
         if (pipe == 1)
             return launch_tma_pipe<T, M, KIND, 2, 2, 6>(b, data, n_samples, stride, stream);
-        if constexpr (M == 4 && KIND == NUM_GENERIC) {
-            if (pipe == 2)
-                return launch_tma_pipe<T, M, KIND, 2, 2, 5>(b, data, n_samples, stride, stream);
-            if (pipe == 3)
-                return launch_tma_pipe<T, M, KIND, 2, 2, 4>(b, data, n_samples, stride, stream);
-            if (pipe == 4)
-                return launch_tma_pipe<T, M, KIND, 4, 2, 4>(b, data, n_samples, stride, stream);
-        }
     }
     // single-warp CTAs, 8-row boxes (measured best of the sweep in profiles/r01_iir_tma_config_sweep.txt).  fp32: scalar
     // arithmetic while the bank leaves schedulers to spare (a warp alone on its scheduler is latency-bound), packed once
