@@ -176,6 +176,11 @@ int sdsp_b200_debug_emulate_iir(int sections, int numerator, int precision, doub
 int sdsp_b200_debug_emulate_iir_scan(int sections, int numerator, int precision, double gain, const double *b,
                                      const double *a, double *mem, void *data, size_t n_samples,
                                      int chunk, int force_general);
+/* Host only.  The memory of one cascade as the time-split IIR path sees it: the number of samples after which every entry
+ * of the n-th power of its one-step transition matrix (zero input) is below 2^-32 (f32) / 2^-62 (f64); 0 = it never decays
+ * (unstable or marginal filter).  Segments of a time-split call are at least this long. */
+int sdsp_b200_debug_iir_decay_length(int sections, int numerator, int precision, const double *b, const double *a,
+                                     unsigned long long *samples);
 
 #ifdef __cplusplus
 }

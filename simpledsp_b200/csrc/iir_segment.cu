@@ -120,12 +120,17 @@ static unsigned long long decay_length_one(int m, int kind, const double *b, con
     return n + 1;
 }
 
+static double negligible_for(int precision)
+{
+    return precision == SDSP_B200_F32 ? 2.3283064365386963e-10 /* 2^-32 */ : 2.1684043449710089e-19 /* 2^-62 */;
+}
+
 // the bank's decay length: the slowest channel's, with a margin; cached per coefficient version
 unsigned long long iir_decay_length(IirBank &b)
 {
     if (b.decay_version == b.coef_version && b.decay_len_valid)
         return b.decay_len;
-    const double negligible = b.precision == SDSP_B200_F32 ? 2.3283064365386963e-10 /* 2^-32 */ : 2.1684043449710089e-19 /* 2^-62 */;
+    const double negligible = negligible_for(b.precision);
     unsigned long long worst = 1;
     const int m = b.sections;
     // identical coefficient sets are common in a bank (bench: a few thousand distinct designs): memoise the last one
@@ -316,6 +321,13 @@ int iir_launch_segmented(IirBank &b, void *data, size_t n_samples, size_t stride
     return SDSP_B200_OK;
 }
 
+// host only (no device): the memory of one filter in samples, as the planner sees it (0 = does not decay)
+unsigned long long iir_decay_length_of(int sections, int numerator, int precision, const double *b, const double *a)
+{
+    const unsigned long long d = decay_length_one(sections, numerator, b, a, negligible_for(precision));
+    return d ? d + d / 8 + 16 : 0; // the same margin the bank-wide figure carries (the envelope of the response is not monotonic)
+}
+
 int iir_segment_describe(IirBank &b, size_t n_samples, char *buf, size_t buf_len)
 {
     size_t segs = 0, seg_len = 0, corr = 0;
@@ -327,3 +339,16 @@ int iir_segment_describe(IirBank &b, size_t n_samples, char *buf, size_t buf_len
     return 0;
 }
 } // namespace sdsp_b200
+
+using namespace sdsp_b200;
+
+// verification aid (host only): samples after which the natural response of a cascade is below the time-split path's threshold
+extern "C" int sdsp_b200_debug_iir_decay_length(int sections, int numerator, int precision, const double *b, const double *a,
+                                                unsigned long long *samples)
+{
+    if (!a || !samples || sections < 1 || sections > 8 || numerator < 0 || numerator > 3 || (numerator == NUM_GENERIC && !b) ||
+        (precision != SDSP_B200_F32 && precision != SDSP_B200_F64))
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "debug_iir_decay_length: bad argument");
+    *samples = iir_decay_length_of(sections, numerator, precision, b, a);
+    return SDSP_B200_OK;
+}
