@@ -228,7 +228,7 @@ def test_time_split_algorithm_on_the_host(case):
             carry = mem[1:].copy()  # the section history this segment ended with (zero-state run)
             y[s_ * seg:(s_ + 1) * seg] = part
         peak = np.abs(whole).max()
-        # fp32 at f0/fs = 0.005: the plain fp32 recurrence is itself 1e-4 of peak from the truth there, and the two
-        # evaluation orders round differently -- the bound is the IIR tolerance, as for the sequential fp32 kernel
-        tol = 1e-12 if pname == "f64" else (3 * IIR_TOL["f32"] if f0 < 1e3 else 2e-6)
+        # fp64: the two computations agree to rounding.  fp32: they round differently (y0 + correction vs one recurrence), and a
+        # low-cutoff fp32 recurrence is itself up to 1e-4 of peak from the truth -- the bound is the IIR tolerance
+        tol = 1e-12 if pname == "f64" else (3 * IIR_TOL["f32"] if f0 < 1e3 else IIR_TOL["f32"])
         assert np.abs(y - whole).max() / peak <= tol, (case, pname)
