@@ -1039,8 +1039,12 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 3 : 1)
                 op[(size_t)(t + Cfg::S * e) * N2] = cmul(v[e], wseq.get(e));
             done = col_done + f;
         } else {
-            // ---- 16 rows k1 = 16 tile + hi16: 256-point transforms over b out of scratch, stored to X[k1 + 256 k2]
+            // ---- 16 rows k1 = 16 tile + r: 256-point transforms over b out of scratch, stored to X[k1 + 256 k2]
             // (col_done[f] was checked by thread 0 before the barrier that published this ticket)
+            // The first pass runs with lanes along b (thread = (t, row): coalesced 128-byte reads of the ring); the exchange
+            // between the passes also re-maps the threads, so the second pass runs with lanes along the rows
+            // (thread = (row, t)) and its natural-order outputs X[k1 + 256 (t + 16 e)] leave as 128-byte runs over k1 --
+            // no separate transposing step.
             const int t = lo16, row = hi16;
             const cplx<T> *gp = sc + (size_t)(16 * tile + row) * N2 + t;
 #pragma unroll
@@ -1048,26 +1052,27 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 3 : 1)
                 v[e] = ld_l2(gp + Cfg::S * e); // written by other SMs: read at L2, never from this SM's L1
             if (STAGE && staged_next)
                 stage_tile(nf_s, nt_s); // (a row tile holds nothing in the staging slots)
+            fft_pass<Cfg, 0, T>(v, t, tw);
             cplx<T> *fs = xbuf + (size_t)row * PITCH;
-            fft_kernel_passes<Cfg, T, 256, MINB, 0>(v, fs, tw, t);
+#pragma unroll
+            for (int e = 0; e < Cfg::E; e++)
+                fs[fft_out_phys<Cfg, 0>(t, e)] = v[e];
+            __syncthreads();
+            const int row2 = lo16, t2 = hi16;
+            const cplx<T> *rs = xbuf + (size_t)row2 * PITCH;
+#pragma unroll
+            for (int e = 0; e < Cfg::E; e++)
+                v[e] = rs[fft_read_phys<Cfg>(t2, e)];
+            fft_pass<Cfg, 1, T>(v, t2, tw);
             if (inverse) {
 #pragma unroll
                 for (int e = 0; e < Cfg::E; e++)
                     v[e] = cplx<T>{ v[e].y * scale, v[e].x * scale };
             }
-            __syncthreads(); // last pass has read the exchange buffer
+            cplx<T> *op = data + f * ((size_t)N2 * N2) + 16 * tile + row2;
 #pragma unroll
             for (int e = 0; e < Cfg::E; e++)
-                fs[Cfg::pad(t + Cfg::S * e)] = v[e]; // natural order: slot e of thread t is k2 = t + 16 e
-            __syncthreads();
-            // transposed read: 16 consecutive lanes take the same k2 of 16 consecutive rows -> 128-byte runs over k1
-            const cplx<T> *rs = xbuf + (size_t)lo16 * PITCH;
-            cplx<T> *op = data + f * ((size_t)N2 * N2) + 16 * tile + lo16;
-#pragma unroll
-            for (int e = 0; e < Cfg::E; e++) {
-                const int k2 = hi16 + 16 * e;
-                st_stream(op + (size_t)k2 * N2, rs[Cfg::pad(k2)]);
-            }
+                st_stream(op + (size_t)(t2 + Cfg::S * e) * N2, v[e]); // natural order: slot e of thread t2 is k2 = t2 + 16 e
             done = row_done + f;
         }
         // ---- end of item: publish the ticket drawn during it, and whether the item that comes next has its dependency met,
