@@ -259,7 +259,6 @@ struct FftPlan {
     // multi-pass ("four-step") path for frames larger than one CTA can hold: n = n1 * 256
     bool large = false;
     bool cluster = false; // n = 65536: one frame per 8-CTA cluster, single pass over HBM
-    bool fused_stage = false;
     bool fused = false;   // n = 65536: column and row tiles in one persistent kernel, intermediate in an L2-resident ring
     void *d_fused_counters = nullptr;
     size_t fused_counter_bytes = 0;
@@ -864,36 +863,14 @@ __device__ __forceinline__ void fused_decode(size_t q, bool &cols, size_t &f, in
     }
 }
 
-__device__ __forceinline__ void cp_async_bytes(void *smem_dst, const void *gsrc, int bytes) // 4 or 8 bytes, this thread's own slot
-{
-    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-    if (bytes == 4)
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
-    else if (bytes == 8)
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
-    else
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit()
-{
-    asm volatile("cp.async.commit_group;" ::: "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all()
-{
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-}
-
-// STAGE: the input of the NEXT column tile is copied from HBM into a thread-private shared-memory slot (cp.async, no
-// registers, no barrier: a thread stages exactly the 16 elements it will transform) while the current item is being
-// computed, so a column tile never waits for HBM.  That needs the queue to run two tickets ahead: the item in hand, the
-// next one (known to every thread at the start of an item) and the one thread 0 is drawing.  Row tiles read the
-// L2-resident ring directly (other SMs wrote it: L2-only loads, not cp.async.ca).
-template <typename T, bool STAGE>
+// Variants measured and dropped (profiles/r01_fft65536_variants.txt): L2 prefetch of the column tile one round ahead, cp.async
+// staging of the next column tile, a separate transposing step in the row tiles, a single barrier per item.
+template <typename T>
 __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 3 : 1)
     fft_fused64k_kernel(cplx<T> *__restrict__ data, const T *__restrict__ real_in, cplx<T> *__restrict__ scratch,
                         const cplx<T> *__restrict__ tw, const cplx<T> *__restrict__ tw_hi, const cplx<T> *__restrict__ tw_lo,
                         unsigned *__restrict__ ticket, unsigned *__restrict__ col_done, unsigned *__restrict__ row_done, size_t n_frames,
-                        int inverse, T scale, int prefetch)
+                        int inverse, T scale)
 {
     using Cfg = FftCfg<256, 16, 16, 16>;
     constexpr int PITCH = LargeStride<Cfg>::value;
@@ -902,39 +879,19 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 3 : 1)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx<T> *xbuf = reinterpret_cast<cplx<T> *>(smem_raw);
     cplx<T> *s_hi = xbuf + 16 * PITCH, *s_lo = s_hi + 256;
-    cplx<T> *stage = s_lo + 256; // STAGE: [16][256] elements, slot [e][thread]
     __shared__ unsigned s_ticket, s_ready;
     s_hi[threadIdx.x] = tw_hi[threadIdx.x];
     s_lo[threadIdx.x] = tw_lo[threadIdx.x];
     const int lo16 = threadIdx.x & 15, hi16 = threadIdx.x >> 4;
     const size_t total = ((size_t)LAG + 2 * n_frames) * TILES;
 
-    // copies of one column tile's input, element (row hi16 + 16 e, column 16 tile + lo16) -> slot [e][thread]
-    auto stage_tile = [&](size_t f, int tile) {
-        const size_t off = f * ((size_t)N2 * N2) + 16u * (unsigned)tile + (unsigned)lo16;
-        if (real_in) {
-            const T *rp = real_in + off;
-#pragma unroll
-            for (int e = 0; e < Cfg::E; e++)
-                cp_async_bytes(reinterpret_cast<T *>(stage + e * 256 + threadIdx.x), rp + (size_t)(hi16 + Cfg::S * e) * N2, (int)sizeof(T));
-        } else {
-            const cplx<T> *gp = data + off;
-#pragma unroll
-            for (int e = 0; e < Cfg::E; e++)
-                cp_async_bytes(stage + e * 256 + threadIdx.x, gp + (size_t)(hi16 + Cfg::S * e) * N2, (int)sizeof(cplx<T>));
-        }
-        cp_async_commit();
-    };
-
     // Latency of the queue itself is kept off the critical path: thread 0 draws tickets ahead of their use (the atomic's
     // round trip overlaps an item), looks at the counter the coming item depends on as soon as its ticket is back, and
     // publishes both with the barrier that ends the item.
-    size_t q = 0, q_next = 0; // item in hand; STAGE: the one after it
+    size_t q = 0; // item in hand
     if (threadIdx.x == 0) {
         const unsigned q0 = atomicAdd(ticket, 1u);
         s_ticket = q0;
-        if (STAGE)
-            s_ready = atomicAdd(ticket, 1u); // (borrowed as the second mailbox until the loop starts)
         bool c0;
         size_t f0;
         int t0;
@@ -944,16 +901,6 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 3 : 1)
     }
     __syncthreads();
     q = s_ticket;
-    if (STAGE) {
-        q_next = s_ready;
-        bool c0;
-        size_t f0;
-        int t0;
-        fused_decode<LAG, TILES>(q, c0, f0, t0);
-        if (q < total && c0 && f0 < n_frames)
-            stage_tile(f0, t0);
-        __syncthreads(); // everyone has read the mailboxes before thread 0 reuses them
-    }
     for (;;) {
         if (q >= total)
             break;
@@ -964,33 +911,10 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 3 : 1)
         size_t f;
         int tile;
         fused_decode<LAG, TILES>(q, cols, f, tile);
-        if (!STAGE) { // whoever draws the item one round ahead will find its input in L2
-            bool pc;
-            size_t pf;
-            int pt;
-            fused_decode<LAG, TILES>(q + gridDim.x, pc, pf, pt);
-            if (prefetch && pc && pf < n_frames) {
-                const size_t off = pf * ((size_t)N2 * N2) + (size_t)threadIdx.x * N2 + 16 * pt;
-                if (real_in)
-                    prefetch_l2_bulk(real_in + off, 16 * (unsigned)sizeof(T));
-                else
-                    prefetch_l2_bulk(data + off, 16 * (unsigned)sizeof(cplx<T>));
-            }
-        }
         cplx<T> *sc = scratch + (f % RING) * ((size_t)N2 * N2);
         cplx<T> v[Cfg::E];
         unsigned *done = nullptr;
-        bool staged_next = false;
-        size_t nf_s = 0;
-        int nt_s = 0;
-        if (STAGE) {
-            bool nc;
-            fused_decode<LAG, TILES>(q_next, nc, nf_s, nt_s);
-            staged_next = q_next < total && nc && nf_s < n_frames;
-        }
         if (f >= n_frames) {
-            if (STAGE && staged_next)
-                stage_tile(nf_s, nt_s);
             __syncthreads(); // empty slot (column tiles past the last frame): everyone has read the mailbox before it is rewritten
         } else if (cols) {
             // ---- 16 columns b = 16 tile + lo16: 256-point transforms over a, times W_N^(b k1), to scratch [k1][b]
@@ -999,20 +923,7 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 3 : 1)
             unsigned seen = TILES;
             if (threadIdx.x == 0 && f >= (size_t)RING)
                 seen = ld_acquire_gpu(row_done + (f - RING)); // has the scratch slot's previous tenant been read out?
-            if (STAGE) {
-                cp_async_wait_all(); // this thread's own 16 slots
-                if (real_in) {
-#pragma unroll
-                    for (int e = 0; e < Cfg::E; e++)
-                        v[e] = cplx<T>{ *reinterpret_cast<const T *>(stage + e * 256 + threadIdx.x), (T)0 };
-                } else {
-#pragma unroll
-                    for (int e = 0; e < Cfg::E; e++)
-                        v[e] = stage[e * 256 + threadIdx.x];
-                }
-                if (staged_next)
-                    stage_tile(nf_s, nt_s); // (after this thread has emptied its slots)
-            } else if (real_in) {
+            if (real_in) {
                 const T *rp = real_in + f * ((size_t)N2 * N2) + b;
 #pragma unroll
                 for (int e = 0; e < Cfg::E; e++)
@@ -1050,8 +961,6 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 3 : 1)
 #pragma unroll
             for (int e = 0; e < Cfg::E; e++)
                 v[e] = ld_l2(gp + Cfg::S * e); // written by other SMs: read at L2, never from this SM's L1
-            if (STAGE && staged_next)
-                stage_tile(nf_s, nt_s); // (a row tile holds nothing in the staging slots)
             fft_pass<Cfg, 0, T>(v, t, tw);
             cplx<T> *fs = xbuf + (size_t)row * PITCH;
 #pragma unroll
@@ -1077,7 +986,7 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 3 : 1)
         }
         // ---- end of item: publish the ticket drawn during it, and whether the item that comes next has its dependency met,
         // with the barrier that also orders this item's stores before the completion count
-        const size_t coming = STAGE ? q_next : (size_t)drawn; // (thread 0's view; other threads learn `drawn` from the mailbox)
+        const size_t coming = drawn; // (thread 0's view; the other threads learn it from the mailbox)
         const unsigned *dep = nullptr;
         if (threadIdx.x == 0) {
             s_ticket = drawn;
@@ -1099,27 +1008,8 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 3 : 1)
                 spin_until(dep, TILES, 0);
             __syncthreads();
         }
-        if (STAGE) {
-            q = q_next;
-            q_next = s_ticket;
-        } else {
-            q = s_ticket;
-        }
+        q = s_ticket;
     }
-    if (STAGE)
-        cp_async_wait_all();
-}
-
-// Prefetching the column tile one round ahead (256 bulk requests of 128 bytes per item) measured 5 % SLOWER here
-// (profiles/r01_fft65536_variants.txt): off unless SDSP_B200_FFT_FUSED_PREFETCH=1
-static bool fused_prefetch_enabled()
-{
-    static int on = -1;
-    if (on < 0) {
-        const char *e = getenv("SDSP_B200_FFT_FUSED_PREFETCH");
-        on = e ? atoi(e) : 0;
-    }
-    return on != 0;
 }
 
 template <typename T>
@@ -1147,12 +1037,10 @@ static int launch_fused64k(const FftPlan &p, void *data, const void *real_in, si
     size_t grid = (size_t)p.sm_count * (size_t)p.ctas_per_sm;
     if (grid > items)
         grid = items;
-    auto kern = p.fused_stage ? fft_fused64k_kernel<T, true> : fft_fused64k_kernel<T, false>;
-    kern<<<(unsigned)grid, 256, p.smem_bytes, stream>>>(
+    fft_fused64k_kernel<T><<<(unsigned)grid, 256, p.smem_bytes, stream>>>(
         reinterpret_cast<cplx<T> *>(data), static_cast<const T *>(real_in), reinterpret_cast<cplx<T> *>(p.d_scratch),
         reinterpret_cast<const cplx<T> *>(p.d_tw_rows), reinterpret_cast<const cplx<T> *>(p.d_tw_hi), reinterpret_cast<const cplx<T> *>(p.d_tw_lo),
-        ctr, ctr + 1, ctr + 1 + n_frames, n_frames, p.direction == SDSP_B200_REVERSE ? 1 : 0, (T)(1.0 / 65536.0),
-        fused_prefetch_enabled() && reinterpret_cast<uintptr_t>(data) % 16 == 0 && reinterpret_cast<uintptr_t>(real_in) % 16 == 0 ? 1 : 0);
+        ctr, ctr + 1, ctr + 1 + n_frames, n_frames, p.direction == SDSP_B200_REVERSE ? 1 : 0, (T)(1.0 / 65536.0));
     SDSP_CUDA(cudaGetLastError());
     return SDSP_B200_OK;
 }
@@ -1161,17 +1049,8 @@ template <typename T>
 static int setup_fused64k(FftPlan &p)
 {
     using Cfg = FftCfg<256, 16, 16, 16>;
-    static int stage = -1;
-    if (stage < 0) {
-        // 1: column-tile input staged with cp.async one item ahead.  Measured SLOWER than loading straight into registers
-        // (2.42 vs 2.83 TB/s, profiles/r01_fft65536_variants.txt): the kernel is bound by its instruction stream, not by
-        // HBM latency.  Kept as a comparison aid.
-        const char *e = getenv("SDSP_B200_FFT_FUSED_STAGE");
-        stage = e ? atoi(e) : 0;
-    }
-    p.fused_stage = stage != 0;
-    p.smem_bytes = ((size_t)16 * LargeStride<Cfg>::value + 512 + (p.fused_stage ? 16 * 256 : 0)) * sizeof(cplx<T>);
-    auto kern = p.fused_stage ? fft_fused64k_kernel<T, true> : fft_fused64k_kernel<T, false>;
+    p.smem_bytes = ((size_t)16 * LargeStride<Cfg>::value + 512) * sizeof(cplx<T>);
+    auto kern = fft_fused64k_kernel<T>;
     if (p.smem_bytes > 48 * 1024)
         SDSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
     int occ = 0;
