@@ -33,6 +33,11 @@ struct IirBank {
     bool decay_len_valid = false;
     void *d_seg_state = nullptr;
     size_t seg_state_bytes = 0;
+    struct SegPlanMemo {
+        bool valid = false, ok = false, first_round = false;
+        unsigned long coef_version = 0;
+        size_t n_samples = 0, segs = 0, seg_len = 0, corr = 0;
+    } seg_plan_memo[2];
     // host staging
     void *d_stage = nullptr;
     size_t stage_bytes = 0;

@@ -203,9 +203,22 @@ __global__ void seg_carry_kernel(const T *__restrict__ row_state, unsigned segs,
 // SDSP_B200_SEG_ROWS=<rows> (tuning aid) pins segs = rows / channels instead.
 bool iir_segment_plan(IirBank &b, size_t n_samples, bool first_round, size_t *segs_out, size_t *seg_len_out, size_t *corr_out)
 {
+    // the search below is a pure function of (coefficients, n_samples, first_round): remember the last two answers
+    for (auto &m : b.seg_plan_memo)
+        if (m.valid && m.coef_version == b.coef_version && m.n_samples == n_samples && m.first_round == first_round) {
+            *segs_out = m.segs;
+            *seg_len_out = m.seg_len;
+            *corr_out = m.corr;
+            return m.ok;
+        }
+    auto remember = [&](bool ok, size_t segs, size_t seg_len, size_t corr) {
+        auto &m = b.seg_plan_memo[first_round ? 0 : 1];
+        m = { true, ok, first_round, b.coef_version, n_samples, segs, seg_len, corr };
+        return ok;
+    };
     const unsigned long long K = iir_decay_length(b);
     if (K == 0)
-        return false;
+        return remember(false, 0, 0, 0);
     const size_t es = b.precision == SDSP_B200_F32 ? 4 : 8;
     const size_t align = 128 / es; // segment starts stay 128-byte aligned relative to the channel start
     const size_t cts = 2 * (128 / es); // the row kernel's compute tile
@@ -214,7 +227,7 @@ bool iir_segment_plan(IirBank &b, size_t n_samples, bool first_round, size_t *se
     const size_t min_len = first_round ? (corr * 4 > 1024 ? corr * 4 : 1024) : corr;
     const size_t max_segs = n_samples / min_len / 8 * 8;
     if (max_segs < 8)
-        return false;
+        return remember(false, 0, 0, 0);
     static long pinned = -1;
     if (pinned < 0) {
         const char *e = getenv("SDSP_B200_SEG_ROWS");
@@ -242,14 +255,14 @@ bool iir_segment_plan(IirBank &b, size_t n_samples, bool first_round, size_t *se
         }
     }
     if (best < 8)
-        return false;
+        return remember(false, 0, 0, 0);
     const size_t seg_len = n_samples / best / align * align;
     if (seg_len < corr || seg_len >= (1ull << 31))
-        return false;
+        return remember(false, 0, 0, 0);
     *segs_out = best;
     *seg_len_out = seg_len;
     *corr_out = corr;
-    return true;
+    return remember(true, best, seg_len, corr);
 }
 
 bool iir_segment_applicable(IirBank &b, const void *data, size_t n_samples, size_t stride)
