@@ -37,6 +37,11 @@ WORKLOADS = {
     "fft4096_f64": dict(kind="fft", n=4096, frames=65536, precision="f64", bytes_per_sample=32),
     "fft65536_f32": dict(kind="fft", n=65536, frames=4096, precision="f32", bytes_per_sample=16),
     "fft1024_f32": dict(kind="fft", n=1024, frames=262144, precision="f32", bytes_per_sample=16),
+    "fft256_f32": dict(kind="fft", n=256, frames=1 << 20, precision="f32", bytes_per_sample=16),
+    "fft64_f32": dict(kind="fft", n=64, frames=1 << 22, precision="f32", bytes_per_sample=16),
+    "fft16384_f32": dict(kind="fft", n=16384, frames=16384, precision="f32", bytes_per_sample=16),
+    "fft8192_f32": dict(kind="fft", n=8192, frames=32768, precision="f32", bytes_per_sample=16),
+    "fft2048_f32": dict(kind="fft", n=2048, frames=131072, precision="f32", bytes_per_sample=16),
     "iir16384_f32": dict(kind="iir", channels=16384, samples=1 << 20, precision="f32", sections=4, bytes_per_sample=8),
     "iir4096_f32": dict(kind="iir", channels=4096, samples=1 << 22, precision="f32", sections=4, bytes_per_sample=8),
     "iir4096_f32_scan": dict(kind="iir", channels=4096, samples=1 << 22, precision="f32", sections=4, bytes_per_sample=8, path="scan"),

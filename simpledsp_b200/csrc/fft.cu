@@ -1165,7 +1165,7 @@ SDSP_FFT_CFG(9, 256, 3, 512, 16, 16, 16, 2)
 SDSP_FFT_CFG(10, 256, 3, 1024, 16, 16, 16, 4)
 SDSP_FFT_CFG(11, 256, 3, 2048, 16, 16, 16, 8)
 SDSP_FFT_CFG(12, 256, 3, 4096, 16, 16, 16, 16)
-SDSP_FFT_CFG(13, 512, 1, 8192, 16, 16, 16, 16, 2)
+SDSP_FFT_CFG(13, 512, 2, 8192, 16, 16, 16, 16, 2)
 SDSP_FFT_CFG(14, 1024, 1, 16384, 16, 16, 16, 16, 4)
 #undef SDSP_FFT_CFG
 
@@ -1203,7 +1203,7 @@ static int setup_for(FftPlan &p)
     if (p.precision == SDSP_B200_F32)
         return setup_cta<typename C::type, float, C::THREADS, C::MINB>(p);
     if constexpr (LG <= MAX_LOG2N_F64)
-        return setup_cta<typename C::type, double, C::THREADS, (C::MINB > 2 ? 2 : C::MINB)>(p);
+        return setup_cta<typename C::type, double, C::THREADS, (LG == 13 ? 1 : (C::MINB > 2 ? 2 : C::MINB))>(p); // (8192 points fp64: 128 registers, one CTA)
     else
         return set_error(SDSP_B200_ERR_UNSUPPORTED, "fft: n=%u in f64 is larger than one CTA can hold and the multi-pass path is not built", p.n);
 }
