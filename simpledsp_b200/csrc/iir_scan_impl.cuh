@@ -522,8 +522,10 @@ static int launch_scan_cfg(IirBank &b, void *data, size_t n_samples, size_t stri
 
     auto kern = iir_scan_kernel<T, M, KIND, L, WARPS, RG, ONE_CH>;
     constexpr size_t smem = (size_t)WARPS * (size_t)(L / TSB) * 32 * 128 + (size_t)(ONE_CH ? 1 : WARPS) * (((size_t)TAB * sizeof(T) + 15) / 16 * 16);
-    static bool configured = false;
-    static int occ = 1;
+    static bool configured_dev[64] = {};
+    static int occ_dev[64] = {};
+    bool &configured = configured_dev[b.device & 63]; // (the attribute is per device; a process may hold banks on several)
+    int &occ = occ_dev[b.device & 63];
     if (!configured) {
         SDSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SDSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WARPS * 32, smem));

@@ -241,7 +241,8 @@ static int launch_tma_cfg(const IirBank &b, void *data, size_t n_samples, size_t
                          b.n_channels, (unsigned long long)pitch);
     auto kern = iir_tma_kernel<T, M, KIND, SUB, CSUB, NST, PF, WARPS, RG, ROWS_PLAIN, PACK>;
     constexpr size_t smem = (size_t)WARPS * NST * SUB * 32 * 128;
-    static bool configured = false;
+    static bool configured_dev[64] = {};
+    bool &configured = configured_dev[b.device & 63]; // (the attribute is per device; a process may hold banks on several)
     if (!configured) {
         SDSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
@@ -448,7 +449,8 @@ static int launch_tma_pipe(const IirBank &b, void *data, size_t n_samples, size_
                          b.n_channels, (unsigned long long)pitch);
     auto kern = iir_tma_pipe_kernel<T, M, KIND, SUB, CSUB, NST>;
     constexpr size_t smem = (size_t)NST * SUB * 32 * 128;
-    static bool configured = false;
+    static bool configured_dev[64] = {};
+    bool &configured = configured_dev[b.device & 63]; // (the attribute is per device; a process may hold banks on several)
     if (!configured) {
         SDSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
@@ -479,8 +481,10 @@ static int launch_rows_cfg(const IirBank &b, void *data, size_t seg_len, size_t 
     constexpr int TSB = 128 / (int)sizeof(T);
     auto kern = iir_tma_kernel<T, M, KIND, SUB, CSUB, NST, PF, WARPS, RG, MODE>;
     constexpr size_t smem = (size_t)WARPS * NST * SUB * 32 * 128;
-    static bool configured = false;
-    static int occ = 0;
+    static bool configured_dev[64] = {};
+    static int occ_dev[64] = {};
+    bool &configured = configured_dev[b.device & 63]; // (the attribute is per device; a process may hold banks on several)
+    int &occ = occ_dev[b.device & 63];
     if (!configured) {
         SDSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SDSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WARPS * 32, smem));

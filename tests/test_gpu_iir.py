@@ -5,7 +5,7 @@ import pytest
 import simpledsp_b200 as S
 from oracle import oracle as O
 from simpledsp_b200 import _capi as K
-from tests.util import IIR_GOLDEN_ABS, IIR_TOL, f32_noise, golden_impulses, peak_rel, ref_vectors
+from tests.util import IIR_GOLDEN_ABS, IIR_TOL, f32_noise, golden_impulses, peak_rel, ref_vectors, rel_l2
 
 pytestmark = pytest.mark.gpu
 PREC = {"f64": (K.F64, np.float64), "f32": (K.F32, np.float32)}
@@ -374,3 +374,40 @@ def test_config4_full_size_windows_against_the_oracle():
         f.design(1, 10e3, 100e3, 1.1)
         ref = f.process(xin)[-win:]
         assert peak_rel(x[0, s0: s0 + win].cpu().numpy(), ref) <= IIR_TOL["f64"], s0
+
+
+def test_banks_and_plans_on_two_devices_in_one_process():
+    """One process, two GPUs: kernel attributes (dynamic shared memory) are per device, handles are bound to the device
+    they were created on.  Skipped on a single-GPU box."""
+    torch = pytest.importorskip("torch")
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    rng = np.random.default_rng(3)
+    g, b, a = S.design(1, 4, 10e3, 100e3)
+    x = f32_noise(rng, (40, 6000))
+    f = [O.Iir(4) for _ in range(40)]
+    ref = np.empty_like(x)
+    for c in range(40):
+        f[c].design(1, 10e3, 100e3, 1.1)
+        ref[c] = f[c].process(x[c])
+    z = (rng.standard_normal((8, 4096)) + 1j * rng.standard_normal((8, 4096))).astype(np.complex64)
+    zref = np.fft.fft(z.astype(np.complex128))
+    for dev in (1, 0, 1):
+        with torch.cuda.device(dev):
+            bank = S.IirBank(4, 40, K.F32, K.NUM_GENERIC, dev)
+            bank.set_coeffs(np.full(40, g), np.tile(b, (40, 1, 1)), np.tile(a, (40, 1, 1)))
+            d = torch.from_numpy(x.astype(np.float32)).cuda(dev)
+            bank.process(d)
+            torch.cuda.synchronize(dev)
+            assert peak_rel(d.cpu().numpy(), ref) <= IIR_TOL["f32"], dev
+            long = torch.from_numpy(np.tile(x[:1].astype(np.float32), (1, 40))).cuda(dev)  # 1 channel x 240000: time-split
+            one = S.IirBank(4, 1, K.F32, K.NUM_GENERIC, dev)
+            one.set_coeffs([g], [b], [a])
+            one.process_ptr(long.data_ptr(), long.shape[1], long.shape[1], K.PTR_DEVICE, K.IIR_SCAN, torch.cuda.current_stream(dev).cuda_stream)
+            torch.cuda.synchronize(dev)
+            assert bool(torch.isfinite(long).all())
+            plan = S.FftPlan(4096, 4, K.F32, K.FORWARD, dev)
+            zd = torch.from_numpy(z).cuda(dev)
+            plan(zd)
+            torch.cuda.synchronize(dev)
+            assert rel_l2(zd.cpu().numpy(), zref) <= 1e-5, dev
