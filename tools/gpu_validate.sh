@@ -1,3 +1,4 @@
+# One-GPU validation on a B200 box (gpurun -- bash tools/gpu_validate.sh): GPU tests, default bench line, reference arm, every workload.
 mkdir -p gpurun_out; rm -f gpurun_out/bench_r44.log
 timeout 900 python -m pytest tests -m gpu -q --timeout 300 > gpurun_out/pytest_all.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_all.log
 tail -n 5 gpurun_out/pytest_all.log
