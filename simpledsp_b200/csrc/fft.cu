@@ -819,7 +819,10 @@ static int setup_cluster64k(FftPlan &p)
 //   at items with smaller tickets, which are held by CTAs that are already running: no deadlock, whatever the residency.
 template <typename T>
 struct FusedRing {
-    static constexpr int LAG = sizeof(T) == 4 ? 32 : 16;  // frames between a frame's column tiles and its row tiles
+#ifndef SDSP_FUSED_LAG
+#define SDSP_FUSED_LAG 32
+#endif
+    static constexpr int LAG = sizeof(T) == 4 ? SDSP_FUSED_LAG : SDSP_FUSED_LAG / 2;  // frames between a frame's column tiles and its row tiles
     static constexpr int RING = 2 * LAG;                   // scratch frames (32 MB)
 };
 
