@@ -4,8 +4,8 @@
 //
 // Data layout in HBM is the reference's: one contiguous range per channel, data[channel*stride + n].
 // A lane-per-channel kernel therefore wants a [32 channels x TS samples] patch transposed on chip.  The
-// TMA engine does that for free: a 2-D tensor map over (samples, channels) with a box of 32 rows x 128
-// bytes and SWIZZLE_128B lands each channel's 128-byte run in its own shared-memory row, XOR-swizzled so
+// TMA engine does that for free: a 2-D tensor map over (samples, channels) with boxes of 8 rows x 128
+// bytes (four per 32 channels) and SWIZZLE_128B lands each channel's 128-byte run in its own shared-memory row, XOR-swizzled so
 // that lane r reading 16-byte chunk c of row r (LDS.128 at r*128 + ((c ^ (r&7))<<4)) is conflict free.
 // Every warp runs its own ring of stages with its own mbarriers -- no block-wide synchronisation -- and
 // writes results back with TMA stores from the same buffers (the filter runs in place, as in the
