@@ -587,7 +587,8 @@ def main():
         wl.data = None
         del wl
         torch.cuda.empty_cache()
-        for name in ("iir16384_f32", "iir16384_f32_scan"):
+        # config 3 on the bit-exact streaming path and on the time-split path, and north_star's ">= 4096 channels" point
+        for name in ("iir16384_f32", "iir16384_f32_scan", "iir4096_f32_scan"):
             sp = dict(WORKLOADS[name])
             w2, r2 = measure(name, sp, 5)
             secondary.append({"workload": name, "metric": "Msamples/s", "value": r2["value"], "ms_per_step": r2["ms_per_step"],
