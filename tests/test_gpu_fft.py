@@ -212,3 +212,35 @@ def test_real_input_frames_match_oracle(n, prec):
     plan(z)
     torch.cuda.synchronize()
     assert torch.equal(z, yd)
+
+
+@pytest.mark.parametrize("frames", [1, 2, 31, 32, 33, 63, 64, 65, 127, 129, 200])
+def test_fused_65536_kernel_at_the_edges_of_its_work_queue(frames):
+    """The 65536-point kernel orders column and row tiles through a queue with a 32-frame lag and a 64-frame scratch ring
+    (fp32): frame counts below, at and just past those boundaries, forward and reverse, complex and real input."""
+    torch = pytest.importorskip("torch")
+    n = 65536
+    g = torch.Generator(device="cuda").manual_seed(frames)
+    x = torch.view_as_complex(torch.randn(frames, n, 2, device="cuda", generator=g, dtype=torch.float32))
+    fwd, inv = S.FftPlan(n, 4, K.F32, K.FORWARD), S.FftPlan(n, 4, K.F32, K.REVERSE)
+    y = x.clone()
+    fwd(y)
+    torch.cuda.synchronize()
+    idx = sorted({0, frames // 2, frames - 1, min(31, frames - 1), min(64, frames - 1)})
+    ref = oracle_fft(x[idx].cpu().numpy())
+    assert rel_l2(y[idx].cpu().numpy(), ref) <= FFT_TOL["f32"]
+    # every frame: Parseval, then the round trip
+    e_t = (x.abs() ** 2).sum(dim=1, dtype=torch.float64)
+    e_f = (y.abs() ** 2).sum(dim=1, dtype=torch.float64) / n
+    assert float(((e_t - e_f).abs() / e_t).max()) < 1e-5
+    inv(y)
+    torch.cuda.synchronize()
+    err = (y - x).abs().pow(2).sum(dim=1).sqrt() / x.abs().pow(2).sum(dim=1).sqrt()
+    assert float(err.max()) <= 2 * FFT_TOL["f32"]
+    # real input, out of place: same bits as the complex entry point fed (x, 0)
+    xr = x.real.contiguous()
+    z = torch.complex(xr, torch.zeros_like(xr)).contiguous()
+    fwd(z)
+    out = fwd.real(xr)
+    torch.cuda.synchronize()
+    assert torch.equal(z, out)
