@@ -58,7 +58,8 @@ enum sdsp_b200_iir_path {
     SDSP_B200_IIR_AUTO = 0,       /* pure function of the bank configuration, never of call length alone */
     SDSP_B200_IIR_SEQUENTIAL = 1, /* lane per channel, samples in order; bit-identical however a stream is cut into calls */
     SDSP_B200_IIR_SCAN = 2,       /* time axis split into chunks that carry boundary state (reassociates; fp64 error ~1e-13 of peak):
-                                     the time-split kernel when the filter's memory fits a segment, else the look-back scan */
+                                     the time-split kernel when the filter's memory fits a segment, else the look-back scan; where neither
+                                     applies (call too short for the filter, unsuitable layout) the sequential kernels */
     SDSP_B200_IIR_SCAN_LOOKBACK = 3, /* force the look-back scan kernel (any stable filter) */
     SDSP_B200_IIR_SCAN_SPLIT = 4     /* force the time-split kernel (error if the filter's memory is too long for the call) */
 };

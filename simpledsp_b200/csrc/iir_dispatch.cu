@@ -27,10 +27,16 @@ static bool iir_use_tma(const IirBank &b, const void *data, size_t n_samples, si
 
 int iir_dispatch(IirBank &b, void *data, size_t n_samples, size_t stride, int path, cudaStream_t stream)
 {
-    // time-parallel: the time-split path when the filter's memory fits a segment, else the look-back scan
-    if (path == SDSP_B200_IIR_SCAN)
-        return iir_segment_applicable(b, data, n_samples, stride) ? iir_launch_segmented(b, data, n_samples, stride, stream) :
-                                                                    iir_launch_scan(b, data, n_samples, stride, stream);
+    // time-parallel: the time-split path when the filter's memory fits a segment of this call, else the look-back scan where
+    // the layout allows it, else (call too short to split, or an unsuitable layout) the sequential kernels -- the request is
+    // for speed, the result is the same stream either way
+    if (path == SDSP_B200_IIR_SCAN) {
+        if (iir_segment_applicable(b, data, n_samples, stride))
+            return iir_launch_segmented(b, data, n_samples, stride, stream);
+        if (iir_scan_applicable(b, data, n_samples, stride))
+            return iir_launch_scan(b, data, n_samples, stride, stream);
+        path = SDSP_B200_IIR_AUTO;
+    }
     if (path == SDSP_B200_IIR_SCAN_LOOKBACK)
         return iir_launch_scan(b, data, n_samples, stride, stream);
     if (path == SDSP_B200_IIR_SCAN_SPLIT) {
@@ -54,9 +60,13 @@ int iir_describe(IirBank &b, size_t n_samples, size_t stride, int path, char *bu
     if (timepar) {
         const bool split = path != SDSP_B200_IIR_SCAN_LOOKBACK && b.h_gain.size() == b.n_channels && iir_use_tma(b, nullptr, n_samples, stride) &&
                            iir_segment_describe(b, n_samples, how, sizeof how) == 0;
-        if (!split)
+        const bool lookback = !split && (path == SDSP_B200_IIR_SCAN_LOOKBACK || (stride % iir_scan_chunk(b.precision) == 0 || b.n_channels == 1));
+        if (!split && lookback)
             snprintf(how, sizeof how, "look-back scan (warp per 32 chunks of %d samples, Kogge-Stone over lanes, decoupled look-back between tiles)",
                      iir_scan_chunk(b.precision));
+        else if (!split)
+            snprintf(how, sizeof how, "%s (no time-parallel kernel applies to this call)",
+                     iir_use_tma(b, nullptr, n_samples, stride) ? "sequential/tma" : "sequential/generic");
     }
     snprintf(buf, buf_len, "iir bank: %zu channels x %d sections %s numerator=%d; n_samples=%zu stride=%zu path=%s -> %s", b.n_channels,
              b.sections, b.precision == SDSP_B200_F32 ? "f32" : "f64", b.numerator, n_samples, stride,

@@ -61,6 +61,7 @@ int iir_segment_describe(IirBank &b, size_t n_samples, char *buf, size_t buf_len
 unsigned long long iir_decay_length(IirBank &b);
 // iir_scan.cu -- time-parallel path, general (look-back carry of the propagation term)
 int iir_launch_scan(IirBank &b, void *data, size_t n_samples, size_t stride, cudaStream_t stream);
+bool iir_scan_applicable(const IirBank &b, const void *data, size_t n_samples, size_t stride);
 int iir_scan_chunk(int precision);
 // iir_dispatch.cu
 int iir_dispatch(IirBank &b, void *data, size_t n_samples, size_t stride, int path, cudaStream_t stream);

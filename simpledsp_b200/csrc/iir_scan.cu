@@ -21,6 +21,16 @@ int iir_scan_chunk(int precision)
     return precision == SDSP_B200_F32 ? iir_scan_chunk_f32() : iir_scan_chunk_f64();
 }
 
+bool iir_scan_applicable(const IirBank &b, const void *data, size_t n_samples, size_t stride)
+{
+    const int L = iir_scan_chunk(b.precision);
+    if (reinterpret_cast<uintptr_t>(data) % 16 != 0 || (b.n_channels > 1 && stride % L != 0) || !get_encode_fn())
+        return false;
+    if (b.sections != 2 && b.sections != 4 && b.sections != 6 && b.sections != 8)
+        return false;
+    return n_samples >= (size_t)32 * L && b.h_gain.size() == b.n_channels;
+}
+
 // whole tiles through the scan kernel, the ragged remainder through the sequential kernel (which picks the
 // bank history up where the scan left it)
 int iir_launch_scan(IirBank &b, void *data, size_t n_samples, size_t stride, cudaStream_t stream)

@@ -411,3 +411,45 @@ def test_banks_and_plans_on_two_devices_in_one_process():
             plan(zd)
             torch.cuda.synchronize(dev)
             assert rel_l2(zd.cpu().numpy(), zref) <= 1e-5, dev
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_time_split_random_shapes_against_the_sequential_kernel(seed):
+    """Random banks (1-40 channels), lengths and channel pitches through the time-parallel path against the sequential
+    kernel on the same device data: exercises the planner's segment choice, the leftover rounds, the ragged tail and the
+    3-D tensor map with pitches that are not multiples of anything convenient.  Memory outside the ranges stays untouched."""
+    torch = pytest.importorskip("torch")
+    rng = np.random.default_rng(1000 + seed)
+    prec = "f32" if seed % 2 else "f64"
+    code, dt = PREC[prec]
+    tdt = torch.float32 if prec == "f32" else torch.float64
+    per16 = 4 if prec == "f32" else 2
+    ch = int(rng.integers(1, 41))
+    n = int(rng.integers(60_000, 700_000))
+    pitch = (n + int(rng.integers(0, 5000)) + per16 - 1) // per16 * per16  # 16-byte multiple, otherwise arbitrary
+    fs = 100e3
+    ftype = rng.integers(1, 3, size=ch)
+    f0 = np.exp(rng.uniform(np.log(2e3), np.log(3e4), size=ch))
+    coef = [S.design(int(t), 4, float(f), fs) for t, f in zip(ftype, f0)]
+    banks = []
+    for _ in range(2):
+        b = S.IirBank(4, ch, code)
+        b.set_coeffs(np.array([c[0] for c in coef]), np.array([c[1] for c in coef]), np.array([c[2] for c in coef]))
+        banks.append(b)
+    gen = torch.Generator(device="cuda").manual_seed(seed)
+    base = torch.zeros(ch * pitch + 64, device="cuda", dtype=tdt)
+    view = base[: ch * pitch].view(ch, pitch)
+    view[:, :n] = torch.randn(ch, n, device="cuda", generator=gen, dtype=tdt)
+    other = base.clone()
+    stream = torch.cuda.current_stream().cuda_stream
+    plan = banks[0].describe(n, pitch, K.IIR_SCAN)
+    banks[0].process_ptr(base.data_ptr(), n, pitch, K.PTR_DEVICE, K.IIR_SCAN, stream)
+    banks[1].process_ptr(other.data_ptr(), n, pitch, K.PTR_DEVICE, K.IIR_SEQUENTIAL, stream)
+    torch.cuda.synchronize()
+    a, b_ = base[: ch * pitch].view(ch, pitch), other[: ch * pitch].view(ch, pitch)
+    peak = b_[:, :n].abs().amax(dim=1)
+    err = ((a[:, :n] - b_[:, :n]).abs().amax(dim=1) / peak).max()
+    assert float(err) <= (1e-10 if prec == "f64" else 2e-5), plan
+    assert float(a[:, n:].abs().max() if pitch > n else 0.0) == 0.0 and float(base[ch * pitch:].abs().max()) == 0.0, plan
+    st_a, st_b = banks[0].get_state(), banks[1].get_state()
+    assert np.abs(st_a - st_b).max() <= (1e-10 if prec == "f64" else 2e-5) * max(1.0, float(peak.max())), plan
