@@ -92,6 +92,8 @@ int sdsp_b200_device_synchronize(int device);
  * frame is factored into register-resident radix-16/8/4/2 passes. */
 int sdsp_b200_fft_plan_create(sdsp_b200_fft_plan *plan, uint32_t n, int radix, int precision, int direction, int device);
 int sdsp_b200_fft_plan_destroy(sdsp_b200_fft_plan plan);
+/* Device-pointer calls on one plan must be ordered with respect to each other (plans for n >= 32768 own scratch memory);
+ * use one plan per concurrent stream. */
 int sdsp_b200_fft_exec(sdsp_b200_fft_plan plan, void *data, size_t n_frames, int ptr_kind, void *stream);
 /* Real frames in (n scalars each), spectra out (n complex each), out of place.  The reference has no real-input
  * entry point; its callers place real signals in the real part of a complex_array and leave the imaginary part
