@@ -39,6 +39,9 @@ WORKLOADS = {
     "fft1024_f32": dict(kind="fft", n=1024, frames=262144, precision="f32", bytes_per_sample=16),
     "fft256_f32": dict(kind="fft", n=256, frames=1 << 20, precision="f32", bytes_per_sample=16),
     "fft64_f32": dict(kind="fft", n=64, frames=1 << 22, precision="f32", bytes_per_sample=16),
+    "fft32768_f32": dict(kind="fft", n=32768, frames=8192, precision="f32", bytes_per_sample=16),
+    "fft131072_f32": dict(kind="fft", n=131072, frames=2048, precision="f32", bytes_per_sample=16),
+    "fft262144_f32": dict(kind="fft", n=262144, frames=1024, precision="f32", bytes_per_sample=16),
     "fft16384_f32": dict(kind="fft", n=16384, frames=16384, precision="f32", bytes_per_sample=16),
     "fft8192_f32": dict(kind="fft", n=8192, frames=32768, precision="f32", bytes_per_sample=16),
     "fft2048_f32": dict(kind="fft", n=2048, frames=131072, precision="f32", bytes_per_sample=16),

@@ -485,7 +485,7 @@ template <class CfgA, typename T>
 static int launch_large(const FftPlan &p, void *data, const void *real_in, size_t n_frames, cudaStream_t stream)
 {
     if (real_in)
-        return set_error(SDSP_B200_ERR_UNSUPPORTED, "fft: real-input frames are built for n <= 16384 and n = 65536 (n=%u)", p.n);
+        return set_error(SDSP_B200_ERR_UNSUPPORTED, "fft: real-input frames are not built for the two-kernel path (n=%u)", p.n);
     using CfgB = FftCfg<256, 16, 16, 16>;
     constexpr int THREADS_A = LARGE_COLS * CfgA::TPF;
     cplx<T> *d = reinterpret_cast<cplx<T> *>(data);
@@ -817,13 +817,33 @@ static int setup_cluster64k(FftPlan &p)
 //   frame have been counted in col_done[f]; a column tile of frame f waits until the row tiles of frame f - RING have
 //   released their scratch slot (row_done).  Items are handed out in order by an atomic ticket, and every wait points
 //   at items with smaller tickets, which are held by CTAs that are already running: no deadlock, whatever the residency.
-template <typename T>
+// geometry of the fused kernel for frames of N1 x 256 points: the column transforms have N1 points (N1 / 16 threads each, so a
+// 256-thread CTA takes 256 / (N1/16) columns per tile), the row transforms 256; both phases have N1 / 16 tiles per frame
+template <int N1>
+struct FusedCols;
+template <>
+struct FusedCols<128> {
+    using Cfg = FftCfg<128, 16, 16, 8>;
+};
+template <>
+struct FusedCols<256> {
+    using Cfg = FftCfg<256, 16, 16, 16>;
+};
+template <>
+struct FusedCols<512> {
+    using Cfg = FftCfg<512, 16, 16, 16, 2>;
+};
+template <>
+struct FusedCols<1024> {
+    using Cfg = FftCfg<1024, 16, 16, 16, 4>;
+};
+template <typename T, int N1>
 struct FusedRing {
-#ifndef SDSP_FUSED_LAG
-#define SDSP_FUSED_LAG 32
-#endif
-    static constexpr int LAG = sizeof(T) == 4 ? SDSP_FUSED_LAG : SDSP_FUSED_LAG / 2;  // frames between a frame's column tiles and its row tiles
-    static constexpr int RING = 2 * LAG;                   // scratch frames (32 MB)
+    static constexpr int TILES = N1 / 16;                     // tiles per frame, either phase
+    static constexpr int COLS = 256 / (N1 / 16);              // columns per column tile
+    // frames between a frame's column tiles and its row tiles: 512 (fp32) / 256 (fp64) tiles of lead, more than the CTAs in flight
+    static constexpr int LAG = (sizeof(T) == 4 ? 512 : 256) / TILES;
+    static constexpr int RING = 2 * LAG;                      // scratch frames: 32 MB whatever the frame size
 };
 
 __device__ __forceinline__ cplx<float> ld_l2(const cplx<float> *p)
@@ -868,24 +888,31 @@ __device__ __forceinline__ void fused_decode(size_t q, bool &cols, size_t &f, in
 
 // Variants measured and dropped (profiles/r01_fft65536_variants.txt): L2 prefetch of the column tile one round ahead, cp.async
 // staging of the next column tile, a separate transposing step in the row tiles, a single barrier per item.
-template <typename T>
+template <typename T, int N1>
 __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 3 : 1)
-    fft_fused64k_kernel(cplx<T> *__restrict__ data, const T *__restrict__ real_in, cplx<T> *__restrict__ scratch,
-                        const cplx<T> *__restrict__ tw, const cplx<T> *__restrict__ tw_hi, const cplx<T> *__restrict__ tw_lo,
+    fft_fused_kernel(cplx<T> *__restrict__ data, const T *__restrict__ real_in, cplx<T> *__restrict__ scratch,
+                     const cplx<T> *__restrict__ tw_cols, const cplx<T> *__restrict__ tw, const cplx<T> *__restrict__ tw_hi,
+                     const cplx<T> *__restrict__ tw_lo,
                         unsigned *__restrict__ ticket, unsigned *__restrict__ col_done, unsigned *__restrict__ row_done, size_t n_frames,
                         int inverse, T scale)
 {
-    using Cfg = FftCfg<256, 16, 16, 16>;
-    constexpr int PITCH = LargeStride<Cfg>::value;
-    constexpr int N2 = 256, TILES = 16, LAG = FusedRing<T>::LAG, RING = FusedRing<T>::RING;
+    using Cfg = FftCfg<256, 16, 16, 16>;          // rows
+    using CCfg = typename FusedCols<N1>::Cfg;     // columns
+    constexpr int PITCH = LargeStride<Cfg>::value, CPITCH = LargeStride<CCfg>::value;
+    constexpr int N2 = 256, TILES = FusedRing<T, N1>::TILES, COLS = FusedRing<T, N1>::COLS;
+    constexpr int LAG = FusedRing<T, N1>::LAG, RING = FusedRing<T, N1>::RING;
+    constexpr int XBUF = 16 * PITCH > COLS * CPITCH ? 16 * PITCH : COLS * CPITCH;
+    constexpr size_t FRAME = (size_t)N1 * N2;
     constexpr int MINB = sizeof(T) == 4 ? 3 : 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx<T> *xbuf = reinterpret_cast<cplx<T> *>(smem_raw);
-    cplx<T> *s_hi = xbuf + 16 * PITCH, *s_lo = s_hi + 256;
+    cplx<T> *s_hi = xbuf + XBUF, *s_lo = s_hi + N1; // W_N1^i (N1 entries) and W_N^i (256 entries): W_N^x = hi[x >> 8] * lo[x & 255]
     __shared__ unsigned s_ticket, s_ready;
-    s_hi[threadIdx.x] = tw_hi[threadIdx.x];
+    for (int i = threadIdx.x; i < N1; i += 256)
+        s_hi[i] = tw_hi[i];
     s_lo[threadIdx.x] = tw_lo[threadIdx.x];
     const int lo16 = threadIdx.x & 15, hi16 = threadIdx.x >> 4;
+    const int ccol = threadIdx.x % COLS, ct = threadIdx.x / COLS; // column tiles: column within the tile, thread within the transform
     const size_t total = ((size_t)LAG + 2 * n_frames) * TILES;
 
     // Latency of the queue itself is kept off the critical path: thread 0 draws tickets ahead of their use (the atomic's
@@ -914,50 +941,50 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 3 : 1)
         size_t f;
         int tile;
         fused_decode<LAG, TILES>(q, cols, f, tile);
-        cplx<T> *sc = scratch + (f % RING) * ((size_t)N2 * N2);
+        cplx<T> *sc = scratch + (f % RING) * (FRAME);
         cplx<T> v[Cfg::E];
         unsigned *done = nullptr;
         if (f >= n_frames) {
             __syncthreads(); // empty slot (column tiles past the last frame): everyone has read the mailbox before it is rewritten
         } else if (cols) {
-            // ---- 16 columns b = 16 tile + lo16: 256-point transforms over a, times W_N^(b k1), to scratch [k1][b]
-            const int t = hi16;
-            const unsigned b = 16u * (unsigned)tile + (unsigned)lo16;
+            // ---- COLS columns b = COLS tile + ccol: N1-point transforms over a, times W_N^(b k1), to scratch [k1][b]
+            const int t = ct;
+            const unsigned b = (unsigned)COLS * (unsigned)tile + (unsigned)ccol;
             unsigned seen = TILES;
             if (threadIdx.x == 0 && f >= (size_t)RING)
                 seen = ld_acquire_gpu(row_done + (f - RING)); // has the scratch slot's previous tenant been read out?
             if (real_in) {
-                const T *rp = real_in + f * ((size_t)N2 * N2) + b;
+                const T *rp = real_in + f * FRAME + b;
 #pragma unroll
-                for (int e = 0; e < Cfg::E; e++)
-                    v[e] = cplx<T>{ __ldcs(rp + (size_t)(t + Cfg::S * e) * N2), (T)0 };
+                for (int e = 0; e < CCfg::E; e++)
+                    v[e] = cplx<T>{ __ldcs(rp + (size_t)(t + CCfg::S * e) * N2), (T)0 };
             } else {
-                const cplx<T> *gp = data + f * ((size_t)N2 * N2) + b;
+                const cplx<T> *gp = data + f * FRAME + b;
 #pragma unroll
-                for (int e = 0; e < Cfg::E; e++)
-                    v[e] = ld_stream(gp + (size_t)(t + Cfg::S * e) * N2);
+                for (int e = 0; e < CCfg::E; e++)
+                    v[e] = ld_stream(gp + (size_t)(t + CCfg::S * e) * N2);
             }
             if (inverse) {
 #pragma unroll
-                for (int e = 0; e < Cfg::E; e++)
+                for (int e = 0; e < CCfg::E; e++)
                     v[e] = cplx<T>{ v[e].y, v[e].x };
             }
             if (threadIdx.x == 0 && f >= (size_t)RING)
                 spin_until(row_done + (f - RING), TILES, seen);
-            // (the barrier inside the passes sits between thread 0's check above and every thread's stores below)
-            fft_kernel_passes<Cfg, T, 256, MINB, 0>(v, xbuf + (size_t)lo16 * PITCH, tw, t);
-            const TwiddleSeq<T> wseq(b * (unsigned)t, b * (unsigned)Cfg::S, s_hi, s_lo);
+            // (the barriers inside the passes sit between thread 0's check above and every thread's stores below)
+            fft_kernel_passes<CCfg, T, 256, MINB, 0>(v, xbuf + (size_t)ccol * CPITCH, tw_cols, t);
+            const TwiddleSeq<T> wseq(b * (unsigned)t, b * (unsigned)CCfg::S, s_hi, s_lo);
             cplx<T> *op = sc + b;
 #pragma unroll
-            for (int e = 0; e < Cfg::E; e++)
-                op[(size_t)(t + Cfg::S * e) * N2] = cmul(v[e], wseq.get(e));
+            for (int e = 0; e < CCfg::E; e++)
+                op[(size_t)(t + CCfg::S * e) * N2] = cmul(v[e], wseq.get(e));
             done = col_done + f;
         } else {
-            // ---- 16 rows k1 = 16 tile + r: 256-point transforms over b out of scratch, stored to X[k1 + 256 k2]
+            // ---- 16 rows k1 = 16 tile + r: 256-point transforms over b out of scratch, stored to X[k1 + N1 k2]
             // (col_done[f] was checked by thread 0 before the barrier that published this ticket)
             // The first pass runs with lanes along b (thread = (t, row): coalesced 128-byte reads of the ring); the exchange
             // between the passes also re-maps the threads, so the second pass runs with lanes along the rows
-            // (thread = (row, t)) and its natural-order outputs X[k1 + 256 (t + 16 e)] leave as 128-byte runs over k1 --
+            // (thread = (row, t)) and its natural-order outputs X[k1 + N1 (t + 16 e)] leave as 128-byte runs over k1 --
             // no separate transposing step.
             const int t = lo16, row = hi16;
             const cplx<T> *gp = sc + (size_t)(16 * tile + row) * N2 + t;
@@ -981,10 +1008,10 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 3 : 1)
                 for (int e = 0; e < Cfg::E; e++)
                     v[e] = cplx<T>{ v[e].y * scale, v[e].x * scale };
             }
-            cplx<T> *op = data + f * ((size_t)N2 * N2) + 16 * tile + row2;
+            cplx<T> *op = data + f * (FRAME) + 16 * tile + row2;
 #pragma unroll
             for (int e = 0; e < Cfg::E; e++)
-                st_stream(op + (size_t)(t2 + Cfg::S * e) * N2, v[e]); // natural order: slot e of thread t2 is k2 = t2 + 16 e
+                st_stream(op + (size_t)(t2 + Cfg::S * e) * N1, v[e]); // natural order: slot e of thread t2 is k2 = t2 + 16 e, X[k1 + N1 k2]
             done = row_done + f;
         }
         // ---- end of item: publish the ticket drawn during it, and whether the item that comes next has its dependency met,
@@ -1015,8 +1042,8 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 3 : 1)
     }
 }
 
-template <typename T>
-static int launch_fused64k(const FftPlan &p, void *data, const void *real_in, size_t n_frames, cudaStream_t stream)
+template <typename T, int N1>
+static int launch_fused(const FftPlan &p, void *data, const void *real_in, size_t n_frames, cudaStream_t stream)
 {
     if (n_frames == 0)
         return SDSP_B200_OK;
@@ -1036,52 +1063,65 @@ static int launch_fused64k(const FftPlan &p, void *data, const void *real_in, si
     }
     SDSP_CUDA(cudaMemsetAsync(mp.d_fused_counters, 0, need, stream));
     unsigned *ctr = static_cast<unsigned *>(mp.d_fused_counters);
-    const size_t items = ((size_t)FusedRing<T>::LAG + 2 * n_frames) * 16;
+    const size_t items = ((size_t)FusedRing<T, N1>::LAG + 2 * n_frames) * FusedRing<T, N1>::TILES;
     size_t grid = (size_t)p.sm_count * (size_t)p.ctas_per_sm;
     if (grid > items)
         grid = items;
-    fft_fused64k_kernel<T><<<(unsigned)grid, 256, p.smem_bytes, stream>>>(
+    fft_fused_kernel<T, N1><<<(unsigned)grid, 256, p.smem_bytes, stream>>>(
         reinterpret_cast<cplx<T> *>(data), static_cast<const T *>(real_in), reinterpret_cast<cplx<T> *>(p.d_scratch),
-        reinterpret_cast<const cplx<T> *>(p.d_tw_rows), reinterpret_cast<const cplx<T> *>(p.d_tw_hi), reinterpret_cast<const cplx<T> *>(p.d_tw_lo),
-        ctr, ctr + 1, ctr + 1 + n_frames, n_frames, p.direction == SDSP_B200_REVERSE ? 1 : 0, (T)(1.0 / 65536.0));
+        reinterpret_cast<const cplx<T> *>(p.d_tw_cols), reinterpret_cast<const cplx<T> *>(p.d_tw_rows),
+        reinterpret_cast<const cplx<T> *>(p.d_tw_hi), reinterpret_cast<const cplx<T> *>(p.d_tw_lo), ctr, ctr + 1, ctr + 1 + n_frames, n_frames,
+        p.direction == SDSP_B200_REVERSE ? 1 : 0, (T)(1.0 / ((double)N1 * 256.0)));
     SDSP_CUDA(cudaGetLastError());
     return SDSP_B200_OK;
 }
 
-template <typename T>
-static int setup_fused64k(FftPlan &p)
+template <typename T, int N1>
+static int setup_fused(FftPlan &p)
 {
     using Cfg = FftCfg<256, 16, 16, 16>;
-    p.smem_bytes = ((size_t)16 * LargeStride<Cfg>::value + 512) * sizeof(cplx<T>);
-    auto kern = fft_fused64k_kernel<T>;
+    using CCfg = typename FusedCols<N1>::Cfg;
+    constexpr int COLS = FusedRing<T, N1>::COLS;
+    constexpr size_t XBUF = 16 * LargeStride<Cfg>::value > COLS * LargeStride<CCfg>::value ? 16 * LargeStride<Cfg>::value : COLS * LargeStride<CCfg>::value;
+    p.smem_bytes = (XBUF + N1 + 256) * sizeof(cplx<T>);
+    auto kern = fft_fused_kernel<T, N1>;
     if (p.smem_bytes > 48 * 1024)
         SDSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
     int occ = 0;
     SDSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, p.smem_bytes));
     if (occ < 1)
-        return set_error(SDSP_B200_ERR_UNSUPPORTED, "fft: the fused 65536-point kernel does not fit on an SM");
+        return set_error(SDSP_B200_ERR_UNSUPPORTED, "fft: the fused kernel for n=%u does not fit on an SM", p.n);
     p.ctas_per_sm = occ;
     p.fused = true;
-    p.n1 = 256;
-    p.npass = 4;
+    p.n1 = N1;
+    p.npass = CCfg::NPASS + 2;
     p.e = 16;
     p.threads = 256;
-    p.scratch_frames = FusedRing<T>::RING;
-    const size_t frame_bytes = (size_t)65536 * sizeof(cplx<T>);
+    p.scratch_frames = FusedRing<T, N1>::RING;
+    const size_t frame_bytes = (size_t)N1 * 256 * sizeof(cplx<T>);
     if (cudaMalloc(&p.d_scratch, p.scratch_frames * frame_bytes) != cudaSuccess) {
         cudaGetLastError();
         return set_error(SDSP_B200_ERR_OOM, "fft: cannot allocate %zu bytes of scratch", p.scratch_frames * frame_bytes);
     }
     std::vector<cplx<T>> tw;
-    int rb[4] = { 16, 16, 1, 1 };
+    int ra[4] = { CCfg::R0, CCfg::R1, CCfg::R2, CCfg::R3 }, rb[4] = { 16, 16, 1, 1 };
+    build_twiddles<T>(N1, ra, CCfg::NPASS, tw);
+    tw.push_back(cplx<T>{ 1, 0 });
+    int rc = upload_table<T>(&p.d_tw_cols, tw);
+    size_t tw_total = tw.size();
     build_twiddles<T>(256, rb, 2, tw);
-    int rc = upload_table<T>(&p.d_tw_rows, tw);
-    std::vector<cplx<T>> hi(256), lo(256);
+    if (!rc)
+        rc = upload_table<T>(&p.d_tw_rows, tw);
+    tw_total += tw.size();
+    std::vector<cplx<T>> hi(N1), lo(256);
+    for (int i = 0; i < N1; i++) {
+        long double re, im;
+        unit_root((uint64_t)i, (uint64_t)N1, re, im);
+        hi[i] = cplx<T>{ (T)re, (T)im };
+    }
     for (int i = 0; i < 256; i++) {
         long double re, im;
-        unit_root((uint64_t)i, (uint64_t)256, re, im);
-        hi[i] = cplx<T>{ (T)re, (T)im };
-        unit_root((uint64_t)i, (uint64_t)65536, re, im);
+        unit_root((uint64_t)i, (uint64_t)N1 * 256, re, im);
         lo[i] = cplx<T>{ (T)re, (T)im };
     }
     if (!rc)
@@ -1090,8 +1130,8 @@ static int setup_fused64k(FftPlan &p)
         rc = upload_table<T>(&p.d_tw_lo, lo);
     if (rc)
         return rc;
-    p.tw_bytes = (tw.size() + hi.size() + lo.size()) * sizeof(cplx<T>);
-    p.launch = &launch_fused64k<T>;
+    p.tw_bytes = (tw_total + hi.size() + lo.size()) * sizeof(cplx<T>);
+    p.launch = &launch_fused<T, N1>;
     return SDSP_B200_OK;
 }
 
@@ -1128,8 +1168,17 @@ static int setup_large_n1(FftPlan &p)
         const char *e = getenv("SDSP_B200_FFT_65536");
         which = !e ? 0 : !strcmp(e, "cluster") ? 1 : !strcmp(e, "twokernel") ? 2 : 0;
     }
-    if (p.n == 65536 && which == 0)
-        return setup_fused64k<T>(p);
+    if (which == 0) { // one persistent kernel, intermediate in an L2-resident ring (n = n1 x 256, n1 = 128 ... 1024)
+        switch (p.n / 256) {
+        case 128: return setup_fused<T, 128>(p);
+        case 256: return setup_fused<T, 256>(p);
+        case 512: return setup_fused<T, 512>(p);
+        case 1024:
+            if constexpr (sizeof(T) == 4)
+                return setup_fused<T, 1024>(p);
+        default: break;
+        }
+    }
     if (p.n == 65536 && which == 1)
         return setup_cluster64k_auto<T>(p);
     switch (p.n / 256) {
@@ -1449,13 +1498,14 @@ int sdsp_b200_fft_plan_describe(sdsp_b200_fft_plan plan, char *buf, size_t buf_l
         return set_error(SDSP_B200_ERR_INVALID_ARG, "fft_plan_describe: bad arguments");
     const FftPlan &p = plan->p;
     if (p.fused) {
+        const int tiles = p.n1 / 16, cols = 256 / tiles;
         snprintf(buf, buf_len,
-                 "fft n=%u %s %s radix-arg=%d: one persistent kernel, single pass over HBM: per frame 16 column tiles (16 columns x 256-point "
-                 "transforms, twiddle) -> ring of %zu scratch frames resident in L2 -> 16 row tiles (16 rows x 256-point transforms, "
-                 "transposed store), ordered by an atomic work queue with per-frame completion counters; 256 threads/CTA, smem/CTA=%zuB, "
-                 "CTAs/SM=%d, SMs=%d",
-                 p.n, p.precision == SDSP_B200_F32 ? "f32" : "f64", p.direction == SDSP_B200_FORWARD ? "forward" : "reverse", p.radix,
-                 p.scratch_frames, p.smem_bytes, p.ctas_per_sm, p.sm_count);
+                 "fft n=%u %s %s radix-arg=%d: one persistent kernel, single pass over HBM: n = %d x 256; per frame %d column tiles (%d columns "
+                 "x %d-point transforms, twiddle) -> ring of %zu scratch frames resident in L2 -> %d row tiles (16 rows x 256-point "
+                 "transforms, threads re-mapped between the passes), ordered by an atomic work queue with per-frame completion counters; "
+                 "256 threads/CTA, smem/CTA=%zuB, CTAs/SM=%d, SMs=%d",
+                 p.n, p.precision == SDSP_B200_F32 ? "f32" : "f64", p.direction == SDSP_B200_FORWARD ? "forward" : "reverse", p.radix, p.n1,
+                 tiles, cols, p.n1, p.scratch_frames, tiles, p.smem_bytes, p.ctas_per_sm, p.sm_count);
         return SDSP_B200_OK;
     }
     if (p.cluster) {

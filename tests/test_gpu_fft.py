@@ -186,7 +186,7 @@ def test_large_frames_many_frames_and_unsupported_sizes(prec):
 
 
 @pytest.mark.parametrize("prec", ["f32", "f64"])
-@pytest.mark.parametrize("n", [64, 1024, 4096, 16384, 65536])
+@pytest.mark.parametrize("n", [64, 1024, 4096, 16384, 32768, 65536, 131072])
 def test_real_input_frames_match_oracle(n, prec):
     """sdsp_b200_fft_exec_real: real frames in, spectra out -- what the reference's callers do by filling only the
     real part of a complex_array (test/testFFT.cpp:24, :86), folded into the first load."""
