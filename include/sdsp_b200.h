@@ -98,7 +98,7 @@ int sdsp_b200_fft_exec(sdsp_b200_fft_plan plan, void *data, size_t n_frames, int
 /* Real frames in (n scalars each), spectra out (n complex each), out of place.  The reference has no real-input
  * entry point; its callers place real signals in the real part of a complex_array and leave the imaginary part
  * zero (test/testFFT.cpp:24, :86).  This does that placement inside the first load of the transform, so the input
- * costs half the bytes.  Built for every size except those on the two-kernel path (fp64, n = 16384). */
+ * costs half the bytes. */
 int sdsp_b200_fft_exec_real(sdsp_b200_fft_plan plan, const void *real_in, void *spectrum_out, size_t n_frames, int ptr_kind, void *stream);
 /* human-readable description of the factorisation / launch geometry the plan chose */
 int sdsp_b200_fft_plan_describe(sdsp_b200_fft_plan plan, char *buf, size_t buf_len);

@@ -822,6 +822,14 @@ static int setup_cluster64k(FftPlan &p)
 template <int N1>
 struct FusedCols;
 template <>
+struct FusedCols<32> {
+    using Cfg = FftCfg<32, 16, 16, 2>;
+};
+template <>
+struct FusedCols<64> {
+    using Cfg = FftCfg<64, 16, 16, 4>;
+};
+template <>
 struct FusedCols<128> {
     using Cfg = FftCfg<128, 16, 16, 8>;
 };
@@ -1170,6 +1178,8 @@ static int setup_large_n1(FftPlan &p)
     }
     if (which == 0) { // one persistent kernel, intermediate in an L2-resident ring (n = n1 x 256, n1 = 128 ... 1024)
         switch (p.n / 256) {
+        case 32: return setup_fused<T, 32>(p);
+        case 64: return setup_fused<T, 64>(p);
         case 128: return setup_fused<T, 128>(p);
         case 256: return setup_fused<T, 256>(p);
         case 512: return setup_fused<T, 512>(p);
@@ -1276,6 +1286,9 @@ static int emulate_for(int precision, bool inverse, void *frame)
 static int setup_plan(FftPlan &p)
 {
     const int lg = ilog2(p.n);
+    static const bool fused_small = getenv("SDSP_B200_FFT_FUSED_SMALL") != nullptr; // comparison aid: 8192 / 16384 through the fused kernel
+    if (fused_small && (lg == 13 || lg == 14))
+        return p.precision == SDSP_B200_F32 ? setup_large_n1<float>(p) : setup_large_n1<double>(p);
     if (lg > (p.precision == SDSP_B200_F32 ? MAX_LOG2N_F32 : MAX_LOG2N_F64))
         return p.precision == SDSP_B200_F32 ? setup_large_n1<float>(p) : setup_large_n1<double>(p);
     switch (lg) {

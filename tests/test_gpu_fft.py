@@ -191,8 +191,6 @@ def test_real_input_frames_match_oracle(n, prec):
     """sdsp_b200_fft_exec_real: real frames in, spectra out -- what the reference's callers do by filling only the
     real part of a complex_array (test/testFFT.cpp:24, :86), folded into the first load."""
     torch = pytest.importorskip("torch")
-    if prec == "f64" and n == 16384:
-        pytest.skip("f64 frames of 16384 points take the two-kernel path (no real-input variant)")
     code, dt = PREC[prec]
     frames = 37 if n <= 4096 else 9
     rng = np.random.default_rng(n)
