@@ -220,8 +220,8 @@ bool iir_segment_plan(IirBank &b, size_t n_samples, bool first_round, size_t *se
     if (K == 0)
         return remember(false, 0, 0, 0);
     const size_t es = b.precision == SDSP_B200_F32 ? 4 : 8;
-    const size_t align = 128 / es; // segment starts stay 128-byte aligned relative to the channel start
-    const size_t cts = 2 * (128 / es); // the row kernel's compute tile
+    const size_t cts = 2 * (128 / es); // the row kernel's compute tile = one ring stage
+    const size_t align = cts;           // segments are whole stages (no ragged tail in every row), starts 256-byte aligned
     const size_t corr = (size_t)((K + cts - 1) / cts * cts);
     // the correction pass costs corr/seg_len extra traffic: <= 25 % on the bulk, anything on the leftovers
     const size_t min_len = first_round ? (corr * 4 > 1024 ? corr * 4 : 1024) : corr;
@@ -241,12 +241,15 @@ bool iir_segment_plan(IirBank &b, size_t n_samples, bool first_round, size_t *se
     } else {
         double best_cost = 0;
         const size_t limit = slots * 32 * 16 / b.n_channels; // beyond 16 waves nothing is left to gain
-        for (size_t segs = 8; segs <= max_segs && segs <= limit; segs += 8) {
+        bool four_waves_seen = false; // measured (profiles/r01_iir_split_ring_sweep.txt): once a bank fills four waves, cutting it
+                                      // finer only adds correction traffic -- the wave model overrates what more segments buy
+        for (size_t segs = 8; segs <= max_segs && segs <= limit && !four_waves_seen; segs += 8) {
             const size_t len = n_samples / segs / align * align;
             if (len < min_len)
                 break;
             const size_t warps = (b.n_channels * segs + 31) / 32;
             const size_t waves = (warps + slots - 1) / slots;
+            four_waves_seen = warps >= 4 * slots;
             const double cost = (double)waves * (double)(len + corr) + 4.0 * (double)(n_samples - segs * len);
             if (best == 0 || cost < best_cost) {
                 best = segs;

@@ -523,12 +523,17 @@ static int launch_rows_ring(const IirBank &b, void *data, size_t seg_len, size_t
         switch (rows_tune()) { //                                         SUB CSUB NST PF   ring per warp
         case 1: return launch_rows_cfg<T, M, KIND, MODE, 2, 2, 4, 2>(b, data, seg_len, segs, stride, row_state, n_samples, stream, slots); // 32 KB
         case 5: return launch_rows_cfg<T, M, KIND, MODE, 2, 2, 6, 3>(b, data, seg_len, segs, stride, row_state, n_samples, stream, slots); // 48 KB
+        case 6: return launch_rows_cfg<T, M, KIND, MODE, 2, 2, 2, 1>(b, data, seg_len, segs, stride, row_state, n_samples, stream, slots); // 16 KB
+        case 7: return launch_rows_cfg<T, M, KIND, MODE, 2, 2, 3, 1>(b, data, seg_len, segs, stride, row_state, n_samples, stream, slots); // 24 KB
         default: break;
         }
     }
-    // default (measured best of the ring sweep, profiles/r01_iir_split_ring_sweep.txt): three 8 KB stages per warp, so that
-    // nine row-warps share an SM -- a single warp is issue/latency-bound, the memory system is filled by having many
-    return launch_rows_cfg<T, M, KIND, MODE, 2, 2, 3, 1>(b, data, seg_len, segs, stride, row_state, n_samples, stream, slots); // 24 KB
+    // defaults (ring sweeps: profiles/r01_iir_split_ring_sweep.txt): a single warp is issue/latency-bound, the memory system is
+    // filled by having many on an SM -- fp32: two 8 KB stages per warp (13 row-warps per SM), fp64: three (8 per SM)
+    if constexpr (sizeof(T) == 4)
+        return launch_rows_cfg<T, M, KIND, MODE, 2, 2, 2, 1>(b, data, seg_len, segs, stride, row_state, n_samples, stream, slots); // 16 KB
+    else
+        return launch_rows_cfg<T, M, KIND, MODE, 2, 2, 3, 1>(b, data, seg_len, segs, stride, row_state, n_samples, stream, slots); // 24 KB
 }
 
 template <typename T, int M, int KIND>
