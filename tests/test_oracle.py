@@ -179,3 +179,25 @@ def test_scipy_fixture_generator_reproduces_the_reference_fixtures():
         assert np.abs(got - h).max() <= 1e-12 * np.abs(h).max(), name
         t, fs, f0, q, back = M.parse_csv_line(M.csv_line(kind, hd[1], hd[2], hd[3], got))
         assert (t, fs, f0, q) == (int(hd[0]), hd[1], hd[2], hd[3]) and np.allclose(back, got, rtol=1e-14, atol=0)
+
+
+@pytest.mark.parametrize("sections", [2, 4, 6, 8])
+def test_designers_and_recurrence_against_scipy_beyond_the_fixtures(sections):
+    """An independent second oracle: scipy's butter -> sos -> sosfilt (the recipe of tools/make_fixtures.py)
+    against the restated designers + recurrence for orders, sample rates, cut-offs and Qs the nine golden files do not
+    cover.  Both build the same Butterworth filter, so the impulse responses agree to rounding."""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+    from tools import make_fixtures as M
+
+    x = np.zeros(600)
+    x[0] = 1.0
+    for kind, t in (("lp", 1), ("hp", 2), ("bp", 3)):
+        for f0, fs, q in ((500.0, 48e3, 0.9), (3000.0, 44.1e3, 1.7), (11e3, 96e3, 2.5), (150.0, 8e3, 1.2)):
+            f = O.Iir(sections)
+            f.design(t, f0, fs, q)
+            h = f.process(x)
+            want = M.impulse_response(kind, fs, f0, q, 2 * sections, 600)
+            assert np.abs(h - want).max() <= 1e-11 * np.abs(want).max(), (sections, kind, f0, fs, q)
