@@ -129,6 +129,99 @@ __device__ __forceinline__ void fft_kernel_passes(cplx<T> (&v)[Cfg::E], cplx<T> 
     }
 }
 
+// ALIAS variant: the exchange buffer doubles as the staging area of the NEXT group.  Once the last exchange has been read
+// (and a barrier has made that true for every thread) the buffer is idle for the rest of the group -- last pass, stores -- so
+// each thread starts cp.async copies of exactly the points it will take next (thread-private slots, natural layout) and the
+// next iteration begins with shared-memory reads instead of an L2 / HBM round trip.  Same number of barriers per group as the
+// plain variant (the barrier that used to end a group now follows the read of the staged points instead).
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+template <class Cfg, typename T, int P, typename Issue>
+__device__ __forceinline__ void fft_kernel_passes_alias(cplx<T> (&v)[Cfg::E], cplx<T> *fs, const cplx<T> *__restrict__ tw, int t, Issue &&issue_next)
+{
+    if constexpr (P < Cfg::NPASS) {
+        if constexpr (P > 0) {
+#pragma unroll
+            for (int e = 0; e < Cfg::E; e++)
+                v[e] = fs[fft_read_phys<Cfg>(t, e)];
+            __syncthreads(); // everyone has read: the buffer may be overwritten (next exchange, or the staging copies)
+        }
+        if constexpr (P + 1 == Cfg::NPASS)
+            issue_next();
+        fft_pass<Cfg, P, T>(v, t, tw);
+        if constexpr (P + 1 < Cfg::NPASS) {
+#pragma unroll
+            for (int e = 0; e < Cfg::E; e++)
+                fs[fft_out_phys<Cfg, P>(t, e)] = v[e];
+            __syncthreads();
+            fft_kernel_passes_alias<Cfg, T, P + 1>(v, fs, tw, t, issue_next);
+        }
+    }
+}
+
+template <class Cfg, typename T, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+    fft_cta_alias_kernel(cplx<T> *__restrict__ data, const cplx<T> *__restrict__ tw, size_t n_frames, int inverse, T scale)
+{
+    constexpr int FPC = THREADS / Cfg::TPF;
+    static_assert(THREADS % Cfg::TPF == 0 && FPC >= 1 && Cfg::NPASS > 1, "block must hold whole frames; needs an exchange buffer");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx<T> *smem = reinterpret_cast<cplx<T> *>(smem_raw);
+    const int fl = threadIdx.x / Cfg::TPF;
+    const int t = threadIdx.x % Cfg::TPF;
+    cplx<T> *fs = smem + (size_t)fl * Cfg::PADDED_N;
+    const size_t groups = (n_frames + FPC - 1) / FPC;
+    auto stage = [&](size_t grp) { // this thread's own points of its frame in group `grp`, natural positions t + S e
+        const size_t frame = grp * FPC + fl;
+        if (grp < groups && frame < n_frames) {
+            const cplx<T> *gp = data + frame * (size_t)Cfg::N + t;
+#pragma unroll
+            for (int e = 0; e < Cfg::E; e++) {
+                if constexpr (sizeof(cplx<T>) == 16)
+                    cp_async16(fs + t + Cfg::S * e, gp + Cfg::S * e);
+                else
+                    cp_async8(fs + t + Cfg::S * e, gp + Cfg::S * e);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    stage(blockIdx.x);
+    for (size_t g = blockIdx.x; g < groups; g += gridDim.x) {
+        const size_t frame = g * FPC + fl;
+        const bool active = frame < n_frames;
+        cplx<T> *gp = data + frame * (size_t)Cfg::N + t;
+        cplx<T> v[Cfg::E];
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+        for (int e = 0; e < Cfg::E; e++)
+            v[e] = active ? fs[t + Cfg::S * e] : cplx<T>{ 0, 0 };
+        __syncthreads(); // everyone holds its points: the first exchange may overwrite the staging area
+        if (inverse) {
+#pragma unroll
+            for (int e = 0; e < Cfg::E; e++)
+                v[e] = cplx<T>{ v[e].y, v[e].x };
+        }
+        fft_kernel_passes_alias<Cfg, T, 0>(v, fs, tw, t, [&] { stage(g + gridDim.x); });
+        if (inverse) {
+#pragma unroll
+            for (int e = 0; e < Cfg::E; e++)
+                v[e] = cplx<T>{ v[e].y * scale, v[e].x * scale };
+        }
+        if (active) {
+#pragma unroll
+            for (int e = 0; e < Cfg::E; e++)
+                st_stream(gp + Cfg::S * e, v[e]);
+        }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 template <class Cfg, typename T, int THREADS, int MINB, bool DB = false>
 __global__ void __launch_bounds__(THREADS, MINB)
     fft_cta_kernel(cplx<T> *__restrict__ data, const T *__restrict__ real_in, const cplx<T> *__restrict__ tw, size_t n_frames, int inverse,
@@ -253,6 +346,7 @@ struct FftPlan {
     size_t smem_bytes = 0;
     int ctas_per_sm = 0, sm_count = 0;
     bool double_buffered = false;
+    bool staged = false; // next group staged into the exchange buffer by cp.async (fft_cta_alias_kernel)
     void *d_tw = nullptr;
     size_t tw_bytes = 0;
     fft_launch_fn launch = nullptr;
@@ -306,6 +400,25 @@ static int launch_cta(const FftPlan &p, void *data, const void *real_in, size_t 
     return SDSP_B200_OK;
 }
 
+template <class Cfg, typename T, int THREADS, int MINB>
+static int launch_cta_alias(const FftPlan &p, void *data, const void *real_in, size_t n_frames, cudaStream_t stream)
+{
+    constexpr int FPC = THREADS / Cfg::TPF;
+    // real input and buffers that are not 16-byte aligned take the plain kernel (same arithmetic, same bits)
+    if (real_in || reinterpret_cast<uintptr_t>(data) % 16 != 0)
+        return launch_cta<Cfg, T, THREADS, MINB, false>(p, data, real_in, n_frames, stream);
+    const size_t groups = (n_frames + FPC - 1) / FPC;
+    if (groups == 0)
+        return SDSP_B200_OK;
+    const size_t resident = (size_t)p.sm_count * (size_t)p.ctas_per_sm;
+    const size_t grid = groups < resident * 4 ? groups : resident * 4;
+    fft_cta_alias_kernel<Cfg, T, THREADS, MINB><<<(unsigned)grid, THREADS, p.smem_bytes, stream>>>(
+        reinterpret_cast<cplx<T> *>(data), reinterpret_cast<const cplx<T> *>(p.d_tw), n_frames, p.direction == SDSP_B200_REVERSE ? 1 : 0,
+        (T)(1.0 / (double)Cfg::N));
+    SDSP_CUDA(cudaGetLastError());
+    return SDSP_B200_OK;
+}
+
 template <class Cfg, typename T, int THREADS, int MINB, bool DB = false>
 static int setup_cta(FftPlan &p)
 {
@@ -337,6 +450,18 @@ static int setup_cta(FftPlan &p)
         SDSP_CUDA(cudaMalloc(&p.d_tw, p.tw_bytes));
         SDSP_CUDA(cudaMemcpy(p.d_tw, tw.data(), p.tw_bytes, cudaMemcpyHostToDevice));
     }
+    return SDSP_B200_OK;
+}
+
+// switch a plan set up by setup_cta<..., DB = false> to the alias-staging kernel (same shared memory, same occupancy)
+template <class Cfg, typename T, int THREADS, int MINB>
+static int enable_alias(FftPlan &p)
+{
+    auto kern = fft_cta_alias_kernel<Cfg, T, THREADS, MINB>;
+    if (p.smem_bytes > 48 * 1024)
+        SDSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
+    p.launch = &launch_cta_alias<Cfg, T, THREADS, MINB>;
+    p.staged = true;
     return SDSP_B200_OK;
 }
 
@@ -1253,6 +1378,10 @@ static int setup_for(FftPlan &p)
                 return setup_cta<typename C::type, float, C::THREADS, 4, true>(p);
             if (tune == 4)
                 return setup_cta<typename C::type, float, C::THREADS, 2, true>(p);
+            if (tune == 5) {
+                const int rc = setup_cta<typename C::type, float, C::THREADS, C::MINB>(p);
+                return rc ? rc : enable_alias<typename C::type, float, C::THREADS, C::MINB>(p);
+            }
         } else {
             if (tune == 1)
                 return setup_cta<typename C::type, double, C::THREADS, 2, true>(p);
@@ -1260,12 +1389,25 @@ static int setup_for(FftPlan &p)
                 return setup_cta<typename C::type, double, C::THREADS, 3, false>(p);
             if (tune == 3)
                 return setup_cta<typename C::type, double, C::THREADS, 1, true>(p);
+            if (tune == 4) {
+                const int rc = setup_cta<typename C::type, double, C::THREADS, 2>(p);
+                return rc ? rc : enable_alias<typename C::type, double, C::THREADS, 2>(p);
+            }
         }
     }
     if (p.precision == SDSP_B200_F32)
         return setup_cta<typename C::type, float, C::THREADS, C::MINB>(p);
     if constexpr (LG <= MAX_LOG2N_F64)
-        return setup_cta<typename C::type, double, C::THREADS, (LG == 13 ? 1 : (C::MINB > 2 ? 2 : C::MINB))>(p); // (8192 points fp64: 128 registers, one CTA)
+    {
+        constexpr int MB = LG == 13 ? 1 : (C::MINB > 2 ? 2 : C::MINB); // (8192 points fp64: 128 registers, one CTA)
+        const int rc = setup_cta<typename C::type, double, C::THREADS, MB>(p);
+        if constexpr (LG == 12) { // headline size: next group staged into the exchange buffer (+5 %, profiles/r01_fft_l2_prefetch_comparison.txt)
+            static const bool plain = getenv("SDSP_B200_FFT_F64_PLAIN") != nullptr; // comparison aid
+            if (rc == SDSP_B200_OK && !plain)
+                return enable_alias<typename C::type, double, C::THREADS, MB>(p);
+        }
+        return rc;
+    }
     else
         return set_error(SDSP_B200_ERR_UNSUPPORTED, "fft: n=%u in f64 is larger than one CTA can hold and the multi-pass path is not built", p.n);
 }
@@ -1544,7 +1686,8 @@ int sdsp_b200_fft_plan_describe(sdsp_b200_fft_plan plan, char *buf, size_t buf_l
              "threads/CTA=%d frames/CTA=%d smem/CTA=%zuB%s CTAs/SM=%d SMs=%d twiddle-table=%zuB",
              p.n, p.precision == SDSP_B200_F32 ? "f32" : "f64", p.direction == SDSP_B200_FORWARD ? "forward" : "reverse", p.radix,
              p.npass, p.radices[0], p.radices[1], p.radices[2], p.radices[3], p.e, p.threads, p.frames_per_cta, p.smem_bytes,
-             p.double_buffered ? " (double-buffered exchange)" : "", p.ctas_per_sm, p.sm_count, p.tw_bytes);
+             p.double_buffered ? " (double-buffered exchange)" : p.staged ? " (next group staged into the exchange buffer)" : "", p.ctas_per_sm,
+             p.sm_count, p.tw_bytes);
     return SDSP_B200_OK;
 }
 
