@@ -37,6 +37,9 @@ WORKLOADS = {
     "fft4096_f64": dict(kind="fft", n=4096, frames=65536, precision="f64", bytes_per_sample=32),
     "fft65536_f32": dict(kind="fft", n=65536, frames=4096, precision="f32", bytes_per_sample=16),
     "fft1024_f32": dict(kind="fft", n=1024, frames=262144, precision="f32", bytes_per_sample=16),
+    "fft1024_f64": dict(kind="fft", n=1024, frames=262144, precision="f64", bytes_per_sample=32),
+    "fft256_f64": dict(kind="fft", n=256, frames=1 << 20, precision="f64", bytes_per_sample=32),
+    "fft2048_f64": dict(kind="fft", n=2048, frames=131072, precision="f64", bytes_per_sample=32),
     "fft256_f32": dict(kind="fft", n=256, frames=1 << 20, precision="f32", bytes_per_sample=16),
     "fft64_f32": dict(kind="fft", n=64, frames=1 << 22, precision="f32", bytes_per_sample=16),
     "fft32768_f32": dict(kind="fft", n=32768, frames=8192, precision="f32", bytes_per_sample=16),

@@ -1401,7 +1401,7 @@ static int setup_for(FftPlan &p)
     {
         constexpr int MB = LG == 13 ? 1 : (C::MINB > 2 ? 2 : C::MINB); // (8192 points fp64: 128 registers, one CTA)
         const int rc = setup_cta<typename C::type, double, C::THREADS, MB>(p);
-        if constexpr (LG == 12) { // headline size: next group staged into the exchange buffer (+5 %, profiles/r01_fft_l2_prefetch_comparison.txt)
+        if constexpr (LG >= 8 && LG <= 12) { // next group staged into the exchange buffer (+5 %, profiles/r01_fft_l2_prefetch_comparison.txt)
             static const bool plain = getenv("SDSP_B200_FFT_F64_PLAIN") != nullptr; // comparison aid
             if (rc == SDSP_B200_OK && !plain)
                 return enable_alias<typename C::type, double, C::THREADS, MB>(p);
