@@ -529,7 +529,7 @@ static int launch_rows_ring(const IirBank &b, void *data, size_t seg_len, size_t
         }
     }
     // defaults (ring sweeps: profiles/r01_iir_split_ring_sweep.txt): a single warp is issue/latency-bound, the memory system is
-    // filled by having many on an SM -- fp32: two 8 KB stages per warp (13 row-warps per SM), fp64: three (8 per SM)
+    // filled by having many on an SM -- fp32: two 8 KB stages per warp (12 row-warps per SM), fp64: three (8 per SM)
     if constexpr (sizeof(T) == 4)
         return launch_rows_cfg<T, M, KIND, MODE, 2, 2, 2, 1>(b, data, seg_len, segs, stride, row_state, n_samples, stream, slots); // 16 KB
     else
