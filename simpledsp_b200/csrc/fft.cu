@@ -15,6 +15,7 @@
 #include <cuda_runtime.h>
 
 #include "fft_core.cuh"
+#include "tma_ptx.cuh"
 
 namespace sdsp_b200
 {
@@ -104,7 +105,16 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void *p, unsigned bytes) 
 //   write (four per 3-pass frame).
 // DB = true: two buffers used alternately; a pass reads one and writes the other, so only the barrier after
 //   each write remains (two per 3-pass frame).  fs1 = second buffer.
-template <class Cfg, typename T, int THREADS, int MINB, int P, bool DB = false>
+// BAR = 0: the barriers are __syncthreads(); BAR > 0: named barrier BAR over THREADS threads (the CTA holds other warps too).
+template <int BAR, int THREADS>
+__device__ __forceinline__ void cta_sync()
+{
+    if constexpr (BAR == 0)
+        __syncthreads();
+    else
+        asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(THREADS) : "memory");
+}
+template <class Cfg, typename T, int THREADS, int MINB, int P, bool DB = false, int BAR = 0>
 __device__ __forceinline__ void fft_kernel_passes(cplx<T> (&v)[Cfg::E], cplx<T> *fs, const cplx<T> *__restrict__ tw, int t,
                                                   cplx<T> *fs1 = nullptr)
 {
@@ -116,15 +126,15 @@ __device__ __forceinline__ void fft_kernel_passes(cplx<T> (&v)[Cfg::E], cplx<T> 
             for (int e = 0; e < Cfg::E; e++)
                 v[e] = rd[fft_read_phys<Cfg>(t, e)];
             if constexpr (P + 1 < Cfg::NPASS && !DB)
-                __syncthreads(); // everyone has read before this pass overwrites the exchange buffer
+                cta_sync<BAR, THREADS>(); // everyone has read before this pass overwrites the exchange buffer
         }
         fft_pass<Cfg, P, T>(v, t, tw);
         if constexpr (P + 1 < Cfg::NPASS) {
 #pragma unroll
             for (int e = 0; e < Cfg::E; e++)
                 wr[fft_out_phys<Cfg, P>(t, e)] = v[e];
-            __syncthreads();
-            fft_kernel_passes<Cfg, T, THREADS, MINB, P + 1, DB>(v, fs, tw, t, fs1);
+            cta_sync<BAR, THREADS>();
+            fft_kernel_passes<Cfg, T, THREADS, MINB, P + 1, DB, BAR>(v, fs, tw, t, fs1);
         }
     }
 }
@@ -944,6 +954,12 @@ static int setup_cluster64k(FftPlan &p)
 //   at items with smaller tickets, which are held by CTAs that are already running: no deadlock, whatever the residency.
 // geometry of the fused kernel for frames of N1 x 256 points: the column transforms have N1 points (N1 / 16 threads each, so a
 // 256-thread CTA takes 256 / (N1/16) columns per tile), the row transforms 256; both phases have N1 / 16 tiles per frame
+#ifndef SDSP_FUSED_TMA_NST
+#define SDSP_FUSED_TMA_NST 1
+#endif
+#ifndef SDSP_FUSED_TMA_MINB
+#define SDSP_FUSED_TMA_MINB 3
+#endif
 template <int N1>
 struct FusedCols;
 template <>
@@ -1209,6 +1225,304 @@ static int launch_fused(const FftPlan &p, void *data, const void *real_in, size_
     return SDSP_B200_OK;
 }
 
+// -------------------------------------------------------------------------------------------------
+// The fused queue again, fed by a data-mover warp (fp32, N1 <= 256; SDSP_B200_FFT_FUSED_TMA=1).  Warp 8 draws the tickets, waits
+// for each item's dependency and brings its 32 KB tile into a shared-memory stage -- a 3-D TMA box for a column tile (COLS columns
+// x N1 rows out of the frame in HBM), one bulk copy for a row tile (16 contiguous rows of the L2-resident ring) -- while the 256
+// compute threads are still busy with the item before: their items start with shared-memory reads, the queue's latency (ticket,
+// dependency look-up) leaves the compute warps' path altogether, and the only CTA-wide waits left are the exchange barriers.
+//   full[s]  : the producer's arrive (+ the tile's bytes)  -> the compute threads may read stage s and mailbox s_item[s]
+//   empty[s] : 256 arrivals, each thread after it has copied its 16 points into registers -> the producer may refill stage s
+// Ordering of the scratch ring across CTAs: column tiles store with ordinary st.global, then (barrier) thread 0 counts the tile
+// with red.release.gpu; the producer that wants the frame's rows reads the counter with ld.acquire.gpu and issues
+// fence.proxy.async before its bulk copy (generic-proxy writes -> async-proxy read).
+__device__ __forceinline__ void bulk_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)), "l"(gsrc),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void wait_counter(const unsigned *ctr, unsigned target) // one thread
+{
+    while (ld_acquire_gpu(ctr) < target)
+        __nanosleep(64);
+}
+
+template <typename T, int N1, int NST, int MINB>
+__global__ void __launch_bounds__(288, MINB)
+    fft_fused_tma_kernel(const __grid_constant__ CUtensorMap in_map, cplx<T> *__restrict__ data, int real_in, cplx<T> *__restrict__ scratch,
+                         const cplx<T> *__restrict__ tw_cols, const cplx<T> *__restrict__ tw, const cplx<T> *__restrict__ tw_hi,
+                         const cplx<T> *__restrict__ tw_lo, unsigned *__restrict__ ticket, unsigned *__restrict__ col_done,
+                         unsigned *__restrict__ row_done, size_t n_frames, int inverse, T scale)
+{
+    using Cfg = FftCfg<256, 16, 16, 16>;          // rows
+    using CCfg = typename FusedCols<N1>::Cfg;     // columns
+    static_assert(N1 <= 256 && CCfg::NPASS == 2, "one TMA box per column tile, one exchange per item");
+    constexpr int PITCH = LargeStride<Cfg>::value, CPITCH = LargeStride<CCfg>::value;
+    constexpr int N2 = 256, TILES = FusedRing<T, N1>::TILES, COLS = FusedRing<T, N1>::COLS;
+    constexpr int LAG = FusedRing<T, N1>::LAG, RING = FusedRing<T, N1>::RING;
+    constexpr int XBUF = 16 * PITCH > COLS * CPITCH ? 16 * PITCH : COLS * CPITCH;
+    constexpr size_t FRAME = (size_t)N1 * N2;
+    constexpr uint32_t TILE_BYTES = 4096 * sizeof(cplx<T>);
+    constexpr int ND = NST + 1; // completion barriers in rotation
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    cplx<T> *stage0 = reinterpret_cast<cplx<T> *>(smem_raw);
+    cplx<T> *xbuf = stage0 + (size_t)NST * 4096;
+    cplx<T> *s_hi = xbuf + XBUF, *s_lo = s_hi + N1;
+    // (no static shared memory in this kernel: the dynamic area then starts at the window's aligned base, as the TMA boxes need)
+    uint64_t *full = reinterpret_cast<uint64_t *>(s_lo + 256), *empty = full + NST, *done_bar = empty + NST, *xfree = done_bar + ND;
+    unsigned *s_item = reinterpret_cast<unsigned *>(xfree + 1);
+    for (int i = threadIdx.x; i < N1; i += 288)
+        s_hi[i] = tw_hi[i];
+    if (threadIdx.x < 256)
+        s_lo[threadIdx.x] = tw_lo[threadIdx.x];
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NST; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 256);
+        }
+        for (int s = 0; s < ND; s++)
+            mbar_init(&done_bar[s], 256);
+        mbar_init(xfree, 256);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    const size_t total = ((size_t)LAG + 2 * n_frames) * TILES;
+
+    if (threadIdx.x >= 256) { // ---- the data mover; it also counts finished tiles, so no compute warp ever waits on a fence
+        if (threadIdx.x != 256)
+            return;
+        // Finished tiles are counted as soon as their barrier completes -- in particular from inside every wait below: a tile that is
+        // done but not yet counted may be exactly what another CTA's (or this CTA's next) item is waiting for.
+        unsigned *pend[ND];
+        for (int i = 0; i < ND; i++)
+            pend[i] = nullptr;
+        unsigned it = 0, next_pub = 0; // items issued so far = it; items counted so far = next_pub
+        auto count_tile = [&](unsigned j) {
+            unsigned *d = pend[j % ND];
+            if (d)
+                asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(d) : "memory");
+        };
+        auto try_publish = [&]() {
+            while (next_pub < it && mbar_test(&done_bar[next_pub % ND], (next_pub / ND) & 1)) {
+                count_tile(next_pub);
+                next_pub++;
+            }
+        };
+        auto wait_dep = [&](const unsigned *ctr) {
+            while (ld_acquire_gpu(ctr) < (unsigned)TILES) {
+                try_publish();
+                __nanosleep(32);
+            }
+        };
+        for (;; it++) {
+            const int s = it % NST;
+            if (it >= (unsigned)NST) {
+                while (!mbar_test(&empty[s], ((it / NST) - 1) & 1)) // until item it - NST has been taken into registers
+                    try_publish();
+                while (next_pub + ND <= it) { // this item's completion barrier is free again once item it - ND is counted
+                    mbar_wait(&done_bar[next_pub % ND], (next_pub / ND) & 1);
+                    count_tile(next_pub);
+                    next_pub++;
+                }
+            }
+            const size_t q = atomicAdd(ticket, 1u);
+            s_item[s] = q < total ? (unsigned)q : 0xffffffffu;
+            if (q >= total) {
+                mbar_arrive(&full[s]);
+                break;
+            }
+            bool cols;
+            size_t f;
+            int tile;
+            fused_decode<LAG, TILES>(q, cols, f, tile);
+            cplx<T> *dst = stage0 + (size_t)s * 4096;
+            unsigned *d = nullptr;
+            if (f >= n_frames) {
+                mbar_arrive(&full[s]); // empty slot
+            } else if (cols) {
+                if (f >= (size_t)RING)
+                    wait_dep(row_done + (f - RING)); // the ring slot's previous tenant has been read out
+                mbar_expect_tx(&full[s], real_in ? TILE_BYTES / 2 : TILE_BYTES);
+                tma_load_3d(dst, &in_map, real_in ? COLS * tile : 2 * COLS * tile, 0, (int)f, &full[s]);
+                d = col_done + f;
+            } else {
+                wait_dep(col_done + f);
+                asm volatile("fence.proxy.async.global;" ::: "memory");
+                mbar_expect_tx(&full[s], TILE_BYTES);
+                bulk_load_1d(dst, scratch + (f % RING) * FRAME + (size_t)(16 * tile) * N2, TILE_BYTES, &full[s]);
+                d = row_done + f;
+            }
+            pend[it % ND] = d;
+        }
+        for (; next_pub < it; next_pub++) { // the tail: the last items are still to be counted
+            mbar_wait(&done_bar[next_pub % ND], (next_pub / ND) & 1);
+            count_tile(next_pub);
+        }
+        return;
+    }
+
+    // ---- the 256 compute threads: one CTA-wide barrier per item (the exchange); reuse of the exchange buffer by the next item is
+    // ordered by a split barrier (xfree: arrive after the exchange reads, wait before the next item's exchange writes)
+    const int lo16 = threadIdx.x & 15, hi16 = threadIdx.x >> 4;
+    const int ccol = threadIdx.x % COLS, ct = threadIdx.x / COLS;
+    unsigned n_real = 0;
+    for (unsigned it = 0;; it++) {
+        const int s = it % NST;
+        mbar_wait(&full[s], (it / NST) & 1);
+        const unsigned q = s_item[s];
+        if (q == 0xffffffffu)
+            break;
+        bool cols;
+        size_t f;
+        int tile;
+        fused_decode<LAG, TILES>(q, cols, f, tile);
+        const cplx<T> *st = stage0 + (size_t)s * 4096;
+        cplx<T> *sc = scratch + (f % RING) * (FRAME);
+        cplx<T> v[Cfg::E];
+        if (f >= n_frames) {
+            mbar_arrive(&empty[s]);
+            mbar_arrive(&done_bar[it % ND]);
+            continue;
+        }
+        if (cols) {
+            const int t = ct;
+            const unsigned b = (unsigned)COLS * (unsigned)tile + (unsigned)ccol;
+            if (real_in) {
+                const T *rs = reinterpret_cast<const T *>(st);
+#pragma unroll
+                for (int e = 0; e < CCfg::E; e++)
+                    v[e] = cplx<T>{ rs[(t + CCfg::S * e) * COLS + ccol], (T)0 };
+            } else {
+#pragma unroll
+                for (int e = 0; e < CCfg::E; e++)
+                    v[e] = st[(t + CCfg::S * e) * COLS + ccol];
+            }
+            mbar_arrive(&empty[s]);
+            if (inverse) {
+#pragma unroll
+                for (int e = 0; e < CCfg::E; e++)
+                    v[e] = cplx<T>{ v[e].y, v[e].x };
+            }
+            fft_pass<CCfg, 0, T>(v, t, tw_cols);
+            cplx<T> *fs = xbuf + (size_t)ccol * CPITCH;
+            if (n_real > 0)
+                mbar_wait(xfree, (n_real - 1) & 1);
+#pragma unroll
+            for (int e = 0; e < CCfg::E; e++)
+                fs[fft_out_phys<CCfg, 0>(t, e)] = v[e];
+            cta_sync<1, 256>();
+#pragma unroll
+            for (int e = 0; e < CCfg::E; e++)
+                v[e] = fs[fft_read_phys<CCfg>(t, e)];
+            mbar_arrive(xfree);
+            fft_pass<CCfg, 1, T>(v, t, tw_cols);
+            const TwiddleSeq<T> wseq(b * (unsigned)t, b * (unsigned)CCfg::S, s_hi, s_lo);
+            cplx<T> *op = sc + b;
+#pragma unroll
+            for (int e = 0; e < CCfg::E; e++)
+                op[(size_t)(t + CCfg::S * e) * N2] = cmul(v[e], wseq.get(e));
+        } else {
+            const int t = lo16, row = hi16;
+            const cplx<T> *gp = st + row * N2 + t;
+#pragma unroll
+            for (int e = 0; e < Cfg::E; e++)
+                v[e] = gp[Cfg::S * e];
+            mbar_arrive(&empty[s]);
+            fft_pass<Cfg, 0, T>(v, t, tw);
+            cplx<T> *fs = xbuf + (size_t)row * PITCH;
+            if (n_real > 0)
+                mbar_wait(xfree, (n_real - 1) & 1);
+#pragma unroll
+            for (int e = 0; e < Cfg::E; e++)
+                fs[fft_out_phys<Cfg, 0>(t, e)] = v[e];
+            cta_sync<1, 256>();
+            const int row2 = lo16, t2 = hi16;
+            const cplx<T> *rs = xbuf + (size_t)row2 * PITCH;
+#pragma unroll
+            for (int e = 0; e < Cfg::E; e++)
+                v[e] = rs[fft_read_phys<Cfg>(t2, e)];
+            mbar_arrive(xfree);
+            fft_pass<Cfg, 1, T>(v, t2, tw);
+            if (inverse) {
+#pragma unroll
+                for (int e = 0; e < Cfg::E; e++)
+                    v[e] = cplx<T>{ v[e].y * scale, v[e].x * scale };
+            }
+            cplx<T> *op = data + f * (FRAME) + 16 * tile + row2;
+#pragma unroll
+            for (int e = 0; e < Cfg::E; e++)
+                st_stream(op + (size_t)(t2 + Cfg::S * e) * N1, v[e]);
+        }
+        mbar_arrive(&done_bar[it % ND]); // (release: this thread's stores are ordered before the data mover's count)
+        n_real++;
+    }
+}
+
+template <typename T, int N1>
+struct FusedTmaCfg {
+    static constexpr int NST = SDSP_FUSED_TMA_NST, MINB = SDSP_FUSED_TMA_MINB;
+};
+
+template <typename T, int N1>
+static int launch_fused_tma(const FftPlan &p, void *data, const void *real_in, size_t n_frames, cudaStream_t stream)
+{
+    if (n_frames == 0)
+        return SDSP_B200_OK;
+    constexpr int NST = FusedTmaCfg<T, N1>::NST, MINB = FusedTmaCfg<T, N1>::MINB, COLS = FusedRing<T, N1>::COLS;
+    const void *src = real_in ? real_in : data;
+    if (reinterpret_cast<uintptr_t>(src) % 16 != 0 || n_frames > 0x7fffffffu) // the tensor map needs a 16-byte-aligned base
+        return launch_fused<T, N1>(p, data, real_in, n_frames, stream);
+    const size_t need = (1 + 2 * n_frames) * sizeof(unsigned);
+    FftPlan &mp = const_cast<FftPlan &>(p);
+    if (mp.fused_counter_bytes < need) {
+        if (mp.d_fused_counters)
+            cudaFree(mp.d_fused_counters);
+        mp.d_fused_counters = nullptr;
+        mp.fused_counter_bytes = 0;
+        if (cudaMalloc(&mp.d_fused_counters, need) != cudaSuccess) {
+            cudaGetLastError();
+            return set_error(SDSP_B200_ERR_OOM, "fft: cannot allocate %zu bytes of work-queue counters", need);
+        }
+        mp.fused_counter_bytes = need;
+    }
+    SDSP_CUDA(cudaMemsetAsync(mp.d_fused_counters, 0, need, stream));
+    unsigned *ctr = static_cast<unsigned *>(mp.d_fused_counters);
+    // the frames as a [frame][a][b] tensor of T: complex input is 2 x 256 values per row, real input 256
+    const cuuint64_t inner = real_in ? 256 : 512;
+    const cuuint64_t gdim[3] = { inner, (cuuint64_t)N1, (cuuint64_t)n_frames };
+    const cuuint64_t gstride[2] = { inner * sizeof(T), inner * sizeof(T) * N1 };
+    const cuuint32_t box[3] = { (cuuint32_t)(real_in ? COLS : 2 * COLS), (cuuint32_t)N1, 1 };
+    const cuuint32_t estr[3] = { 1, 1, 1 };
+    CUtensorMap map;
+    CUresult r = get_encode_fn()(&map, sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void *>(src),
+                                 gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return set_error(SDSP_B200_ERR_CUDA, "fft: cuTensorMapEncodeTiled failed with %d (n=%u frames=%zu)", (int)r, p.n, n_frames);
+    const size_t items = ((size_t)FusedRing<T, N1>::LAG + 2 * n_frames) * FusedRing<T, N1>::TILES;
+    size_t grid = (size_t)p.sm_count * (size_t)p.ctas_per_sm;
+    if (grid > items)
+        grid = items;
+    fft_fused_tma_kernel<T, N1, NST, MINB><<<(unsigned)grid, 288, p.smem_bytes, stream>>>(
+        map, reinterpret_cast<cplx<T> *>(data), real_in ? 1 : 0, reinterpret_cast<cplx<T> *>(p.d_scratch),
+        reinterpret_cast<const cplx<T> *>(p.d_tw_cols), reinterpret_cast<const cplx<T> *>(p.d_tw_rows),
+        reinterpret_cast<const cplx<T> *>(p.d_tw_hi), reinterpret_cast<const cplx<T> *>(p.d_tw_lo), ctr, ctr + 1, ctr + 1 + n_frames, n_frames,
+        p.direction == SDSP_B200_REVERSE ? 1 : 0, (T)(1.0 / ((double)N1 * 256.0)));
+    SDSP_CUDA(cudaGetLastError());
+    return SDSP_B200_OK;
+}
+
+static bool fused_tma_wanted()
+{
+    static int w = -1;
+    if (w < 0) {
+        const char *e = getenv("SDSP_B200_FFT_FUSED_TMA");
+        w = (e && atoi(e) > 0 && get_encode_fn()) ? 1 : 0;
+    }
+    return w == 1;
+}
+
 template <typename T, int N1>
 static int setup_fused(FftPlan &p)
 {
@@ -1265,6 +1579,23 @@ static int setup_fused(FftPlan &p)
         return rc;
     p.tw_bytes = (tw_total + hi.size() + lo.size()) * sizeof(cplx<T>);
     p.launch = &launch_fused<T, N1>;
+    if constexpr (sizeof(T) == 4 && N1 <= 256) {
+        if (fused_tma_wanted()) { // same queue, tiles brought in by a data-mover warp
+            constexpr int NST = FusedTmaCfg<T, N1>::NST, MINB = FusedTmaCfg<T, N1>::MINB;
+            auto tk = fft_fused_tma_kernel<T, N1, NST, MINB>;
+            const size_t smem = p.smem_bytes + (size_t)NST * 4096 * sizeof(cplx<T>) + 128; // stages + barriers and mailboxes
+            SDSP_CUDA(cudaFuncSetAttribute(tk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int tocc = 0;
+            SDSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tocc, tk, 288, smem));
+            if (tocc >= 1) {
+                p.smem_bytes = smem;
+                p.ctas_per_sm = tocc;
+                p.threads = 288;
+                p.staged = true;
+                p.launch = &launch_fused_tma<T, N1>;
+            }
+        }
+    }
     return SDSP_B200_OK;
 }
 
@@ -1658,9 +1989,10 @@ int sdsp_b200_fft_plan_describe(sdsp_b200_fft_plan plan, char *buf, size_t buf_l
                  "fft n=%u %s %s radix-arg=%d: one persistent kernel, single pass over HBM: n = %d x 256; per frame %d column tiles (%d columns "
                  "x %d-point transforms, twiddle) -> ring of %zu scratch frames resident in L2 -> %d row tiles (16 rows x 256-point "
                  "transforms, threads re-mapped between the passes), ordered by an atomic work queue with per-frame completion counters; "
-                 "256 threads/CTA, smem/CTA=%zuB, CTAs/SM=%d, SMs=%d",
+                 "%d threads/CTA%s, smem/CTA=%zuB, CTAs/SM=%d, SMs=%d",
                  p.n, p.precision == SDSP_B200_F32 ? "f32" : "f64", p.direction == SDSP_B200_FORWARD ? "forward" : "reverse", p.radix, p.n1,
-                 tiles, cols, p.n1, p.scratch_frames, tiles, p.smem_bytes, p.ctas_per_sm, p.sm_count);
+                 tiles, cols, p.n1, p.scratch_frames, tiles, p.threads, p.staged ? " (256 compute + a TMA data-mover warp)" : "", p.smem_bytes,
+                 p.ctas_per_sm, p.sm_count);
         return SDSP_B200_OK;
     }
     if (p.cluster) {
