@@ -954,6 +954,9 @@ static int setup_cluster64k(FftPlan &p)
 //   at items with smaller tickets, which are held by CTAs that are already running: no deadlock, whatever the residency.
 // geometry of the fused kernel for frames of N1 x 256 points: the column transforms have N1 points (N1 / 16 threads each, so a
 // 256-thread CTA takes 256 / (N1/16) columns per tile), the row transforms 256; both phases have N1 / 16 tiles per frame
+#ifndef SDSP_FUSED_LEAD_F32
+#define SDSP_FUSED_LEAD_F32 512 // tiles of lead between a frame's column tiles and its row tiles (fp32)
+#endif
 #ifndef SDSP_FUSED_TMA_NST
 #define SDSP_FUSED_TMA_NST 1
 #endif
@@ -991,7 +994,7 @@ struct FusedRing {
     static constexpr int TILES = N1 / 16;                     // tiles per frame, either phase
     static constexpr int COLS = 256 / (N1 / 16);              // columns per column tile
     // frames between a frame's column tiles and its row tiles: 512 (fp32) / 256 (fp64) tiles of lead, more than the CTAs in flight
-    static constexpr int LAG = (sizeof(T) == 4 ? 512 : 256) / TILES;
+    static constexpr int LAG = (sizeof(T) == 4 ? SDSP_FUSED_LEAD_F32 : 256) / TILES;
     static constexpr int RING = 2 * LAG;                      // scratch frames: 32 MB whatever the frame size
 };
 
@@ -1226,7 +1229,7 @@ static int launch_fused(const FftPlan &p, void *data, const void *real_in, size_
 }
 
 // -------------------------------------------------------------------------------------------------
-// The fused queue again, fed by a data-mover warp (fp32, N1 <= 256; SDSP_B200_FFT_FUSED_TMA=1).  Warp 8 draws the tickets, waits
+// The fused queue again, fed by a data-mover warp (fp32, N1 <= 256: the default there; SDSP_B200_FFT_FUSED_TMA=0 disables).  Warp 8 draws the tickets, waits
 // for each item's dependency and brings its 32 KB tile into a shared-memory stage -- a 3-D TMA box for a column tile (COLS columns
 // x N1 rows out of the frame in HBM), one bulk copy for a row tile (16 contiguous rows of the L2-resident ring) -- while the 256
 // compute threads are still busy with the item before: their items start with shared-memory reads, the queue's latency (ticket,
@@ -1315,6 +1318,8 @@ __global__ void __launch_bounds__(288, MINB)
                 __nanosleep(32);
             }
         };
+        // (Drawing the ticket while the stage is still occupied was measured and is slower: a ticket held without being worked on
+        // delays every item that depends on it.  profiles/r01_fft65536_variants.txt)
         for (;; it++) {
             const int s = it % NST;
             if (it >= (unsigned)NST) {
@@ -1341,13 +1346,16 @@ __global__ void __launch_bounds__(288, MINB)
             if (f >= n_frames) {
                 mbar_arrive(&full[s]); // empty slot
             } else if (cols) {
+                // the dependency of a column tile guards the compute threads' stores into the ring, not this copy: start the copy,
+                // then look at the counter, and only then hand the stage over
+                mbar_expect_tx_only(&full[s], real_in ? TILE_BYTES / 2 : TILE_BYTES);
+                tma_load_3d(dst, &in_map, real_in ? COLS * tile : 2 * COLS * tile, 0, (int)f, &full[s]);
                 if (f >= (size_t)RING)
                     wait_dep(row_done + (f - RING)); // the ring slot's previous tenant has been read out
-                mbar_expect_tx(&full[s], real_in ? TILE_BYTES / 2 : TILE_BYTES);
-                tma_load_3d(dst, &in_map, real_in ? COLS * tile : 2 * COLS * tile, 0, (int)f, &full[s]);
+                mbar_arrive(&full[s]);
                 d = col_done + f;
             } else {
-                wait_dep(col_done + f);
+                wait_dep(col_done + f); // the frame's column tiles are all in the ring
                 asm volatile("fence.proxy.async.global;" ::: "memory");
                 mbar_expect_tx(&full[s], TILE_BYTES);
                 bulk_load_1d(dst, scratch + (f % RING) * FRAME + (size_t)(16 * tile) * N2, TILE_BYTES, &full[s]);
@@ -1517,8 +1525,8 @@ static bool fused_tma_wanted()
 {
     static int w = -1;
     if (w < 0) {
-        const char *e = getenv("SDSP_B200_FFT_FUSED_TMA");
-        w = (e && atoi(e) > 0 && get_encode_fn()) ? 1 : 0;
+        const char *e = getenv("SDSP_B200_FFT_FUSED_TMA"); // =0: the variant whose compute threads load their own tiles
+        w = ((!e || atoi(e) > 0) && get_encode_fn()) ? 1 : 0;
     }
     return w == 1;
 }

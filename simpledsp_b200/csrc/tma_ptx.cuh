@@ -31,6 +31,10 @@ namespace
     {
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
     }
+    __device__ __forceinline__ void mbar_expect_tx_only(uint64_t *bar, uint32_t bytes) // raises the byte count, no arrival
+    {
+        asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    }
     __device__ __forceinline__ void mbar_arrive(uint64_t *bar) // release at CTA scope: orders this thread's earlier writes
     {
         asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
