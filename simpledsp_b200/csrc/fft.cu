@@ -957,6 +957,9 @@ static int setup_cluster64k(FftPlan &p)
 #ifndef SDSP_FUSED_LEAD_F32
 #define SDSP_FUSED_LEAD_F32 512 // tiles of lead between a frame's column tiles and its row tiles (fp32)
 #endif
+#ifndef SDSP_FUSED_POLL
+#define SDSP_FUSED_POLL mbar_test // or mbar_try: one try_wait (suspends up to the hardware time limit) per round
+#endif
 #ifndef SDSP_FUSED_TMA_NST
 #define SDSP_FUSED_TMA_NST 1
 #endif
@@ -1318,12 +1321,13 @@ __global__ void __launch_bounds__(288, MINB)
                 __nanosleep(32);
             }
         };
-        // (Drawing the ticket while the stage is still occupied was measured and is slower: a ticket held without being worked on
-        // delays every item that depends on it.  profiles/r01_fft65536_variants.txt)
+        // When to draw the next ticket: as late as possible -- once the stage is free.  A ticket held without being worked on delays
+        // every item that depends on it: drawing a whole item early, or when the compute threads pass the exchange of the item
+        // before, were both measured slower although they take the ticket's round trip off the path (profiles/r01_fft65536_variants.txt).
         for (;; it++) {
             const int s = it % NST;
             if (it >= (unsigned)NST) {
-                while (!mbar_test(&empty[s], ((it / NST) - 1) & 1)) // until item it - NST has been taken into registers
+                while (!SDSP_FUSED_POLL(&empty[s], ((it / NST) - 1) & 1)) // until item it - NST has been taken into registers
                     try_publish();
                 while (next_pub + ND <= it) { // this item's completion barrier is free again once item it - ND is counted
                     mbar_wait(&done_bar[next_pub % ND], (next_pub / ND) & 1);
@@ -1332,18 +1336,22 @@ __global__ void __launch_bounds__(288, MINB)
                 }
             }
             const size_t q = atomicAdd(ticket, 1u);
+            bool cols = false;
+            size_t f = n_frames;
+            int tile = 0;
+            if (q < total)
+                fused_decode<LAG, TILES>(q, cols, f, tile);
+            const bool real = q < total && f < n_frames;
+            if (real && !cols)
+                wait_dep(col_done + f); // the frame's column tiles are all in the ring
             s_item[s] = q < total ? (unsigned)q : 0xffffffffu;
             if (q >= total) {
                 mbar_arrive(&full[s]);
                 break;
             }
-            bool cols;
-            size_t f;
-            int tile;
-            fused_decode<LAG, TILES>(q, cols, f, tile);
             cplx<T> *dst = stage0 + (size_t)s * 4096;
             unsigned *d = nullptr;
-            if (f >= n_frames) {
+            if (!real) {
                 mbar_arrive(&full[s]); // empty slot
             } else if (cols) {
                 // the dependency of a column tile guards the compute threads' stores into the ring, not this copy: start the copy,
@@ -1355,7 +1363,6 @@ __global__ void __launch_bounds__(288, MINB)
                 mbar_arrive(&full[s]);
                 d = col_done + f;
             } else {
-                wait_dep(col_done + f); // the frame's column tiles are all in the ring
                 asm volatile("fence.proxy.async.global;" ::: "memory");
                 mbar_expect_tx(&full[s], TILE_BYTES);
                 bulk_load_1d(dst, scratch + (f % RING) * FRAME + (size_t)(16 * tile) * N2, TILE_BYTES, &full[s]);
@@ -1512,11 +1519,14 @@ static int launch_fused_tma(const FftPlan &p, void *data, const void *real_in, s
     size_t grid = (size_t)p.sm_count * (size_t)p.ctas_per_sm;
     if (grid > items)
         grid = items;
-    fft_fused_tma_kernel<T, N1, NST, MINB><<<(unsigned)grid, 288, p.smem_bytes, stream>>>(
-        map, reinterpret_cast<cplx<T> *>(data), real_in ? 1 : 0, reinterpret_cast<cplx<T> *>(p.d_scratch),
-        reinterpret_cast<const cplx<T> *>(p.d_tw_cols), reinterpret_cast<const cplx<T> *>(p.d_tw_rows),
-        reinterpret_cast<const cplx<T> *>(p.d_tw_hi), reinterpret_cast<const cplx<T> *>(p.d_tw_lo), ctr, ctr + 1, ctr + 1 + n_frames, n_frames,
-        p.direction == SDSP_B200_REVERSE ? 1 : 0, (T)(1.0 / ((double)N1 * 256.0)));
+    cplx<T> *a_data = reinterpret_cast<cplx<T> *>(data), *a_scratch = reinterpret_cast<cplx<T> *>(p.d_scratch);
+    const cplx<T> *a_twc = reinterpret_cast<const cplx<T> *>(p.d_tw_cols), *a_twr = reinterpret_cast<const cplx<T> *>(p.d_tw_rows);
+    const cplx<T> *a_hi = reinterpret_cast<const cplx<T> *>(p.d_tw_hi), *a_lo = reinterpret_cast<const cplx<T> *>(p.d_tw_lo);
+    unsigned *a_col = ctr + 1, *a_row = ctr + 1 + n_frames;
+    const int a_real = real_in ? 1 : 0, a_inv = p.direction == SDSP_B200_REVERSE ? 1 : 0;
+    const T a_scale = (T)(1.0 / ((double)N1 * 256.0));
+    fft_fused_tma_kernel<T, N1, NST, MINB><<<(unsigned)grid, 288, p.smem_bytes, stream>>>(map, a_data, a_real, a_scratch, a_twc, a_twr, a_hi, a_lo, ctr,
+                                                                                         a_col, a_row, n_frames, a_inv, a_scale);
     SDSP_CUDA(cudaGetLastError());
     return SDSP_B200_OK;
 }

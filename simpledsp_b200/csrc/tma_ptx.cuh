@@ -31,6 +31,20 @@ namespace
     {
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
     }
+    __device__ __forceinline__ bool mbar_try(uint64_t *bar, uint32_t parity) // one try_wait: may suspend up to the hardware time limit
+    {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        return ok != 0;
+    }
     __device__ __forceinline__ void mbar_expect_tx_only(uint64_t *bar, uint32_t bytes) // raises the byte count, no arrival
     {
         asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
