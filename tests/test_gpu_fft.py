@@ -242,3 +242,46 @@ def test_fused_65536_kernel_at_the_edges_of_its_work_queue(frames):
     out = fwd.real(xr)
     torch.cuda.synchronize()
     assert torch.equal(z, out)
+
+
+_OTHER_QUEUE_SNIPPET = r"""
+import sys, numpy as np, torch
+import simpledsp_b200 as S
+from simpledsp_b200 import _capi as K
+n, frames = int(sys.argv[1]), int(sys.argv[2])
+g = torch.Generator(device="cuda").manual_seed(7)
+x = torch.view_as_complex(torch.randn(frames, n, 2, device="cuda", generator=g, dtype=torch.float32))
+plan = S.FftPlan(n, 4 if (n.bit_length() - 1) % 2 == 0 else 2, K.F32, K.FORWARD)
+print("PLAN", plan.describe())
+plan(x)
+torch.cuda.synchronize()
+np.save(sys.argv[3], x.cpu().numpy())
+"""
+
+
+@pytest.mark.parametrize("n", [32768, 65536])
+def test_fused_queue_with_and_without_the_data_mover_warp_agree(n, tmp_path):
+    """fp32 frames of 2^15 / 2^16 points run the work queue fed by a TMA data-mover warp by default; SDSP_B200_FFT_FUSED_TMA=0
+    selects the variant whose compute threads load their own tiles.  Same arithmetic in the same order: the two must give the
+    same bits (each in its own process: the choice is read once per process)."""
+    import os
+    import subprocess
+    import sys
+
+    from tests.util import ROOT
+
+    outs = {}
+    for flag in ("1", "0"):
+        path = str(tmp_path / f"out_{flag}.npy")
+        env = dict(os.environ, SDSP_B200_FFT_FUSED_TMA=flag, PYTHONPATH=ROOT)
+        r = subprocess.run([sys.executable, "-c", _OTHER_QUEUE_SNIPPET, str(n), "97", path], env=env, capture_output=True, text=True, timeout=300, cwd=ROOT)
+        assert r.returncode == 0, r.stderr[-2000:]
+        assert ("data-mover" in r.stdout) == (flag == "1"), r.stdout
+        outs[flag] = np.load(path)
+    assert np.array_equal(outs["1"], outs["0"])
+    g = np.random.default_rng(0).integers(0, 97, 3)
+    # and against the oracle, for a few frames, using the same generator seed as the snippet
+    torch = pytest.importorskip("torch")
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    x = torch.view_as_complex(torch.randn(97, n, 2, device="cuda", generator=gen, dtype=torch.float32)).cpu().numpy()
+    assert rel_l2(outs["1"][g], oracle_fft(x[g])) <= FFT_TOL["f32"]
