@@ -74,7 +74,7 @@ WORKLOADS = {
 NCU_TRAFFIC = {
     "fft4096_f32": (4.2705e9, "profiles/r01_ncu_fft4096_f32_v2.txt"),
     "fft4096_f64": (8.683e9, "profiles/r01_ncu_fft4096_f64_v2.txt"),
-    "fft65536_f32": (5.2328e9, "profiles/r01_ncu_fft65536_f32_fused_tma_v1.txt"),
+    "fft65536_f32": (4.3077e9, "profiles/r01_ncu_fft65536_f32_fused_tma_v2.txt"),
     "iir16384_f32": (1.37386e11, "profiles/r01_ncu_iir16384_f32_tma_v5.txt"),
     "iir4096_f32_scan": (1.37408e11, "profiles/r01_ncu_iir4096_f32_split_v1.txt (main pass)"),
     "iirscan_f64": (1.7126e10, "profiles/r01_launches_iir_split_v1.txt (main pass)"),

@@ -957,6 +957,9 @@ static int setup_cluster64k(FftPlan &p)
 #ifndef SDSP_FUSED_LEAD_F32
 #define SDSP_FUSED_LEAD_F32 512 // tiles of lead between a frame's column tiles and its row tiles (fp32)
 #endif
+#ifndef SDSP_FUSED_LEAD_F32_TMA
+#define SDSP_FUSED_LEAD_F32_TMA 768
+#endif
 #ifndef SDSP_FUSED_POLL
 #define SDSP_FUSED_POLL mbar_test // or mbar_try: one try_wait (suspends up to the hardware time limit) per round
 #endif
@@ -997,8 +1000,9 @@ struct FusedRing {
     static constexpr int TILES = N1 / 16;                     // tiles per frame, either phase
     static constexpr int COLS = 256 / (N1 / 16);              // columns per column tile
     // frames between a frame's column tiles and its row tiles: 512 (fp32) / 256 (fp64) tiles of lead, more than the CTAs in flight
-    static constexpr int LAG = (sizeof(T) == 4 ? SDSP_FUSED_LEAD_F32 : 256) / TILES;
-    static constexpr int RING = 2 * LAG;                      // scratch frames: 32 MB whatever the frame size
+    // (fp32, N1 <= 256 -- the sizes the data-mover kernel takes, which discards consumed ring lines: 768 tiles of lead, 48 MB)
+    static constexpr int LAG = (sizeof(T) == 4 ? (N1 <= 256 ? SDSP_FUSED_LEAD_F32_TMA : SDSP_FUSED_LEAD_F32) : 256) / TILES;
+    static constexpr int RING = 2 * LAG;                      // scratch frames: 32 MB (48 MB) whatever the frame size
 };
 
 __device__ __forceinline__ cplx<float> ld_l2(const cplx<float> *p)
@@ -1327,6 +1331,8 @@ __global__ void __launch_bounds__(288, MINB)
         for (;; it++) {
             const int s = it % NST;
             if (it >= (unsigned)NST) {
+                // (counting here, promptly, matters: leaving it until the next copy is out was measured 3 % slower -- other CTAs'
+                // row tiles follow their frame's column tiles by barely more than an item's latency)
                 while (!SDSP_FUSED_POLL(&empty[s], ((it / NST) - 1) & 1)) // until item it - NST has been taken into registers
                     try_publish();
                 while (next_pub + ND <= it) { // this item's completion barrier is free again once item it - ND is counted
@@ -1444,6 +1450,11 @@ __global__ void __launch_bounds__(288, MINB)
             for (int e = 0; e < Cfg::E; e++)
                 v[e] = gp[Cfg::S * e];
             mbar_arrive(&empty[s]);
+            // the tile's 32 KB of the ring are dead now (256 lines of 128 bytes, one per thread): drop them from L2 instead of
+            // letting them be written back to HBM when they are evicted -- that is what makes a 48 MB ring affordable
+            // (profiles/r01_fft65536_variants.txt)
+            if constexpr (sizeof(cplx<T>) == 8)
+                asm volatile("discard.global.L2 [%0], 128;" ::"l"(sc + (size_t)(16 * tile) * N2 + (size_t)threadIdx.x * 16) : "memory");
             fft_pass<Cfg, 0, T>(v, t, tw);
             cplx<T> *fs = xbuf + (size_t)row * PITCH;
             if (n_real > 0)

@@ -212,10 +212,11 @@ def test_real_input_frames_match_oracle(n, prec):
     assert torch.equal(z, yd)
 
 
-@pytest.mark.parametrize("frames", [1, 2, 31, 32, 33, 63, 64, 65, 127, 129, 200])
+@pytest.mark.parametrize("frames", [1, 2, 31, 32, 33, 47, 48, 49, 63, 64, 65, 95, 96, 97, 127, 129, 200])
 def test_fused_65536_kernel_at_the_edges_of_its_work_queue(frames):
-    """The 65536-point kernel orders column and row tiles through a queue with a 32-frame lag and a 64-frame scratch ring
-    (fp32): frame counts below, at and just past those boundaries, forward and reverse, complex and real input."""
+    """The 65536-point kernel orders column and row tiles through a queue with a 48-frame lag and a 96-frame scratch ring
+    (fp32; 32 / 64 in the variant without the data-mover warp): frame counts below, at and just past those boundaries,
+    forward and reverse, complex and real input."""
     torch = pytest.importorskip("torch")
     n = 65536
     g = torch.Generator(device="cuda").manual_seed(frames)
@@ -224,7 +225,7 @@ def test_fused_65536_kernel_at_the_edges_of_its_work_queue(frames):
     y = x.clone()
     fwd(y)
     torch.cuda.synchronize()
-    idx = sorted({0, frames // 2, frames - 1, min(31, frames - 1), min(64, frames - 1)})
+    idx = sorted({0, frames // 2, frames - 1, min(31, frames - 1), min(48, frames - 1), min(64, frames - 1), min(96, frames - 1)})
     ref = oracle_fft(x[idx].cpu().numpy())
     assert rel_l2(y[idx].cpu().numpy(), ref) <= FFT_TOL["f32"]
     # every frame: Parseval, then the round trip
