@@ -1236,7 +1236,7 @@ static int launch_fused(const FftPlan &p, void *data, const void *real_in, size_
 }
 
 // -------------------------------------------------------------------------------------------------
-// The fused queue again, fed by a data-mover warp (fp32, N1 <= 256: the default there; SDSP_B200_FFT_FUSED_TMA=0 disables).  Warp 8 draws the tickets, waits
+// The fused queue again, fed by a data-mover warp (fp32: the default there; SDSP_B200_FFT_FUSED_TMA=0 disables).  Warp 8 draws the tickets, waits
 // for each item's dependency and brings its 32 KB tile into a shared-memory stage -- a 3-D TMA box for a column tile (COLS columns
 // x N1 rows out of the frame in HBM), one bulk copy for a row tile (16 contiguous rows of the L2-resident ring) -- while the 256
 // compute threads are still busy with the item before: their items start with shared-memory reads, the queue's latency (ticket,
@@ -1267,7 +1267,7 @@ __global__ void __launch_bounds__(288, MINB)
 {
     using Cfg = FftCfg<256, 16, 16, 16>;          // rows
     using CCfg = typename FusedCols<N1>::Cfg;     // columns
-    static_assert(N1 <= 256 && CCfg::NPASS == 2, "one TMA box per column tile, one exchange per item");
+    constexpr int BOXES = N1 <= 256 ? 1 : N1 / 256; // a TMA box holds at most 256 rows
     constexpr int PITCH = LargeStride<Cfg>::value, CPITCH = LargeStride<CCfg>::value;
     constexpr int N2 = 256, TILES = FusedRing<T, N1>::TILES, COLS = FusedRing<T, N1>::COLS;
     constexpr int LAG = FusedRing<T, N1>::LAG, RING = FusedRing<T, N1>::RING;
@@ -1363,7 +1363,12 @@ __global__ void __launch_bounds__(288, MINB)
                 // the dependency of a column tile guards the compute threads' stores into the ring, not this copy: start the copy,
                 // then look at the counter, and only then hand the stage over
                 mbar_expect_tx_only(&full[s], real_in ? TILE_BYTES / 2 : TILE_BYTES);
-                tma_load_3d(dst, &in_map, real_in ? COLS * tile : 2 * COLS * tile, 0, (int)f, &full[s]);
+#pragma unroll
+                for (int bx = 0; bx < BOXES; bx++) {
+                    void *bd = real_in ? static_cast<void *>(reinterpret_cast<T *>(dst) + (size_t)bx * 256 * COLS)
+                                       : static_cast<void *>(dst + (size_t)bx * 256 * COLS);
+                    tma_load_3d(bd, &in_map, real_in ? COLS * tile : 2 * COLS * tile, 256 * bx, (int)f, &full[s]);
+                }
                 if (f >= (size_t)RING)
                     wait_dep(row_done + (f - RING)); // the ring slot's previous tenant has been read out
                 mbar_arrive(&full[s]);
@@ -1425,19 +1430,26 @@ __global__ void __launch_bounds__(288, MINB)
                 for (int e = 0; e < CCfg::E; e++)
                     v[e] = cplx<T>{ v[e].y, v[e].x };
             }
-            fft_pass<CCfg, 0, T>(v, t, tw_cols);
             cplx<T> *fs = xbuf + (size_t)ccol * CPITCH;
-            if (n_real > 0)
-                mbar_wait(xfree, (n_real - 1) & 1);
+            if constexpr (CCfg::NPASS == 2) {
+                fft_pass<CCfg, 0, T>(v, t, tw_cols);
+                if (n_real > 0)
+                    mbar_wait(xfree, (n_real - 1) & 1);
 #pragma unroll
-            for (int e = 0; e < CCfg::E; e++)
-                fs[fft_out_phys<CCfg, 0>(t, e)] = v[e];
-            cta_sync<1, 256>();
+                for (int e = 0; e < CCfg::E; e++)
+                    fs[fft_out_phys<CCfg, 0>(t, e)] = v[e];
+                cta_sync<1, 256>();
 #pragma unroll
-            for (int e = 0; e < CCfg::E; e++)
-                v[e] = fs[fft_read_phys<CCfg>(t, e)];
-            mbar_arrive(xfree);
-            fft_pass<CCfg, 1, T>(v, t, tw_cols);
+                for (int e = 0; e < CCfg::E; e++)
+                    v[e] = fs[fft_read_phys<CCfg>(t, e)];
+                mbar_arrive(xfree);
+                fft_pass<CCfg, 1, T>(v, t, tw_cols);
+            } else { // three passes: two exchanges with the usual barriers between them, inside the split barrier
+                if (n_real > 0)
+                    mbar_wait(xfree, (n_real - 1) & 1);
+                fft_kernel_passes<CCfg, T, 256, MINB, 0, false, 1>(v, fs, tw_cols, t);
+                mbar_arrive(xfree);
+            }
             const TwiddleSeq<T> wseq(b * (unsigned)t, b * (unsigned)CCfg::S, s_hi, s_lo);
             cplx<T> *op = sc + b;
 #pragma unroll
@@ -1518,7 +1530,7 @@ static int launch_fused_tma(const FftPlan &p, void *data, const void *real_in, s
     const cuuint64_t inner = real_in ? 256 : 512;
     const cuuint64_t gdim[3] = { inner, (cuuint64_t)N1, (cuuint64_t)n_frames };
     const cuuint64_t gstride[2] = { inner * sizeof(T), inner * sizeof(T) * N1 };
-    const cuuint32_t box[3] = { (cuuint32_t)(real_in ? COLS : 2 * COLS), (cuuint32_t)N1, 1 };
+    const cuuint32_t box[3] = { (cuuint32_t)(real_in ? COLS : 2 * COLS), (cuuint32_t)(N1 < 256 ? N1 : 256), 1 };
     const cuuint32_t estr[3] = { 1, 1, 1 };
     CUtensorMap map;
     CUresult r = get_encode_fn()(&map, sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void *>(src),
@@ -1608,7 +1620,7 @@ static int setup_fused(FftPlan &p)
         return rc;
     p.tw_bytes = (tw_total + hi.size() + lo.size()) * sizeof(cplx<T>);
     p.launch = &launch_fused<T, N1>;
-    if constexpr (sizeof(T) == 4 && N1 <= 256) {
+    if constexpr (sizeof(T) == 4) {
         if (fused_tma_wanted()) { // same queue, tiles brought in by a data-mover warp
             constexpr int NST = FusedTmaCfg<T, N1>::NST, MINB = FusedTmaCfg<T, N1>::MINB;
             auto tk = fft_fused_tma_kernel<T, N1, NST, MINB>;
