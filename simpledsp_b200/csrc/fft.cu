@@ -1000,8 +1000,9 @@ struct FusedRing {
     static constexpr int TILES = N1 / 16;                     // tiles per frame, either phase
     static constexpr int COLS = 256 / (N1 / 16);              // columns per column tile
     // frames between a frame's column tiles and its row tiles: 512 (fp32) / 256 (fp64) tiles of lead, more than the CTAs in flight
-    // (fp32, N1 <= 256 -- the sizes the data-mover kernel takes, which discards consumed ring lines: 768 tiles of lead, 48 MB)
-    static constexpr int LAG = (sizeof(T) == 4 ? (N1 <= 256 ? SDSP_FUSED_LEAD_F32_TMA : SDSP_FUSED_LEAD_F32) : 256) / TILES;
+    // (fp32 runs the data-mover kernel, which discards consumed ring lines: 768 tiles of lead, 48 MB, measured best up to
+    // N1 = 512; 512 tiles for N1 = 1024)
+    static constexpr int LAG = (sizeof(T) == 4 ? (N1 <= 512 ? SDSP_FUSED_LEAD_F32_TMA : SDSP_FUSED_LEAD_F32) : 256) / TILES;
     static constexpr int RING = 2 * LAG;                      // scratch frames: 32 MB (48 MB) whatever the frame size
 };
 
