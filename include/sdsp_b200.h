@@ -184,6 +184,11 @@ int sdsp_b200_debug_emulate_iir_scan(int sections, int numerator, int precision,
  * (unstable or marginal filter).  Segments of a time-split call are at least this long. */
 int sdsp_b200_debug_iir_decay_length(int sections, int numerator, int precision, const double *b, const double *a,
                                      unsigned long long *samples);
+/* Host only.  The order in which the work-queue FFT kernels (frames larger than one CTA, n = n1 x 256) hand out their items:
+ * geom = { tiles per frame and phase, columns per column tile, lag in frames, scratch-ring frames }; item = { 1 = column tile /
+ * 0 = row tile, tile index, frame } for ticket q (frames past the batch are empty slots).  A row tile waits for the column tiles
+ * of its frame, a column tile for the row tiles of frame - ring: both must hold smaller tickets. */
+int sdsp_b200_debug_fft_queue_item(unsigned n, int precision, unsigned long long q, int *geom, int *item);
 
 #ifdef __cplusplus
 }

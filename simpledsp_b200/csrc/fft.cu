@@ -1032,7 +1032,7 @@ __device__ __forceinline__ void spin_until(const unsigned *ctr, unsigned target,
 
 // decode work item q -> (column tile?, frame, tile); frame >= n_frames marks an empty slot
 template <int LAG, int TILES>
-__device__ __forceinline__ void fused_decode(size_t q, bool &cols, size_t &f, int &tile)
+__host__ __device__ __forceinline__ void fused_decode(size_t q, bool &cols, size_t &f, int &tile)
 {
     const size_t slot = q / TILES;
     tile = (int)(q % TILES);
@@ -1276,8 +1276,8 @@ __global__ void __launch_bounds__(288, MINB)
     constexpr size_t FRAME = (size_t)N1 * N2;
     constexpr uint32_t TILE_BYTES = 4096 * sizeof(cplx<T>);
     constexpr int ND = NST + 1; // completion barriers in rotation
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    cplx<T> *stage0 = reinterpret_cast<cplx<T> *>(smem_raw);
+    extern __shared__ __align__(128) unsigned char smem_raw128[];
+    cplx<T> *stage0 = reinterpret_cast<cplx<T> *>(smem_raw128);
     cplx<T> *xbuf = stage0 + (size_t)NST * 4096;
     cplx<T> *s_hi = xbuf + XBUF, *s_lo = s_hi + N1;
     // (no static shared memory in this kernel: the dynamic area then starts at the window's aligned base, as the TMA boxes need)
@@ -1849,6 +1849,24 @@ struct sdsp_b200_fft_plan_s {
     FftPlan p;
 };
 
+// host-side view of the fused kernels' work queue (tests/test_capi_cpu.py checks the dependency argument on it)
+template <typename T, int N1>
+static void fused_queue_item(unsigned long long q, int *geom, int *item)
+{
+    using R = FusedRing<T, N1>;
+    geom[0] = R::TILES;
+    geom[1] = R::COLS;
+    geom[2] = R::LAG;
+    geom[3] = R::RING;
+    bool cols;
+    size_t f;
+    int tile;
+    fused_decode<R::LAG, R::TILES>((size_t)q, cols, f, tile);
+    item[0] = cols ? 1 : 0;
+    item[1] = tile;
+    item[2] = (int)(f & 0x7fffffff);
+}
+
 extern "C" {
 
 int sdsp_b200_fft_plan_create(sdsp_b200_fft_plan *plan, uint32_t n, int radix, int precision, int direction, int device)
@@ -2063,6 +2081,25 @@ int sdsp_b200_fft_plan_describe(sdsp_b200_fft_plan plan, char *buf, size_t buf_l
              p.double_buffered ? " (double-buffered exchange)" : p.staged ? " (next group staged into the exchange buffer)" : "", p.ctas_per_sm,
              p.sm_count, p.tw_bytes);
     return SDSP_B200_OK;
+}
+
+int sdsp_b200_debug_fft_queue_item(unsigned n, int precision, unsigned long long q, int *geom, int *item)
+{
+    if (!geom || !item || (precision != SDSP_B200_F32 && precision != SDSP_B200_F64) || n % 256 != 0)
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "debug_fft_queue_item: bad arguments");
+    const bool f32 = precision == SDSP_B200_F32;
+    switch (n / 256) {
+#define X(N1) \
+    case N1: \
+        if (f32) \
+            fused_queue_item<float, N1>(q, geom, item); \
+        else \
+            fused_queue_item<double, N1>(q, geom, item); \
+        return SDSP_B200_OK;
+        X(32) X(64) X(128) X(256) X(512) X(1024)
+#undef X
+    default: return set_error(SDSP_B200_ERR_UNSUPPORTED, "debug_fft_queue_item: n=%u is not a size the work-queue kernels take", n);
+    }
 }
 
 int sdsp_b200_fft_plan_launches(sdsp_b200_fft_plan plan, size_t n_frames, int *launches)

@@ -232,3 +232,45 @@ def test_time_split_algorithm_on_the_host(case):
         # low-cutoff fp32 recurrence is itself up to 1e-4 of peak from the truth -- the bound is the IIR tolerance
         tol = 1e-12 if pname == "f64" else (3 * IIR_TOL["f32"] if f0 < 1e3 else IIR_TOL["f32"])
         assert np.abs(y - whole).max() / peak <= tol, (case, pname)
+
+
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+@pytest.mark.parametrize("n1", [32, 64, 128, 256, 512, 1024])
+def test_fft_work_queue_order_makes_every_wait_point_at_a_smaller_ticket(n1, prec):
+    """Frames larger than one CTA run as a queue of column tiles and row tiles handed out in ticket order
+    (fft_fused_kernel / fft_fused_tma_kernel).  Its freedom from deadlock rests on the order alone: a row tile waits for the
+    column tiles of its frame, a column tile for the row tiles of the frame that held its scratch-ring slot before -- both
+    must have been handed out EARLIER, whatever the batch size.  Checked here on the kernels' own decode function
+    (sdsp_b200_debug_fft_queue_item), for batches below, at and past the lag and the ring size."""
+    L = K.lib()
+    geom, item = (C.c_int * 4)(), (C.c_int * 3)()
+    p = K.F32 if prec == "f32" else K.F64
+    K.check(L.sdsp_b200_debug_fft_queue_item(n1 * 256, p, 0, geom, item))
+    tiles, cols, lag, ring = list(geom)
+    assert tiles == n1 // 16 and cols * tiles == 256 and ring >= lag + 1 and lag >= 1
+    # the scratch ring stays within the L2-resident budget the design states (32 MB; 48 MB where consumed lines are discarded)
+    assert ring * n1 * 256 * (8 if prec == "f32" else 16) <= 48 << 20
+    for frames in sorted({1, 2, lag - 1, lag, lag + 1, ring - 1, ring, ring + 1, 2 * ring + 3}):
+        if frames < 1:
+            continue
+        total = (lag + 2 * frames) * tiles
+        col_ticket, row_ticket = {}, {}
+        for q in range(total):
+            K.check(L.sdsp_b200_debug_fft_queue_item(n1 * 256, p, q, geom, item))
+            is_col, tile, f = list(item)
+            if f >= frames:
+                assert is_col  # empty slots are column slots past the last frame
+                continue
+            (col_ticket if is_col else row_ticket).setdefault(f, []).append((q, tile))
+        for f in range(frames):
+            assert sorted(t for _, t in col_ticket[f]) == list(range(tiles))  # every tile exactly once
+            assert sorted(t for _, t in row_ticket[f]) == list(range(tiles))
+            first_row = min(q for q, _ in row_ticket[f])
+            assert max(q for q, _ in col_ticket[f]) < first_row  # rows after their frame's columns
+            if f >= ring:  # the slot's previous tenant has been handed out in full before the new columns
+                assert max(q for q, _ in row_ticket[f - ring]) < min(q for q, _ in col_ticket[f])
+            # the lead the design relies on: a frame's rows follow its columns by about 2 x lag x tiles tickets
+            if frames > lag:
+                assert first_row - min(q for q, _ in col_ticket[f]) >= (2 * lag - 1) * tiles or f < lag
+    # sizes the queue kernels do not take are refused
+    assert L.sdsp_b200_debug_fft_queue_item(4096, p, 0, geom, item) != 0
