@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define SDSP_B200_VERSION 100 /* 0.1.0 */
+#define SDSP_B200_VERSION 200 /* 0.2.0 */
 
 enum sdsp_b200_status {
     SDSP_B200_OK = 0,
@@ -142,6 +142,14 @@ int sdsp_b200_iir_bank_set_coeffs(sdsp_b200_iir_bank bank, size_t first, size_t 
 int sdsp_b200_iir_bank_set_state(sdsp_b200_iir_bank bank, size_t first, size_t count, const double *mem);
 int sdsp_b200_iir_bank_get_state(sdsp_b200_iir_bank bank, size_t first, size_t count, double *mem);
 int sdsp_b200_iir_bank_reset_state(sdsp_b200_iir_bank bank);
+/* fp32 banks evaluate the recurrence in difference form (d_j[n] = v_j[n] - v_j[n-1] is carried next to v_j: this is what
+ * keeps an fp32 narrow-band filter within 1e-4 of the fp64 reference, see simpledsp_b200/csrc/iir_core.cuh) and so hold one
+ * more number per section than the reference's m_mem: diff[count][sections].  set_state() starts it at mem[j+1][0] - mem[j+1][1]
+ * (rounded to fp32), which is right up to the rounding of one addition; a caller that checkpoints an fp32 bank and wants the
+ * resumed stream to be BIT-identical to the uninterrupted one saves and restores diff as well (set_state first, then
+ * set_state_diff).  fp64 banks have no such state: get gives zeros, set is a no-op. */
+int sdsp_b200_iir_bank_set_state_diff(sdsp_b200_iir_bank bank, size_t first, size_t count, const double *diff);
+int sdsp_b200_iir_bank_get_state_diff(sdsp_b200_iir_bank bank, size_t first, size_t count, double *diff);
 /* casc_2o_iir<m_t>::process(begin, end) (casc_2o_iir.h:36-80) over every channel of the bank:
  * data[c * channel_stride + i], i < n_samples, filtered in place; history carries to the next call.
  * path: sdsp_b200_iir_path. */
@@ -162,7 +170,9 @@ int sdsp_b200_iir_preload_state(int sections, int filter_type, double gain, cons
 
 /* One-shot convenience used by the drop-in header for a single filter object held on the host:
  * uploads {gain,b,a,mem}, filters data[0..n) in place on the device (sequential path), downloads the
- * new history.  precision is that of `data`. */
+ * new history.  precision is that of `data` ONLY: the arithmetic is fp64 either way, as in the reference, whose
+ * object computes and keeps m_mem in double for any sample type (casc_2o_iir.h:13-18, 45-71); float samples are
+ * widened on the way in and rounded once on the way out.  (fp32 arithmetic: sdsp_b200_iir_bank_* with SDSP_B200_F32.) */
 int sdsp_b200_iir_process_once(int sections, int numerator, int precision, double gain, const double *b,
                                const double *a, double *mem, void *data, size_t n_samples, int device);
 
@@ -173,6 +183,9 @@ int sdsp_b200_iir_process_once(int sections, int numerator, int precision, doubl
 int sdsp_b200_debug_emulate_fft(uint32_t n, int precision, int direction, void *data, size_t n_frames);
 int sdsp_b200_debug_emulate_iir(int sections, int numerator, int precision, double gain, const double *b,
                                 const double *a, double *mem, void *data, size_t n_samples);
+/* the same with the fp32 running differences in / out (diff[sections], may be NULL = as sdsp_b200_iir_bank_set_state) */
+int sdsp_b200_debug_emulate_iir_diff(int sections, int numerator, int precision, double gain, const double *b,
+                                     const double *a, double *mem, double *diff, void *data, size_t n_samples);
 /* the scan path's algorithm (iir_scan_core.cuh) played on the host: whole tiles of 32*chunk samples go
  * through the chunked scan, the remainder through the sequential loop.  force_general != 0 takes the
  * wait-for-predecessor carry path whatever the filter's reach. */

@@ -51,6 +51,8 @@ SIGNATURES = {
     "sdsp_b200_iir_bank_set_state": (C.c_int, [_vp, _sz, _sz, _dp]),
     "sdsp_b200_iir_bank_get_state": (C.c_int, [_vp, _sz, _sz, _dp]),
     "sdsp_b200_iir_bank_reset_state": (C.c_int, [_vp]),
+    "sdsp_b200_iir_bank_set_state_diff": (C.c_int, [_vp, _sz, _sz, _dp]),
+    "sdsp_b200_iir_bank_get_state_diff": (C.c_int, [_vp, _sz, _sz, _dp]),
     "sdsp_b200_iir_bank_process": (C.c_int, [_vp, _vp, _sz, _sz, C.c_int, C.c_int, _vp]),
     "sdsp_b200_iir_bank_describe": (C.c_int, [_vp, _sz, _sz, C.c_int, C.c_char_p, _sz]),
     "sdsp_b200_iir_design_lp": (C.c_int, [C.c_int, C.c_double, C.c_double, C.c_double, _dp, _dp, _dp]),
@@ -60,6 +62,7 @@ SIGNATURES = {
     "sdsp_b200_iir_process_once": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_double, _dp, _dp, _dp, _vp, _sz, C.c_int]),
     "sdsp_b200_debug_emulate_fft": (C.c_int, [C.c_uint32, C.c_int, C.c_int, _vp, _sz]),
     "sdsp_b200_debug_emulate_iir": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_double, _dp, _dp, _dp, _vp, _sz]),
+    "sdsp_b200_debug_emulate_iir_diff": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_double, _dp, _dp, _dp, _dp, _vp, _sz]),
     "sdsp_b200_debug_iir_decay_length": (C.c_int, [C.c_int, C.c_int, C.c_int, _dp, _dp, C.POINTER(C.c_ulonglong)]),
     "sdsp_b200_debug_fft_queue_item": (C.c_int, [C.c_uint, C.c_int, C.c_ulonglong, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "sdsp_b200_debug_emulate_iir_scan": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_double, _dp, _dp, _dp, _vp, _sz,

@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 
 #include "common.h"
+#include "iir_internal.h"
 
 namespace sdsp_b200
 {
@@ -111,7 +112,10 @@ int sdsp_b200_init(int device)
 
 int sdsp_b200_shutdown(void)
 {
-    return SDSP_B200_OK; // handles own every allocation; nothing global outlives them
+    // plans and banks own their allocations and die with their handles; the one library-owned cache is the set of
+    // one-channel banks behind sdsp_b200_iir_process_once
+    iir_release_process_once_cache();
+    return SDSP_B200_OK;
 }
 
 int sdsp_b200_host_alloc(void **ptr, size_t bytes)

@@ -63,6 +63,44 @@ SDSP_HD double fma_t(double a, double b, double c)
 #endif
 }
 
+// products and sums that must round on their own (nvcc contracts a plain a*b + c into an fma, gcc may too): the
+// IIR paths promise bit-identical output however a stream is cut, which only holds if every kernel and the host
+// emulation round every operation alike
+SDSP_HD float mul_t(float a, float b)
+{
+#if defined(__CUDA_ARCH__)
+    return __fmul_rn(a, b);
+#else
+    volatile float r = a * b;
+    return r;
+#endif
+}
+SDSP_HD double mul_t(double a, double b)
+{
+#if defined(__CUDA_ARCH__)
+    return __dmul_rn(a, b);
+#else
+    volatile double r = a * b;
+    return r;
+#endif
+}
+SDSP_HD float add_t(float a, float b)
+{
+#if defined(__CUDA_ARCH__)
+    return __fadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
+SDSP_HD double add_t(double a, double b)
+{
+#if defined(__CUDA_ARCH__)
+    return __dadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
+
 // a * w with two multiplies and two fused multiply-adds
 template <typename T>
 SDSP_HD cplx<T> cmul(cplx<T> a, cplx<T> w)

@@ -27,37 +27,11 @@ __device__ __forceinline__ void iir_load_channel(IirCoef<T, M> &c, IirState<T, M
                                                  const T *__restrict__ state, size_t n_channels, size_t ch, bool active)
 {
     if (active) {
-        c.gain = coef[ch];
-#pragma unroll
-        for (int j = 0; j < M; j++) {
-            c.b1[j] = coef[(size_t)(1 + j) * n_channels + ch];
-            c.b2[j] = coef[(size_t)(1 + M + j) * n_channels + ch];
-            c.na1[j] = coef[(size_t)(1 + 2 * M + j) * n_channels + ch];
-            c.na2[j] = coef[(size_t)(1 + 3 * M + j) * n_channels + ch];
-        }
-#pragma unroll
-        for (int r = 0; r <= M; r++) {
-            s.h[r][0] = state[(size_t)(2 * r) * n_channels + ch];
-            s.h[r][1] = state[(size_t)(2 * r + 1) * n_channels + ch];
-        }
+        iir_load_coef<T, M>(c, coef, n_channels, ch);
+        iir_load_state<T, M>(s, state, n_channels, ch);
     } else {
-        c.gain = 0;
-#pragma unroll
-        for (int j = 0; j < M; j++)
-            c.b1[j] = c.b2[j] = c.na1[j] = c.na2[j] = 0;
-#pragma unroll
-        for (int r = 0; r <= M; r++)
-            s.h[r][0] = s.h[r][1] = 0;
-    }
-}
-
-template <typename T, int M>
-__device__ __forceinline__ void iir_store_state(const IirState<T, M> &s, T *__restrict__ state, size_t n_channels, size_t ch)
-{
-#pragma unroll
-    for (int r = 0; r <= M; r++) {
-        state[(size_t)(2 * r) * n_channels + ch] = s.h[r][0];
-        state[(size_t)(2 * r + 1) * n_channels + ch] = s.h[r][1];
+        iir_zero_coef<T, M>(c);
+        iir_zero_state<T, M>(s);
     }
 }
 
@@ -172,15 +146,15 @@ int iir_launch_sequential(const IirBank &b, void *data, size_t n_samples, size_t
 // =================================================================================================
 // host emulation of the sequential path (same iir_step, compiled for the host)
 template <typename T, int M, int KIND>
-static void emulate_seq(double gain, const double *b, const double *a, double *mem, void *data, size_t n)
+static void emulate_seq(double gain, const double *b, const double *a, double *mem, double *diff, void *data, size_t n)
 {
     IirCoef<T, M> c;
     IirState<T, M> s;
     iir_pack_coef<T, M>(c, gain, b, a);
-    for (int r = 0; r <= M; r++) {
-        s.h[r][0] = (T)mem[2 * r];
-        s.h[r][1] = (T)mem[2 * r + 1];
-    }
+    iir_state_from_mem<T, M>(s, mem);
+    if (diff && IirDelta<T>::value)
+        for (int j = 0; j < M; j++)
+            s.d[j] = (T)diff[j];
     T *d = static_cast<T *>(data);
     // as the TMA kernel does: whole tiles with the sections skewed, the ragged tail sample by sample
     constexpr int TS = 2 * 128 / (int)sizeof(T);
@@ -192,30 +166,30 @@ static void emulate_seq(double gain, const double *b, const double *a, double *m
     }
     for (; i < n; i++)
         d[i] = iir_step<T, M, KIND>(d[i], c, s);
-    for (int r = 0; r <= M; r++) {
-        mem[2 * r] = (double)s.h[r][0];
-        mem[2 * r + 1] = (double)s.h[r][1];
-    }
+    iir_state_to_mem<T, M>(s, mem);
+    if (diff)
+        for (int j = 0; j < M; j++)
+            diff[j] = IirDelta<T>::value ? (double)s.d[j] : 0.0;
 }
 
 template <typename T, int M>
-static void emulate_seq_kind(int kind, double gain, const double *b, const double *a, double *mem, void *data, size_t n)
+static void emulate_seq_kind(int kind, double gain, const double *b, const double *a, double *mem, double *diff, void *data, size_t n)
 {
     switch (kind) {
-    case NUM_GENERIC: emulate_seq<T, M, NUM_GENERIC>(gain, b, a, mem, data, n); break;
-    case NUM_LP: emulate_seq<T, M, NUM_LP>(gain, b, a, mem, data, n); break;
-    case NUM_HP: emulate_seq<T, M, NUM_HP>(gain, b, a, mem, data, n); break;
-    default: emulate_seq<T, M, NUM_BP>(gain, b, a, mem, data, n); break;
+    case NUM_GENERIC: emulate_seq<T, M, NUM_GENERIC>(gain, b, a, mem, diff, data, n); break;
+    case NUM_LP: emulate_seq<T, M, NUM_LP>(gain, b, a, mem, diff, data, n); break;
+    case NUM_HP: emulate_seq<T, M, NUM_HP>(gain, b, a, mem, diff, data, n); break;
+    default: emulate_seq<T, M, NUM_BP>(gain, b, a, mem, diff, data, n); break;
     }
 }
 
 template <typename T>
-static int emulate_seq_sections(int sections, int kind, double gain, const double *b, const double *a, double *mem, void *data,
-                                size_t n)
+static int emulate_seq_sections(int sections, int kind, double gain, const double *b, const double *a, double *mem, double *diff,
+                                void *data, size_t n)
 {
     switch (sections) {
 #define X(MM) \
-    case MM: emulate_seq_kind<T, MM>(kind, gain, b, a, mem, data, n); return SDSP_B200_OK;
+    case MM: emulate_seq_kind<T, MM>(kind, gain, b, a, mem, diff, data, n); return SDSP_B200_OK;
         X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8)
 #undef X
     default: return set_error(SDSP_B200_ERR_UNSUPPORTED, "iir: sections=%d not built (1..8)", sections);
@@ -309,7 +283,7 @@ static int check_bank_args(int sections, int precision, int numerator)
 template <typename T>
 static void pack_coef_soa(std::vector<T> &out, int m, size_t count, const double *gain, const double *b, const double *a)
 {
-    // [k][c] with k = gain, b1[0..m), b2[0..m), -a1[0..m), -a2[0..m)
+    // [k][c] with k = gain, b1[0..m), b2[0..m), fa[0..m), fb[0..m)  (feedback pair: see IirCoef)
     out.assign((size_t)iir_coef_count(m) * count, (T)0);
     for (size_t c = 0; c < count; c++) {
         out[c] = (T)gain[c];
@@ -318,8 +292,10 @@ static void pack_coef_soa(std::vector<T> &out, int m, size_t count, const double
             const double *aj = a + (c * m + j) * 3;
             out[(size_t)(1 + j) * count + c] = bj ? (T)bj[1] : (T)0;
             out[(size_t)(1 + m + j) * count + c] = bj ? (T)bj[2] : (T)0;
-            out[(size_t)(1 + 2 * m + j) * count + c] = (T)(-aj[1]);
-            out[(size_t)(1 + 3 * m + j) * count + c] = (T)(-aj[2]);
+            double fa, fb;
+            iir_feedback_pair(IirDelta<T>::value, aj[1], aj[2], fa, fb);
+            out[(size_t)(1 + 2 * m + j) * count + c] = (T)fa;
+            out[(size_t)(1 + 3 * m + j) * count + c] = (T)fb;
         }
     }
 }
@@ -348,6 +324,72 @@ struct sdsp_b200_iir_bank_s {
     IirBank b;
 };
 
+extern "C" int sdsp_b200_iir_bank_destroy(sdsp_b200_iir_bank bank);
+
+// host layout mem[c][k] (k < rows)  <->  device rows [row0 + k][channel]
+template <typename T>
+static int state_rows_io(IirBank &b, int row0, int rows, size_t first, size_t count, double *mem, bool to_device)
+{
+    std::vector<T> soa((size_t)rows * count);
+    void *dev = static_cast<char *>(b.d_state) + (size_t)row0 * b.n_channels * sizeof(T);
+    if (to_device) {
+        for (size_t c = 0; c < count; c++)
+            for (int k = 0; k < rows; k++)
+                soa[(size_t)k * count + c] = (T)mem[c * rows + k];
+        return copy_rows(b, dev, soa.data(), rows, first, count, true);
+    }
+    int rc = copy_rows(b, dev, soa.data(), rows, first, count, false);
+    for (size_t c = 0; c < count && rc == 0; c++)
+        for (int k = 0; k < rows; k++)
+            mem[c * rows + k] = (double)soa[(size_t)k * count + c];
+    return rc;
+}
+
+static int state_io(sdsp_b200_iir_bank bank, size_t first, size_t count, double *mem, bool to_device, bool diff_rows)
+{
+    if (!bank || !mem)
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "iir_bank_state: null argument");
+    IirBank &b = bank->b;
+    if (first + count > b.n_channels)
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "iir_bank_state: channels [%zu,%zu) outside bank of %zu", first, first + count,
+                         b.n_channels);
+    if (count == 0)
+        return SDSP_B200_OK;
+    SDSP_CUDA(cudaSetDevice(b.device));
+    const int m = b.sections, hist = iir_hist_count(m);
+    if (diff_rows) { // the running differences of a delta-form (fp32) bank; an fp64 bank has none: reads give zeros
+        if (b.precision != SDSP_B200_F32) {
+            if (!to_device)
+                memset(mem, 0, sizeof(double) * count * (size_t)m);
+            return SDSP_B200_OK;
+        }
+        return state_rows_io<float>(b, hist, m, first, count, mem, to_device);
+    }
+    if (b.precision != SDSP_B200_F32)
+        return state_rows_io<double>(b, 0, hist, first, count, mem, to_device);
+    int rc = state_rows_io<float>(b, 0, hist, first, count, mem, to_device);
+    if (rc == SDSP_B200_OK && to_device) {
+        // a history that comes from outside starts the running differences at v[n-1] - v[n-2] (iir_state_from_mem)
+        std::vector<double> diff(count * (size_t)m);
+        for (size_t c = 0; c < count; c++)
+            for (int j = 0; j < m; j++)
+                diff[c * m + j] = (double)((float)mem[c * hist + 2 * (j + 1)] - (float)mem[c * hist + 2 * (j + 1) + 1]);
+        rc = state_rows_io<float>(b, hist, m, first, count, diff.data(), true);
+    }
+    return rc;
+}
+
+static std::mutex g_once_mu;
+static std::map<std::tuple<int, int, int>, sdsp_b200_iir_bank> g_once_cache;
+
+void sdsp_b200::iir_release_process_once_cache()
+{
+    std::lock_guard<std::mutex> lock(g_once_mu);
+    for (auto &kv : g_once_cache)
+        sdsp_b200_iir_bank_destroy(kv.second);
+    g_once_cache.clear();
+}
+
 extern "C" {
 
 int sdsp_b200_iir_bank_create(sdsp_b200_iir_bank *bank, int sections, size_t n_channels, int precision, int numerator, int device)
@@ -373,7 +415,7 @@ int sdsp_b200_iir_bank_create(sdsp_b200_iir_bank *bank, int sections, size_t n_c
     b.sm_count = device_sm_count(device);
     const size_t es = elem_size(precision);
     const size_t coef_bytes = (size_t)iir_coef_count(sections) * n_channels * es;
-    const size_t state_bytes = (size_t)iir_state_count(sections) * n_channels * es;
+    const size_t state_bytes = (size_t)iir_bank_state_rows(b) * n_channels * es;
     if (cudaMalloc(&b.d_coef, coef_bytes) != cudaSuccess || cudaMalloc(&b.d_state, state_bytes) != cudaSuccess) {
         cudaGetLastError();
         if (b.d_coef)
@@ -448,55 +490,24 @@ int sdsp_b200_iir_bank_set_coeffs(sdsp_b200_iir_bank bank, size_t first, size_t 
     return rc;
 }
 
-static int state_io(sdsp_b200_iir_bank bank, size_t first, size_t count, double *mem, bool to_device)
-{
-    if (!bank || !mem)
-        return set_error(SDSP_B200_ERR_INVALID_ARG, "iir_bank_state: null argument");
-    IirBank &b = bank->b;
-    if (first + count > b.n_channels)
-        return set_error(SDSP_B200_ERR_INVALID_ARG, "iir_bank_state: channels [%zu,%zu) outside bank of %zu", first, first + count,
-                         b.n_channels);
-    if (count == 0)
-        return SDSP_B200_OK;
-    SDSP_CUDA(cudaSetDevice(b.device));
-    const int rows = iir_state_count(b.sections);
-    // host layout mem[c][row][2]  <->  device layout [2*row + i][channel]
-    if (b.precision == SDSP_B200_F32) {
-        std::vector<float> soa((size_t)rows * count);
-        if (to_device) {
-            for (size_t c = 0; c < count; c++)
-                for (int k = 0; k < rows; k++)
-                    soa[(size_t)k * count + c] = (float)mem[c * rows + k];
-            return copy_rows(b, b.d_state, soa.data(), rows, first, count, true);
-        }
-        int rc = copy_rows(b, b.d_state, soa.data(), rows, first, count, false);
-        for (size_t c = 0; c < count && rc == 0; c++)
-            for (int k = 0; k < rows; k++)
-                mem[c * rows + k] = (double)soa[(size_t)k * count + c];
-        return rc;
-    }
-    std::vector<double> soa((size_t)rows * count);
-    if (to_device) {
-        for (size_t c = 0; c < count; c++)
-            for (int k = 0; k < rows; k++)
-                soa[(size_t)k * count + c] = mem[c * rows + k];
-        return copy_rows(b, b.d_state, soa.data(), rows, first, count, true);
-    }
-    int rc = copy_rows(b, b.d_state, soa.data(), rows, first, count, false);
-    for (size_t c = 0; c < count && rc == 0; c++)
-        for (int k = 0; k < rows; k++)
-            mem[c * rows + k] = soa[(size_t)k * count + c];
-    return rc;
-}
-
 int sdsp_b200_iir_bank_set_state(sdsp_b200_iir_bank bank, size_t first, size_t count, const double *mem)
 {
-    return state_io(bank, first, count, const_cast<double *>(mem), true);
+    return state_io(bank, first, count, const_cast<double *>(mem), true, false);
 }
 
 int sdsp_b200_iir_bank_get_state(sdsp_b200_iir_bank bank, size_t first, size_t count, double *mem)
 {
-    return state_io(bank, first, count, mem, false);
+    return state_io(bank, first, count, mem, false, false);
+}
+
+int sdsp_b200_iir_bank_set_state_diff(sdsp_b200_iir_bank bank, size_t first, size_t count, const double *diff)
+{
+    return state_io(bank, first, count, const_cast<double *>(diff), true, true);
+}
+
+int sdsp_b200_iir_bank_get_state_diff(sdsp_b200_iir_bank bank, size_t first, size_t count, double *diff)
+{
+    return state_io(bank, first, count, diff, false, true);
 }
 
 int sdsp_b200_iir_bank_reset_state(sdsp_b200_iir_bank bank)
@@ -505,7 +516,7 @@ int sdsp_b200_iir_bank_reset_state(sdsp_b200_iir_bank bank)
         return set_error(SDSP_B200_ERR_INVALID_ARG, "iir_bank_reset_state: null bank");
     IirBank &b = bank->b;
     SDSP_CUDA(cudaSetDevice(b.device));
-    SDSP_CUDA(cudaMemset(b.d_state, 0, (size_t)iir_state_count(b.sections) * b.n_channels * elem_size(b.precision)));
+    SDSP_CUDA(cudaMemset(b.d_state, 0, (size_t)iir_bank_state_rows(b) * b.n_channels * elem_size(b.precision)));
     return SDSP_B200_OK;
 }
 
@@ -602,7 +613,11 @@ int sdsp_b200_iir_preload_state(int sections, int filter_type, double gain, cons
     return SDSP_B200_OK;
 }
 
-// a small cache of one-channel banks serves the drop-in header's single-object process() calls
+// A small cache of one-channel banks serves the drop-in header's single-object process() calls.  The arithmetic is
+// fp64 whatever the sample type: the reference object computes and keeps m_mem in double for any iterator value type
+// (casc_2o_iir.h:13-18, 45-71), so float samples are widened on the way in and rounded once on the way out, and the
+// history the caller holds (double mem[sections+1][2]) round-trips exactly -- block-wise calls stay bit-identical to
+// one whole-buffer call (test/testIIR.cpp:61-75).  fp32 ARITHMETIC is what sdsp_b200_iir_bank_* with SDSP_B200_F32 is for.
 int sdsp_b200_iir_process_once(int sections, int numerator, int precision, double gain, const double *bco, const double *aco,
                                double *mem, void *data, size_t n_samples, int device)
 {
@@ -613,31 +628,46 @@ int sdsp_b200_iir_process_once(int sections, int numerator, int precision, doubl
         return set_error(SDSP_B200_ERR_INVALID_ARG, "iir_process_once: null argument");
     if (n_samples == 0)
         return SDSP_B200_OK;
-    static std::mutex mu;
-    static std::map<std::tuple<int, int, int, int>, sdsp_b200_iir_bank> cache;
-    std::lock_guard<std::mutex> lock(mu);
-    auto key = std::make_tuple(sections, numerator, precision, device);
-    auto it = cache.find(key);
-    if (it == cache.end()) {
+    if (!data)
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "iir_process_once: null data");
+    std::lock_guard<std::mutex> lock(g_once_mu);
+    auto key = std::make_tuple(sections, numerator, device);
+    auto it = g_once_cache.find(key);
+    if (it == g_once_cache.end()) {
         sdsp_b200_iir_bank nb = nullptr;
-        rc = sdsp_b200_iir_bank_create(&nb, sections, 1, precision, numerator, device);
+        rc = sdsp_b200_iir_bank_create(&nb, sections, 1, SDSP_B200_F64, numerator, device);
         if (rc)
             return rc;
-        it = cache.emplace(key, nb).first;
+        it = g_once_cache.emplace(key, nb).first;
     }
     sdsp_b200_iir_bank bk = it->second;
+    std::vector<double> wide;
+    double *work = static_cast<double *>(data);
+    if (precision == SDSP_B200_F32) {
+        const float *src = static_cast<const float *>(data);
+        wide.assign(src, src + n_samples);
+        work = wide.data();
+    }
     rc = sdsp_b200_iir_bank_set_coeffs(bk, 0, 1, &gain, bco, aco);
     if (!rc)
         rc = sdsp_b200_iir_bank_set_state(bk, 0, 1, mem);
     if (!rc)
-        rc = sdsp_b200_iir_bank_process(bk, data, n_samples, n_samples, SDSP_B200_PTR_HOST, SDSP_B200_IIR_SEQUENTIAL, nullptr);
+        rc = sdsp_b200_iir_bank_process(bk, work, n_samples, n_samples, SDSP_B200_PTR_HOST, SDSP_B200_IIR_SEQUENTIAL, nullptr);
     if (!rc)
         rc = sdsp_b200_iir_bank_get_state(bk, 0, 1, mem);
+    if (!rc && precision == SDSP_B200_F32) {
+        float *dst = static_cast<float *>(data);
+        for (size_t i = 0; i < n_samples; i++)
+            dst[i] = (float)wide[i];
+    }
     return rc;
 }
 
-int sdsp_b200_debug_emulate_iir(int sections, int numerator, int precision, double gain, const double *bco, const double *aco,
-                                double *mem, void *data, size_t n_samples)
+// host emulation of the sequential kernels.  diff (may be null): the running differences of the fp32 delta form,
+// [sections] doubles in / out next to mem -- with them a stream cut into calls reproduces the uncut run bit for bit;
+// without, each call starts them at v[n-1] - v[n-2] as sdsp_b200_iir_bank_set_state does.
+int sdsp_b200_debug_emulate_iir_diff(int sections, int numerator, int precision, double gain, const double *bco, const double *aco,
+                                     double *mem, double *diff, void *data, size_t n_samples)
 {
     int rc = check_bank_args(sections, precision, numerator);
     if (rc)
@@ -645,7 +675,13 @@ int sdsp_b200_debug_emulate_iir(int sections, int numerator, int precision, doub
     if (!aco || !mem || !data || (numerator == NUM_GENERIC && !bco))
         return set_error(SDSP_B200_ERR_INVALID_ARG, "emulate_iir: null argument");
     if (precision == SDSP_B200_F32)
-        return emulate_seq_sections<float>(sections, numerator, gain, bco, aco, mem, data, n_samples);
-    return emulate_seq_sections<double>(sections, numerator, gain, bco, aco, mem, data, n_samples);
+        return emulate_seq_sections<float>(sections, numerator, gain, bco, aco, mem, diff, data, n_samples);
+    return emulate_seq_sections<double>(sections, numerator, gain, bco, aco, mem, diff, data, n_samples);
+}
+
+int sdsp_b200_debug_emulate_iir(int sections, int numerator, int precision, double gain, const double *bco, const double *aco,
+                                double *mem, void *data, size_t n_samples)
+{
+    return sdsp_b200_debug_emulate_iir_diff(sections, numerator, precision, gain, bco, aco, mem, nullptr, data, n_samples);
 }
 }

@@ -11,6 +11,19 @@
 // equality of block-wise and whole-buffer runs).  The history is kept as the two most recent values of
 // every row of the reference's m_mem; its 3-slot ring and m_pos (casc_2o_iir.h:11,15,54-60,73-75) are
 // a private representation, replaced here by register rotation.
+//
+// fp64 evaluates that line as it stands.  fp32 evaluates the SAME recurrence in difference ("delta") form:
+//     d_j[n] = g*d_j[n-1] + (numerator - c0*v_j[n-2]),      v_j[n] = v_j[n-1] + d_j[n]
+//     with  c0 = 1 + a1 + a2   and   g = a2 - c0 = -(1 + a1)       (both formed in double on the host, rounded once)
+// which is algebraically identical (substitute d = v[n] - v[n-1]) but keeps what fp32 cannot afford to lose: for a
+// narrow-band section a1 -> -2, a2 -> 1 and the quantity that places the poles is c0 ~ (2 pi f0/fs)^2, i.e. the last
+// bits of a1 and a2.  Rounding a1, a2 to fp32 moves c0 by up to 2^-24 ABSOLUTE (10 % of c0 at f0/fs = 2.5e-4, and
+// 1e-4 of the impulse response already at f0/fs = 0.005: reference test_data/impulse_response/LPimpulse.csv, SURVEY
+// H3); rounding c0 itself moves it by 2^-24 RELATIVE, and a rounding error of g multiplies (1 - z^-1), which
+// vanishes where such a filter has its gain.  The running difference d is carried as state next to v, so rounding
+// errors of v never re-enter the resonant part of the recurrence.  Measured against the fp64 reference on the nine
+// golden fixtures and on noise: direct form 1e-4 (f0/fs = 0.005) ... 1e-3 (f0/fs = 0.001), delta form <= 3e-6 for
+// every low-pass / band-pass case and <= 1.3e-5 for the high-pass ones (profiles/r02_iir_f32_delta_form.txt).
 #pragma once
 #include "common.h"
 
@@ -18,101 +31,177 @@ namespace sdsp_b200
 {
 enum : int { NUM_GENERIC = 0, NUM_LP = 1, NUM_HP = 2, NUM_BP = 3 };
 
-// coefficients of one channel, negated denominators so that every update is a plain fma
+// does precision T run the difference form (and carry d next to the history)?
+template <typename T>
+struct IirDelta {
+    static constexpr bool value = sizeof(T) == 4;
+};
+
+// coefficients of one channel, feedback pair pre-arranged so that every update is a plain fma:
+//   fp64 (direct form):  fa = -a1,          fb = -a2
+//   fp32 (delta form):   fa = g = -(1+a1),  fb = -c0 = -(1+a1+a2)
 template <typename T, int M>
 struct IirCoef {
     T gain;
-    T b1[M], b2[M];   // only read by NUM_GENERIC
-    T na1[M], na2[M]; // -a1, -a2
+    T b1[M], b2[M]; // only read by NUM_GENERIC
+    T fa[M], fb[M];
 };
 
-// history of one channel: row 0 = scaled input, row j+1 = output of section j; [.][0] = x[n-1], [.][1] = x[n-2]
+// history of one channel: row 0 = scaled input, row j+1 = output of section j; [.][0] = x[n-1], [.][1] = x[n-2];
+// d[j] = the running difference of section j's output (delta form only; never read in fp64)
 template <typename T, int M>
 struct IirState {
     T h[M + 1][2];
+    T d[M];
 };
 
-// number of coefficient / state scalars per channel in the device-side structure-of-arrays banks
+// number of coefficient / state scalars per channel in the device-side structure-of-arrays banks.
+// State rows: 2r, 2r+1 = history row r (as the C ABI's mem[r][0..1]); delta form: row 2(m+1)+j = d[j].
 SDSP_HD constexpr int iir_coef_count(int m)
 {
     return 1 + 4 * m;
 }
-SDSP_HD constexpr int iir_state_count(int m)
+SDSP_HD constexpr int iir_hist_count(int m) // the part of the state the C ABI exposes (reference m_mem)
 {
     return 2 * (m + 1);
 }
+SDSP_HD constexpr int iir_state_count(int m, bool delta)
+{
+    return 2 * (m + 1) + (delta ? m : 0);
+}
+// the feedback pair of one section from the reference's a1, a2 (host, double)
+inline void iir_feedback_pair(bool delta, double a1, double a2, double &fa, double &fb)
+{
+    if (delta) {
+        fa = -(1.0 + a1);
+        fb = -(1.0 + a1 + a2);
+    } else {
+        fa = -a1;
+        fb = -a2;
+    }
+}
 
-// one section, one sample:  v = in0 + b1*in1 + b2*in2 - a2*v2 - a1*v1.
-// The evaluation order is fixed (SDSP_IIR_ORDER): every kernel (sequential, skewed, packed, scan) and the host
-// emulation call this one function, which is what makes their results bit-identical to one another.
-// Order 'A' -- fma(na1, v1, fma(na2, v2, fma(b2, in2, fma(b1, in1, in0)))) -- puts v1, this section's previous
-// output and the only loop-carried operand that is one sample old, into the LAST operation: the recurrence costs one
-// FMA latency per sample and a section four instructions.  The four orders measured on the nine golden fixtures and
-// on noise in fp32 are equally accurate (worst fixture 9.6e-5 .. 1.07e-4 of peak), so
-// the shortest chain wins; the lane-per-channel kernel with 512 warps is bound by exactly this latency.
-#ifndef SDSP_IIR_ORDER
-#define SDSP_IIR_ORDER 'A'
+// ---- bank rows <-> registers (structure-of-arrays banks: row k of channel ch at [k * pitch + ch]) ------------------
+#if defined(__CUDA_ARCH__)
+#define SDSP_UNROLL _Pragma("unroll")
+#else
+#define SDSP_UNROLL
 #endif
+template <typename T, int M>
+SDSP_HD void iir_load_coef(IirCoef<T, M> &c, const T *__restrict__ coef, size_t pitch, size_t ch)
+{
+    c.gain = coef[ch];
+    SDSP_UNROLL
+    for (int j = 0; j < M; j++) {
+        c.b1[j] = coef[(size_t)(1 + j) * pitch + ch];
+        c.b2[j] = coef[(size_t)(1 + M + j) * pitch + ch];
+        c.fa[j] = coef[(size_t)(1 + 2 * M + j) * pitch + ch];
+        c.fb[j] = coef[(size_t)(1 + 3 * M + j) * pitch + ch];
+    }
+}
+template <typename T, int M>
+SDSP_HD void iir_zero_coef(IirCoef<T, M> &c)
+{
+    c.gain = 0;
+    SDSP_UNROLL
+    for (int j = 0; j < M; j++)
+        c.b1[j] = c.b2[j] = c.fa[j] = c.fb[j] = 0;
+}
+template <typename T, int M>
+SDSP_HD void iir_load_state(IirState<T, M> &s, const T *__restrict__ state, size_t pitch, size_t ch)
+{
+    SDSP_UNROLL
+    for (int r = 0; r <= M; r++) {
+        s.h[r][0] = state[(size_t)(2 * r) * pitch + ch];
+        s.h[r][1] = state[(size_t)(2 * r + 1) * pitch + ch];
+    }
+    SDSP_UNROLL
+    for (int j = 0; j < M; j++)
+        s.d[j] = IirDelta<T>::value ? state[(size_t)(2 * (M + 1) + j) * pitch + ch] : (T)0;
+}
+template <typename T, int M>
+SDSP_HD void iir_zero_state(IirState<T, M> &s)
+{
+    SDSP_UNROLL
+    for (int r = 0; r <= M; r++)
+        s.h[r][0] = s.h[r][1] = 0;
+    SDSP_UNROLL
+    for (int j = 0; j < M; j++)
+        s.d[j] = 0;
+}
+template <typename T, int M>
+SDSP_HD void iir_store_state(const IirState<T, M> &s, T *__restrict__ state, size_t pitch, size_t ch)
+{
+    SDSP_UNROLL
+    for (int r = 0; r <= M; r++) {
+        state[(size_t)(2 * r) * pitch + ch] = s.h[r][0];
+        state[(size_t)(2 * r + 1) * pitch + ch] = s.h[r][1];
+    }
+    if (IirDelta<T>::value) {
+        SDSP_UNROLL
+        for (int j = 0; j < M; j++)
+            state[(size_t)(2 * (M + 1) + j) * pitch + ch] = s.d[j];
+    }
+}
+// the C ABI's history mem[r][0..1] (double) <-> a register state; the running differences are not part of that
+// interface (the reference's m_mem has no such thing): a history that comes in from outside starts them at
+// v[n-1] - v[n-2], which is what they are up to the rounding of one addition
+template <typename T, int M>
+inline void iir_state_from_mem(IirState<T, M> &s, const double *mem)
+{
+    for (int r = 0; r <= M; r++) {
+        s.h[r][0] = (T)mem[2 * r];
+        s.h[r][1] = (T)mem[2 * r + 1];
+    }
+    for (int j = 0; j < M; j++)
+        s.d[j] = IirDelta<T>::value ? s.h[j + 1][0] - s.h[j + 1][1] : (T)0;
+}
+template <typename T, int M>
+inline void iir_state_to_mem(const IirState<T, M> &s, double *mem)
+{
+    for (int r = 0; r <= M; r++) {
+        mem[2 * r] = (double)s.h[r][0];
+        mem[2 * r + 1] = (double)s.h[r][1];
+    }
+}
+
+// one section, one sample.  Every kernel (sequential, skewed, packed, scan) and the host emulation call this one
+// function with a fixed evaluation order, which is what makes their results bit-identical to one another.
+//   numerator   acc = in0 + b1*in1 + b2*in2        (fixed kinds: {1,2,1}, {1,-2,1}, {1,0,-1} without multiplies)
+//   fp64        v = fma(fa, v1, fma(fb, v2, acc))                       fa = -a1, fb = -a2
+//               v1, the only loop-carried operand that is one sample old, enters the LAST operation: the recurrence
+//               costs one FMA latency per sample.
+//   fp32        d = fma(fa, d, fma(fb, v2, acc));  v = v1 + d           fa = g,   fb = -c0   (see the header comment)
+//               loop-carried: d -> d one FMA, v -> v one add, and d -> v -> (two samples later) d three operations.
 template <int KIND, typename T>
-SDSP_HD T iir_numpart(T in1, T in2, T b1, T b2) // b1*in1 + b2*in2
+SDSP_HD T iir_numerator(T in0, T in1, T in2, T b1, T b2)
 {
     if (KIND == NUM_GENERIC)
-        return fma_t(b2, in2, b1 * in1);
-    if (KIND == NUM_LP) // {1, 2, 1}
-        return fma_t((T)2, in1, in2);
-    if (KIND == NUM_HP) // {1, -2, 1}
-        return fma_t((T)-2, in1, in2);
-    return -in2; // NUM_BP {1, 0, -1}
+        return fma_t(b2, in2, fma_t(b1, in1, in0));
+    if (KIND == NUM_LP)
+        return fma_t((T)2, in1, in0) + in2;
+    if (KIND == NUM_HP)
+        return fma_t((T)-2, in1, in0) + in2;
+    return in0 - in2; // NUM_BP
 }
-// fp64: four fused multiply-adds in the obvious order (accuracy is not at stake there -- 7e-15 absolute on the
-// golden fixtures -- and the FP64 pipe is what bounds the fp64 kernels, so the operation count matters)
 template <int KIND>
-SDSP_HD double iir_section(double in0, double in1, double in2, double v1, double v2, double b1, double b2, double na1, double na2)
+SDSP_HD double iir_section(double in0, double in1, double in2, double v1, double v2, double &d, double b1, double b2, double fa, double fb)
 {
-    double acc;
-    if (KIND == NUM_GENERIC)
-        acc = fma_t(b2, in2, fma_t(b1, in1, in0));
-    else if (KIND == NUM_LP)
-        acc = fma_t(2.0, in1, in0) + in2;
-    else if (KIND == NUM_HP)
-        acc = fma_t(-2.0, in1, in0) + in2;
-    else
-        acc = in0 - in2;
-    return fma_t(na1, v1, fma_t(na2, v2, acc));
+    (void)d;
+    return fma_t(fa, v1, fma_t(fb, v2, iir_numerator<KIND, double>(in0, in1, in2, b1, b2)));
 }
-// fp32: SDSP_IIR_ORDER
 template <int KIND>
-SDSP_HD float iir_section(float in0, float in1, float in2, float v1, float v2, float b1, float b2, float na1, float na2)
+SDSP_HD float iir_section(float in0, float in1, float in2, float v1, float v2, float &d, float b1, float b2, float fa, float fb)
 {
-    using T = float;
-#if SDSP_IIR_ORDER == 'A' // numerator chain from in0, then both feedback terms
-    T acc;
-    if (KIND == NUM_GENERIC)
-        acc = fma_t(b2, in2, fma_t(b1, in1, in0));
-    else if (KIND == NUM_LP)
-        acc = fma_t((T)2, in1, in0) + in2;
-    else if (KIND == NUM_HP)
-        acc = fma_t((T)-2, in1, in0) + in2;
-    else
-        acc = in0 - in2;
-    return fma_t(na1, v1, fma_t(na2, v2, acc));
-#elif SDSP_IIR_ORDER == 'B' // everything old first, then (part + in0), then the v1 term
-    const T part = fma_t(na2, v2, iir_numpart<KIND, T>(in1, in2, b1, b2));
-    return fma_t(na1, v1, part + in0);
-#elif SDSP_IIR_ORDER == 'J' // feedback pair combined on its own (the cancelling terms), numerator and in0 added last
-    const T fb = fma_t(na1, v1, na2 * v2);
-    return (fb + iir_numpart<KIND, T>(in1, in2, b1, b2)) + in0;
-#else // 'K'
-    const T t = na2 * v2 + (iir_numpart<KIND, T>(in1, in2, b1, b2) + in0);
-    return fma_t(na1, v1, t);
-#endif
+    d = fma_t(fa, d, fma_t(fb, v2, iir_numerator<KIND, float>(in0, in1, in2, b1, b2)));
+    return add_t(v1, d);
 }
 
 // one input sample through the whole cascade; returns the output sample and advances the history
 template <typename T, int M, int KIND>
 SDSP_HD T iir_step(T x, const IirCoef<T, M> &c, IirState<T, M> &s)
 {
-    T in0 = x * c.gain;
+    T in0 = mul_t(x, c.gain);
     T in1 = s.h[0][0], in2 = s.h[0][1];
     s.h[0][1] = in1;
     s.h[0][0] = in0;
@@ -121,7 +210,7 @@ SDSP_HD T iir_step(T x, const IirCoef<T, M> &c, IirState<T, M> &s)
 #endif
     for (int j = 0; j < M; j++) {
         const T v1 = s.h[j + 1][0], v2 = s.h[j + 1][1];
-        const T v = iir_section<KIND>(in0, in1, in2, v1, v2, c.b1[j], c.b2[j], c.na1[j], c.na2[j]);
+        const T v = iir_section<KIND>(in0, in1, in2, v1, v2, s.d[j], c.b1[j], c.b2[j], c.fa[j], c.fb[j]);
         s.h[j + 1][1] = v1;
         s.h[j + 1][0] = v;
         in0 = v;
@@ -141,7 +230,7 @@ SDSP_HD T iir_step(T x, const IirCoef<T, M> &c, IirState<T, M> &s)
 template <typename T, int M, int KIND, int TS, typename Load, typename Store>
 SDSP_HD void iir_tile_skewed(const IirCoef<T, M> &c, IirState<T, M> &s, Load &&load, Store &&store)
 {
-    T inh[M][2], vh[M][2], pipe[M + 1];
+    T inh[M][2], vh[M][2], dh[M], pipe[M + 1];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -150,6 +239,7 @@ SDSP_HD void iir_tile_skewed(const IirCoef<T, M> &c, IirState<T, M> &s, Load &&l
         inh[j][1] = s.h[j][1];
         vh[j][0] = s.h[j + 1][0];
         vh[j][1] = s.h[j + 1][1];
+        dh[j] = s.d[j];
         pipe[j] = 0;
     }
 #if defined(__CUDA_ARCH__)
@@ -162,8 +252,8 @@ SDSP_HD void iir_tile_skewed(const IirCoef<T, M> &c, IirState<T, M> &s, Load &&l
         for (int j = M - 1; j >= 0; j--) { // downstream first: pipe[j] still holds last iteration's value
             const int smp = i - j;
             if (smp >= 0 && smp < TS) {
-                const T in0 = (j == 0) ? load(smp) * c.gain : pipe[j];
-                const T v = iir_section<KIND>(in0, inh[j][0], inh[j][1], vh[j][0], vh[j][1], c.b1[j], c.b2[j], c.na1[j], c.na2[j]);
+                const T in0 = (j == 0) ? mul_t(load(smp), c.gain) : pipe[j];
+                const T v = iir_section<KIND>(in0, inh[j][0], inh[j][1], vh[j][0], vh[j][1], dh[j], c.b1[j], c.b2[j], c.fa[j], c.fb[j]);
                 inh[j][1] = inh[j][0];
                 inh[j][0] = in0;
                 vh[j][1] = vh[j][0];
@@ -183,6 +273,7 @@ SDSP_HD void iir_tile_skewed(const IirCoef<T, M> &c, IirState<T, M> &s, Load &&l
     for (int j = 0; j < M; j++) {
         s.h[j + 1][0] = vh[j][0];
         s.h[j + 1][1] = vh[j][1];
+        s.d[j] = dh[j];
     }
 }
 
@@ -235,40 +326,22 @@ SDSP_HD f32x2 add2(f32x2 a, f32x2 b)
 // iir_section(), so the bits equal the scalar path; the instruction count per sample drops from
 // 1 + 4M to about 2 + 2M.
 template <int KIND>
-SDSP_HD f32x2 iir_numpart_x2(f32x2 in1, f32x2 in2, f32x2 b1, f32x2 b2)
+SDSP_HD f32x2 iir_numerator_x2(f32x2 in0, f32x2 in1, f32x2 in2, f32x2 b1, f32x2 b2)
 {
     if (KIND == NUM_GENERIC)
-        return fma2(b2, in2, mul2(b1, in1));
+        return fma2(b2, in2, fma2(b1, in1, in0));
     if (KIND == NUM_LP)
-        return fma2(mk2(2.f, 2.f), in1, in2);
+        return add2(fma2(mk2(2.f, 2.f), in1, in0), in2);
     if (KIND == NUM_HP)
-        return fma2(mk2(-2.f, -2.f), in1, in2);
-    return mk2(-in2.x, -in2.y);
+        return add2(fma2(mk2(-2.f, -2.f), in1, in0), in2);
+    return add2(in0, mk2(-in2.x, -in2.y));
 }
+// the delta-form update of iir_section(float ...), both halves at once
 template <int KIND>
-SDSP_HD f32x2 iir_section_x2(f32x2 in0, f32x2 in1, f32x2 in2, f32x2 v1, f32x2 v2, f32x2 b1, f32x2 b2, f32x2 na1, f32x2 na2)
+SDSP_HD f32x2 iir_section_x2(f32x2 in0, f32x2 in1, f32x2 in2, f32x2 v1, f32x2 v2, f32x2 &d, f32x2 b1, f32x2 b2, f32x2 fa, f32x2 fb)
 {
-#if SDSP_IIR_ORDER == 'A'
-    f32x2 acc;
-    if (KIND == NUM_GENERIC)
-        acc = fma2(b2, in2, fma2(b1, in1, in0));
-    else if (KIND == NUM_LP)
-        acc = add2(fma2(mk2(2.f, 2.f), in1, in0), in2);
-    else if (KIND == NUM_HP)
-        acc = add2(fma2(mk2(-2.f, -2.f), in1, in0), in2);
-    else
-        acc = add2(in0, mk2(-in2.x, -in2.y));
-    return fma2(na1, v1, fma2(na2, v2, acc));
-#elif SDSP_IIR_ORDER == 'B'
-    const f32x2 part = fma2(na2, v2, iir_numpart_x2<KIND>(in1, in2, b1, b2));
-    return fma2(na1, v1, add2(part, in0));
-#elif SDSP_IIR_ORDER == 'J'
-    const f32x2 fb = fma2(na1, v1, mul2(na2, v2));
-    return add2(add2(fb, iir_numpart_x2<KIND>(in1, in2, b1, b2)), in0);
-#else
-    const f32x2 t = add2(mul2(na2, v2), add2(iir_numpart_x2<KIND>(in1, in2, b1, b2), in0));
-    return fma2(na1, v1, t);
-#endif
+    d = fma2(fa, d, fma2(fb, v2, iir_numerator_x2<KIND>(in0, in1, in2, b1, b2)));
+    return add2(v1, d);
 }
 
 template <int M, int KIND, int TS, typename Load, typename Store>
@@ -276,15 +349,16 @@ SDSP_HD void iir_tile_skewed_x2(const IirCoef<float, M> &c, IirState<float, M> &
 {
     static_assert(M % 2 == 0, "pairs of sections");
     constexpr int P = M / 2;
-    f32x2 b1[P], b2[P], na1[P], na2[P], inh0[P], inh1[P], vh0[P], vh1[P];
+    f32x2 b1[P], b2[P], fa[P], fb[P], inh0[P], inh1[P], vh0[P], vh1[P], dh[P];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
     for (int p = 0; p < P; p++) {
         b1[p] = mk2(c.b1[p], c.b1[p + P]);
         b2[p] = mk2(c.b2[p], c.b2[p + P]);
-        na1[p] = mk2(c.na1[p], c.na1[p + P]);
-        na2[p] = mk2(c.na2[p], c.na2[p + P]);
+        fa[p] = mk2(c.fa[p], c.fa[p + P]);
+        fb[p] = mk2(c.fb[p], c.fb[p + P]);
+        dh[p] = mk2(s.d[p], s.d[p + P]);
         inh0[p] = mk2(s.h[p][0], s.h[p + P][0]);
         inh1[p] = mk2(s.h[p][1], s.h[p + P][1]);
         vh0[p] = mk2(s.h[p + 1][0], s.h[p + P + 1][0]);
@@ -308,13 +382,13 @@ SDSP_HD void iir_tile_skewed_x2(const IirCoef<float, M> &c, IirState<float, M> &
                 continue;
             f32x2 in0;
             if (p == 0) {
-                in0.x = lo_on ? load(slo) * c.gain : 0.f;
+                in0.x = lo_on ? mul_t(load(slo), c.gain) : 0.f;
                 in0.y = from_mid;
             } else {
                 in0 = vh0[p - 1];
             }
             if (lo_on && hi_on) {
-                const f32x2 v = iir_section_x2<KIND>(in0, inh0[p], inh1[p], vh0[p], vh1[p], b1[p], b2[p], na1[p], na2[p]);
+                const f32x2 v = iir_section_x2<KIND>(in0, inh0[p], inh1[p], vh0[p], vh1[p], dh[p], b1[p], b2[p], fa[p], fb[p]);
                 inh1[p] = inh0[p];
                 inh0[p] = in0;
                 vh1[p] = vh0[p];
@@ -322,13 +396,13 @@ SDSP_HD void iir_tile_skewed_x2(const IirCoef<float, M> &c, IirState<float, M> &
                 if (p == P - 1)
                     store(shi, v.y);
             } else if (lo_on) { // ramp-up: only the low section of the pair has a sample
-                const float v = iir_section<KIND>(in0.x, inh0[p].x, inh1[p].x, vh0[p].x, vh1[p].x, b1[p].x, b2[p].x, na1[p].x, na2[p].x);
+                const float v = iir_section<KIND>(in0.x, inh0[p].x, inh1[p].x, vh0[p].x, vh1[p].x, dh[p].x, b1[p].x, b2[p].x, fa[p].x, fb[p].x);
                 inh1[p].x = inh0[p].x;
                 inh0[p].x = in0.x;
                 vh1[p].x = vh0[p].x;
                 vh0[p].x = v;
             } else { // ramp-down: only the high section still has samples
-                const float v = iir_section<KIND>(in0.y, inh0[p].y, inh1[p].y, vh0[p].y, vh1[p].y, b1[p].y, b2[p].y, na1[p].y, na2[p].y);
+                const float v = iir_section<KIND>(in0.y, inh0[p].y, inh1[p].y, vh0[p].y, vh1[p].y, dh[p].y, b1[p].y, b2[p].y, fa[p].y, fb[p].y);
                 inh1[p].y = inh0[p].y;
                 inh0[p].y = in0.y;
                 vh1[p].y = vh0[p].y;
@@ -350,6 +424,8 @@ SDSP_HD void iir_tile_skewed_x2(const IirCoef<float, M> &c, IirState<float, M> &
         s.h[p + 1][1] = vh1[p].x;
         s.h[p + P + 1][0] = vh0[p].y;
         s.h[p + P + 1][1] = vh1[p].y;
+        s.d[p] = dh[p].x;
+        s.d[p + P] = dh[p].y;
     }
 }
 
@@ -376,8 +452,10 @@ inline void iir_pack_coef(IirCoef<T, M> &c, double gain, const double *b /*[M][3
     for (int j = 0; j < M; j++) {
         c.b1[j] = b ? (T)b[3 * j + 1] : (T)0;
         c.b2[j] = b ? (T)b[3 * j + 2] : (T)0;
-        c.na1[j] = (T)(-a[3 * j + 1]);
-        c.na2[j] = (T)(-a[3 * j + 2]);
+        double fa, fb;
+        iir_feedback_pair(IirDelta<T>::value, a[3 * j + 1], a[3 * j + 2], fa, fb);
+        c.fa[j] = (T)fa;
+        c.fb[j] = (T)fb;
     }
 }
 } // namespace sdsp_b200

@@ -13,7 +13,7 @@ struct IirBank {
     int sections = 0, precision = 0, numerator = 0, device = 0, sm_count = 0;
     size_t n_channels = 0;
     void *d_coef = nullptr;  // [1 + 4m][n_channels]   gain, b1[m], b2[m], -a1[m], -a2[m]
-    void *d_state = nullptr; // [2(m + 1)][n_channels] row r: x[n-1], x[n-2]
+    void *d_state = nullptr; // [2(m + 1) (+ m)][n_channels] rows 2r, 2r+1: x[n-1], x[n-2] of history row r; fp32: + m rows of running differences
     void *d_state_alt = nullptr; // scan path: the launch reads d_state and writes here, then the two are swapped
     // host copy of the coefficients in double (scan tables are derived from it)
     std::vector<double> h_gain, h_b, h_a;
@@ -44,7 +44,14 @@ struct IirBank {
     std::mutex mu;
 };
 
+// rows of the device-side state array (iir_core.cuh: the fp32 delta form carries one running difference per section)
+inline int iir_bank_state_rows(const IirBank &b)
+{
+    return 2 * (b.sections + 1) + (b.precision == SDSP_B200_F32 ? b.sections : 0);
+}
+
 // iir.cu
+void iir_release_process_once_cache(); // sdsp_b200_shutdown()
 int iir_launch_sequential(const IirBank &b, void *data, size_t n_samples, size_t stride, cudaStream_t stream);
 // iir_tma.cu -- the fast sequential path (needs 16-byte aligned base and pitch, even section count)
 bool iir_tma_applicable(const IirBank &b, const void *data, size_t n_samples, size_t stride);

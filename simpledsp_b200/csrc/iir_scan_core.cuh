@@ -74,21 +74,41 @@ SDSP_HD void tri_matvec_acc(const T *__restrict__ A, const T (&x)[SD], T (&y)[SD
     }
 }
 
+// The carried vector.  fp64: c = (v_j[n-1], v_j[n-2]).  fp32 (delta form, iir_core.cuh): c = (v_j[n-1], d_j[n-1]) with
+// d = v[n-1] - v[n-2] the running difference -- in that basis the propagation matrices of a narrow-band section are
+// well conditioned (in the (v1, v2) basis A_L ~ [[1+L, -L], [L, 1-L]]: its product with a state rounded to fp32
+// cancels L-fold), and it is what the fp32 section carries anyway.  The host tables are built in the same basis.
 template <typename T, int M>
 SDSP_HD void scan_state_to_vec(const IirState<T, M> &s, T (&c)[2 * M])
 {
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
+    SDSP_UNROLL
     for (int j = 0; j < M; j++) {
         c[2 * j] = s.h[j + 1][0];
-        c[2 * j + 1] = s.h[j + 1][1];
+        c[2 * j + 1] = IirDelta<T>::value ? s.d[j] : s.h[j + 1][1];
+    }
+}
+template <typename T, int M>
+SDSP_HD void scan_vec_to_state(const T (&c)[2 * M], IirState<T, M> &s)
+{
+    SDSP_UNROLL
+    for (int j = 0; j < M; j++) {
+        s.h[j + 1][0] = c[2 * j];
+        if (IirDelta<T>::value) {
+            s.d[j] = c[2 * j + 1];
+            s.h[j + 1][1] = c[2 * j] - c[2 * j + 1];
+        } else {
+            s.h[j + 1][1] = c[2 * j + 1];
+            s.d[j] = 0;
+        }
     }
 }
 
 // ---- host: tables ---------------------------------------------------------------------------------
+// delta_basis: tables for the carried vector (v1, d) instead of (v1, v2): with S = blockdiag([[1, 0], [1, -1]]) (its own
+// inverse; (v1, v2) = S (v1, d)),  H' = H S  and  A' = S A S
 template <int M, int KIND>
-inline void scan_build_tables_mk(double gain, const double *b, const double *a, int L, double negligible, std::vector<double> &out, int &reach)
+inline void scan_build_tables_mk(double gain, const double *b, const double *a, int L, double negligible, bool delta_basis,
+                                 std::vector<double> &out, int &reach)
 {
     constexpr int SD = 2 * M;
     IirCoef<double, M> c;
@@ -100,6 +120,8 @@ inline void scan_build_tables_mk(double gain, const double *b, const double *a, 
         IirState<double, M> s;
         for (int r = 0; r <= M; r++)
             s.h[r][0] = s.h[r][1] = 0.0;
+        for (int j = 0; j < M; j++)
+            s.d[j] = 0.0;
         s.h[1 + k / 2][k % 2] = 1.0;
         for (int i = 0; i < L; i++)
             H[i * SD + k] = iir_step<double, M, KIND>(0.0, c, s);
@@ -107,6 +129,23 @@ inline void scan_build_tables_mk(double gain, const double *b, const double *a, 
             A0[(2 * j) * SD + k] = s.h[j + 1][0];
             A0[(2 * j + 1) * SD + k] = s.h[j + 1][1];
         }
+    }
+    if (delta_basis) {
+        for (int i = 0; i < L; i++) // H S: column pair (2j, 2j+1) -> (h0 + h1, -h1)
+            for (int j = 0; j < M; j++) {
+                const double h0 = H[i * SD + 2 * j], h1 = H[i * SD + 2 * j + 1];
+                H[i * SD + 2 * j] = h0 + h1;
+                H[i * SD + 2 * j + 1] = -h1;
+            }
+        for (int r = 0; r < SD; r++) // A S
+            for (int j = 0; j < M; j++) {
+                const double x0 = A0[r * SD + 2 * j], x1 = A0[r * SD + 2 * j + 1];
+                A0[r * SD + 2 * j] = x0 + x1;
+                A0[r * SD + 2 * j + 1] = -x1;
+            }
+        for (int k = 0; k < SD; k++) // S (A S): row pair (2j, 2j+1) -> (r0, r0 - r1)
+            for (int j = 0; j < M; j++)
+                A0[(2 * j + 1) * SD + k] = A0[(2 * j) * SD + k] - A0[(2 * j + 1) * SD + k];
     }
     auto square = [&](const double *X, double *Y) {
         for (int r = 0; r < SD; r++)
@@ -143,16 +182,16 @@ inline void scan_build_tables_mk(double gain, const double *b, const double *a, 
     }
 }
 
-inline int scan_build_tables(int m, int kind, double gain, const double *b, const double *a, int L, double negligible, std::vector<double> &out,
-                             int &reach)
+inline int scan_build_tables(int m, int kind, double gain, const double *b, const double *a, int L, double negligible, bool delta_basis,
+                             std::vector<double> &out, int &reach)
 {
 #define SDSP_SCAN_CASE(MM)                                                                \
     case MM:                                                                              \
         switch (kind) {                                                                   \
-        case NUM_GENERIC: scan_build_tables_mk<MM, NUM_GENERIC>(gain, b, a, L, negligible, out, reach); break; \
-        case NUM_LP: scan_build_tables_mk<MM, NUM_LP>(gain, b, a, L, negligible, out, reach); break;  \
-        case NUM_HP: scan_build_tables_mk<MM, NUM_HP>(gain, b, a, L, negligible, out, reach); break;  \
-        default: scan_build_tables_mk<MM, NUM_BP>(gain, b, a, L, negligible, out, reach); break;      \
+        case NUM_GENERIC: scan_build_tables_mk<MM, NUM_GENERIC>(gain, b, a, L, negligible, delta_basis, out, reach); break; \
+        case NUM_LP: scan_build_tables_mk<MM, NUM_LP>(gain, b, a, L, negligible, delta_basis, out, reach); break;  \
+        case NUM_HP: scan_build_tables_mk<MM, NUM_HP>(gain, b, a, L, negligible, delta_basis, out, reach); break;  \
+        default: scan_build_tables_mk<MM, NUM_BP>(gain, b, a, L, negligible, delta_basis, out, reach); break;      \
         }                                                                                 \
         return 0;
     switch (m) {
@@ -206,8 +245,7 @@ inline size_t scan_emulate_channel(const IirCoef<T, M> &c, IirState<T, M> &s, co
         // zero-state pass
         for (int l = 0; l < SCAN_LANES; l++) {
             IirState<T, M> z;
-            for (int r = 0; r <= M; r++)
-                z.h[r][0] = z.h[r][1] = 0;
+            iir_zero_state<T, M>(z);
             z.h[0][0] = halo[l][0];
             z.h[0][1] = halo[l][1];
             T *chunk = x + (size_t)l * L;
@@ -298,10 +336,10 @@ inline size_t scan_emulate_channel(const IirCoef<T, M> &c, IirState<T, M> &s, co
     }
     s.h[0][0] = uh[0];
     s.h[0][1] = uh[1];
-    for (int j = 0; j < M; j++) {
-        s.h[j + 1][0] = incl[n_tiles - 1][2 * j];
-        s.h[j + 1][1] = incl[n_tiles - 1][2 * j + 1];
-    }
+    T last[SD];
+    for (int k = 0; k < SD; k++)
+        last[k] = incl[n_tiles - 1][k];
+    scan_vec_to_state<T, M>(last, s);
     return n_tiles * tile;
 }
 } // namespace sdsp_b200

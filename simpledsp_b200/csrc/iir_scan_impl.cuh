@@ -23,22 +23,16 @@ static int emulate_scan(double gain, const double *b, const double *a, double *m
     IirCoef<T, M> c;
     IirState<T, M> s;
     iir_pack_coef<T, M>(c, gain, b, a);
-    for (int r = 0; r <= M; r++) {
-        s.h[r][0] = (T)mem[2 * r];
-        s.h[r][1] = (T)mem[2 * r + 1];
-    }
+    iir_state_from_mem<T, M>(s, mem);
     std::vector<double> tab;
     int reach = 0;
-    if (scan_build_tables(M, KIND, gain, b, a, L, scan_negligible<T>(), tab, reach) != 0)
+    if (scan_build_tables(M, KIND, gain, b, a, L, scan_negligible<T>(), IirDelta<T>::value, tab, reach) != 0)
         return set_error(SDSP_B200_ERR_UNSUPPORTED, "scan: sections=%d not built", M);
     T *d = static_cast<T *>(data);
     const size_t done = scan_emulate_channel<T, M, KIND>(c, s, tab, reach, L, d, n, force_general);
     for (size_t i = done; i < n; i++)
         d[i] = iir_step<T, M, KIND>(d[i], c, s);
-    for (int r = 0; r <= M; r++) {
-        mem[2 * r] = (double)s.h[r][0];
-        mem[2 * r + 1] = (double)s.h[r][1];
-    }
+    iir_state_to_mem<T, M>(s, mem);
     return SDSP_B200_OK;
 }
 
@@ -137,10 +131,7 @@ __global__ void __launch_bounds__(WARPS * 32)
     T *tab = reinterpret_cast<T *>(smem_raw + (size_t)WARPS * TILE_BYTES + (size_t)(ONE_CH ? 0 : warp) * TABLE_BYTES);
     unsigned tab_ch = 0xffffffffu;
     IirCoef<T, M> c;
-    c.gain = 0;
-#pragma unroll
-    for (int j = 0; j < M; j++)
-        c.b1[j] = c.b2[j] = c.na1[j] = c.na2[j] = 0;
+    iir_zero_coef<T, M>(c);
     int reach = 0;
     uint64_t *bar = &bars[warp];
     if (lane == 0) {
@@ -158,14 +149,7 @@ __global__ void __launch_bounds__(WARPS * 32)
     // coefficients into registers, tables into shared memory.  H is re-laid for the correction loop: fp32 keeps
     // sample pairs together, [i/2][k][2], so that one 16-byte load feeds two FFMA2; fp64 stays [i][k]
     auto load_channel = [&](unsigned ch, int first, int step) {
-        c.gain = coef[ch];
-#pragma unroll
-        for (int j = 0; j < M; j++) {
-            c.b1[j] = coef[(size_t)(1 + j) * n_channels + ch];
-            c.b2[j] = coef[(size_t)(1 + M + j) * n_channels + ch];
-            c.na1[j] = coef[(size_t)(1 + 2 * M + j) * n_channels + ch];
-            c.na2[j] = coef[(size_t)(1 + 3 * M + j) * n_channels + ch];
-        }
+        iir_load_coef<T, M>(c, coef, n_channels, ch);
         reach = reach_of[ch];
         const T *src = tables + (size_t)ch * TAB;
         for (int idx = first; idx < L * SD; idx += step) {
@@ -212,9 +196,7 @@ __global__ void __launch_bounds__(WARPS * 32)
 
         // ---- scaled-input history entering each chunk, read before anything is overwritten
         IirState<T, M> z;
-#pragma unroll
-        for (int r = 0; r <= M; r++)
-            z.h[r][0] = z.h[r][1] = 0;
+        iir_zero_state<T, M>(z);
         if (lane > 0) {
             z.h[0][0] = *elem(lane - 1, L - 1) * c.gain;
             z.h[0][1] = *elem(lane - 1, L - 2) * c.gain;
@@ -291,16 +273,21 @@ __global__ void __launch_bounds__(WARPS * 32)
 
         // ---- state entering the tile (identical in every lane)
         const T *Mt = tab + scan_off_A(M, L, SCAN_KS_STEPS);
+        // the bank's section history as a carried vector: (v1, v2) rows 2 + k; delta form (v1, d): d in rows 2(M+1) + j
+        auto bank_vec = [&](int k) -> T {
+            const int row = (IirDelta<T>::value && (k & 1)) ? 2 * (M + 1) + k / 2 : 2 + k;
+            return state[(size_t)row * n_channels + ch];
+        };
         T cin[SD];
         if (t == 0) {
 #pragma unroll
             for (int k = 0; k < SD; k++)
-                cin[k] = state[(size_t)(2 + k) * n_channels + ch];
+                cin[k] = bank_vec(k);
         } else if (reach <= SCAN_MAX_REACH) {
             const unsigned K = (unsigned)reach < t ? (unsigned)reach : t;
 #pragma unroll
             for (int k = 0; k < SD; k++)
-                cin[k] = (K == t) ? state[(size_t)(2 + k) * n_channels + ch] : (T)0;
+                cin[k] = (K == t) ? bank_vec(k) : (T)0;
             for (unsigned kk = K; kk >= 1; kk--) {
                 const ScanRec<T, SD> *pr = rec - kk;
                 warp_wait_flag(&pr->flag_a, epoch, lane);
@@ -333,11 +320,11 @@ __global__ void __launch_bounds__(WARPS * 32)
             }
             if (t + 1 == n_tiles) { // the bank's history after the last whole tile.  It goes to a second buffer: the
                                     // first tiles of this launch may not have read the incoming history yet
-                state_out[(size_t)0 * n_channels + ch] = out_u1;
-                state_out[(size_t)1 * n_channels + ch] = out_u2;
-#pragma unroll
-                for (int k = 0; k < SD; k++)
-                    state_out[(size_t)(2 + k) * n_channels + ch] = incl[k];
+                IirState<T, M> fin;
+                fin.h[0][0] = out_u1;
+                fin.h[0][1] = out_u2;
+                scan_vec_to_state<T, M>(incl, fin);
+                iir_store_state<T, M>(fin, state_out, n_channels, ch);
             }
         }
 
@@ -459,7 +446,7 @@ static int launch_scan_cfg(IirBank &b, void *data, size_t n_samples, size_t stri
         std::vector<double> one;
         for (size_t ch = 0; ch < b.n_channels; ch++) {
             int r = 0;
-            scan_build_tables(M, KIND, b.h_gain[ch], &b.h_b[ch * 3 * M], &b.h_a[ch * 3 * M], L, scan_negligible<T>(), one, r);
+            scan_build_tables(M, KIND, b.h_gain[ch], &b.h_b[ch * 3 * M], &b.h_a[ch * 3 * M], L, scan_negligible<T>(), IirDelta<T>::value, one, r);
             reach[ch] = r;
             for (int i = 0; i < TAB; i++)
                 tabs[ch * TAB + i] = (T)one[i];
@@ -538,7 +525,7 @@ static int launch_scan_cfg(IirBank &b, void *data, size_t n_samples, size_t stri
     if (grid * WARPS > total_tiles)
         grid = (total_tiles + WARPS - 1) / WARPS;
     // outgoing history is written to the bank's second state buffer, which then becomes the current one
-    const size_t state_bytes = (size_t)(2 + SD) * b.n_channels * sizeof(T);
+    const size_t state_bytes = (size_t)iir_bank_state_rows(b) * b.n_channels * sizeof(T);
     if (!b.d_state_alt) {
         if (cudaMalloc(&b.d_state_alt, state_bytes) != cudaSuccess) {
             cudaGetLastError();

@@ -171,8 +171,8 @@ __global__ void seg_gather_kernel(const T *__restrict__ data, size_t stride, siz
     }
     const T *p = data + ch * stride + (size_t)s * seg_len;
     const T gain = coef[ch];
-    row_state[v] = p[-1] * gain; // the same product iir_step() forms for row 0 of the history
-    row_state[rows + v] = p[-2] * gain;
+    row_state[v] = mul_t(p[-1], gain); // the same product iir_step() forms for row 0 of the history
+    row_state[rows + v] = mul_t(p[-2], gain);
     for (int k = 2; k < state_rows; k++)
         row_state[(size_t)k * rows + v] = (T)0;
 }
@@ -281,7 +281,9 @@ bool iir_segment_applicable(IirBank &b, const void *data, size_t n_samples, size
 template <typename T>
 static int segment_round(IirBank &b, T *data, size_t stride, size_t segs, size_t seg_len, size_t corr, cudaStream_t stream)
 {
-    const int state_rows = iir_state_count(b.sections);
+    // all rows of the bank's state array travel: the section history AND (fp32) the running differences a segment ends
+    // with are what its successor's natural response starts from
+    const int state_rows = iir_bank_state_rows(b);
     const size_t rows = b.n_channels * segs;
     const size_t need = 2 * (size_t)state_rows * rows * sizeof(T);
     if (b.seg_state_bytes < need) {

@@ -78,27 +78,11 @@ __global__ void __launch_bounds__(WARPS * 32)
     IirState<T, M> st;
     if (active) {
         const size_t cc = MODE == ROWS_PLAIN ? ch : ch / seg_per_ch; // whose coefficients
-        c.gain = coef[cc];
-#pragma unroll
-        for (int j = 0; j < M; j++) {
-            c.b1[j] = coef[(size_t)(1 + j) * n_coef_channels + cc];
-            c.b2[j] = coef[(size_t)(1 + M + j) * n_coef_channels + cc];
-            c.na1[j] = coef[(size_t)(1 + 2 * M + j) * n_coef_channels + cc];
-            c.na2[j] = coef[(size_t)(1 + 3 * M + j) * n_coef_channels + cc];
-        }
-#pragma unroll
-        for (int r = 0; r <= M; r++) {
-            st.h[r][0] = state[(size_t)(2 * r) * n_channels + ch];
-            st.h[r][1] = state[(size_t)(2 * r + 1) * n_channels + ch];
-        }
+        iir_load_coef<T, M>(c, coef, n_coef_channels, cc);
+        iir_load_state<T, M>(st, state, n_channels, ch);
     } else {
-        c.gain = 0;
-#pragma unroll
-        for (int j = 0; j < M; j++)
-            c.b1[j] = c.b2[j] = c.na1[j] = c.na2[j] = 0;
-#pragma unroll
-        for (int r = 0; r <= M; r++)
-            st.h[r][0] = st.h[r][1] = 0;
+        iir_zero_coef<T, M>(c);
+        iir_zero_state<T, M>(st);
     }
 
     const int n_stages = (n_samples + TS - 1) / TS;
@@ -209,13 +193,8 @@ __global__ void __launch_bounds__(WARPS * 32)
     }
     if (lane == 0)
         tma_wait_all();
-    if (active && MODE != ROWS_SEG_ACC) { // (the correction pass ends in a history that is negligible by construction)
-#pragma unroll
-        for (int r = 0; r <= M; r++) {
-            state[(size_t)(2 * r) * n_channels + ch] = st.h[r][0];
-            state[(size_t)(2 * r + 1) * n_channels + ch] = st.h[r][1];
-        }
-    }
+    if (active && MODE != ROWS_SEG_ACC) // (the correction pass ends in a history that is negligible by construction)
+        iir_store_state<T, M>(st, state, n_channels, ch);
 }
 
 template <typename T, int M, int KIND, int SUB, int CSUB, int NST, int PF, int WARPS, int RG, bool PACK = true>
@@ -313,22 +292,20 @@ __global__ void __launch_bounds__((M / 2 + 1) * 32)
         for (int j = 0; j < 2; j++) {
             c.b1[j] = coef[(size_t)(1 + j0 + j) * n_channels + ch];
             c.b2[j] = coef[(size_t)(1 + M + j0 + j) * n_channels + ch];
-            c.na1[j] = coef[(size_t)(1 + 2 * M + j0 + j) * n_channels + ch];
-            c.na2[j] = coef[(size_t)(1 + 3 * M + j0 + j) * n_channels + ch];
+            c.fa[j] = coef[(size_t)(1 + 2 * M + j0 + j) * n_channels + ch];
+            c.fb[j] = coef[(size_t)(1 + 3 * M + j0 + j) * n_channels + ch];
         }
 #pragma unroll
         for (int r = 0; r <= 2; r++) { // rows j0 .. j0+2 of the history: input of section j0, outputs of j0 and j0+1
             st.h[r][0] = state[(size_t)(2 * (j0 + r)) * n_channels + ch];
             st.h[r][1] = state[(size_t)(2 * (j0 + r) + 1) * n_channels + ch];
         }
-    } else {
-        c.gain = 0;
 #pragma unroll
         for (int j = 0; j < 2; j++)
-            c.b1[j] = c.b2[j] = c.na1[j] = c.na2[j] = 0;
-#pragma unroll
-        for (int r = 0; r <= 2; r++)
-            st.h[r][0] = st.h[r][1] = 0;
+            st.d[j] = IirDelta<T>::value ? state[(size_t)(2 * (M + 1) + j0 + j) * n_channels + ch] : (T)0;
+    } else {
+        iir_zero_coef<T, 2>(c);
+        iir_zero_state<T, 2>(st);
     }
     // the only block-wide barrier: mbarriers are initialised, and every warp has read its share of the bank's history
     // before a faster neighbour can write its own back at the end of a short stream
@@ -427,6 +404,11 @@ __global__ void __launch_bounds__((M / 2 + 1) * 32)
                 state[(size_t)(2 * (j0 + r)) * n_channels + ch] = st.h[r][0];
                 state[(size_t)(2 * (j0 + r) + 1) * n_channels + ch] = st.h[r][1];
             }
+        }
+        if (IirDelta<T>::value) {
+#pragma unroll
+            for (int j = 0; j < 2; j++)
+                state[(size_t)(2 * (M + 1) + j0 + j) * n_channels + ch] = st.d[j];
         }
     }
 }

@@ -69,6 +69,17 @@ class IirBank:
         K.check(K.lib().sdsp_b200_iir_bank_get_state(self._h, first, count, _p(mem)))
         return mem
 
+    def set_state_diff(self, diff, first: int = 0):
+        """fp32 banks only carry these (difference-form recurrence): with get_state()/set_state() an exact checkpoint."""
+        diff = np.ascontiguousarray(diff, dtype=np.float64).reshape(-1, self.sections)
+        K.check(K.lib().sdsp_b200_iir_bank_set_state_diff(self._h, first, diff.shape[0], _p(diff)))
+
+    def get_state_diff(self, first: int = 0, count: int | None = None) -> np.ndarray:
+        count = self.n_channels - first if count is None else count
+        diff = np.zeros((count, self.sections))
+        K.check(K.lib().sdsp_b200_iir_bank_get_state_diff(self._h, first, count, _p(diff)))
+        return diff
+
     def reset_state(self):
         K.check(K.lib().sdsp_b200_iir_bank_reset_state(self._h))
 
@@ -86,6 +97,8 @@ class IirBank:
         ptr, kind, stream, prec, dev = describe(data, _REAL)
         if prec != self.precision:
             raise TypeError("dtype does not match the bank's precision")
+        if kind == K.PTR_DEVICE and dev is not None and dev != self.device:
+            raise ValueError(f"tensor lives on cuda:{dev}, the bank on cuda:{self.device}")
         shape = tuple(int(s) for s in data.shape)
         if len(shape) == 1:
             shape = (1,) + shape

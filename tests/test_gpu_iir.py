@@ -5,7 +5,7 @@ import pytest
 import simpledsp_b200 as S
 from oracle import oracle as O
 from simpledsp_b200 import _capi as K
-from tests.util import IIR_GOLDEN_ABS, IIR_TOL, f32_noise, golden_impulses, peak_rel, ref_vectors, rel_l2
+from tests.util import IIR_FIXTURE_F32, IIR_GOLDEN_ABS, IIR_TOL, f32_noise, golden_impulses, peak_rel, ref_vectors, rel_l2
 
 pytestmark = pytest.mark.gpu
 PREC = {"f64": (K.F64, np.float64), "f32": (K.F32, np.float32)}
@@ -21,9 +21,59 @@ def _design(f, ftype, f0, fs, q, gain=1.0):
         f.set_bp_coeff(f0, fs, q, gain)
 
 
+@pytest.mark.parametrize("num_fixed", [False, True])
+def test_golden_impulse_responses_fp32_bank_and_exact_checkpoint(num_fixed):
+    """The nine golden fixtures through the fp32 KERNELS (a bank of nine channels, one per fixture; generic and
+    fixed numerators): within IIR_FIXTURE_F32 of the reference's fp64 impulse responses -- LPimpulse (f0/fs = 0.005)
+    included, which a direct-form fp32 recurrence misses by 1e-4.  Then reference test/testIIR.cpp:61-75 on
+    the bank: 32-sample blocks reproduce the whole-buffer run bit for bit, also through a checkpoint
+    (get_state + get_state_diff -> another bank -> set_state + set_state_diff) in the middle of the stream."""
+    cases = list(golden_impulses())
+    n = cases[0][5]
+    assert all(c[5] == n for c in cases)
+    for kind in ((1, 2, 3) if num_fixed else (0,)):
+        sel = [c for c in cases if not num_fixed or c[1] == kind]
+        coef = [S.design(c[1], 4, c[3], c[2], c[4]) for c in sel]
+        want = np.array([c[6] for c in sel])
+
+        def make():
+            bank = S.IirBank(4, len(sel), K.F32, kind)
+            bank.set_coeffs(np.array([c[0] for c in coef]), None if num_fixed else np.array([c[1] for c in coef]),
+                            np.array([c[2] for c in coef]))
+            return bank
+
+        x = np.zeros((len(sel), n), dtype=np.float32)
+        x[:, 0] = 1.0
+        y = make().process(x.copy())
+        for i, c in enumerate(sel):
+            assert peak_rel(y[i], want[i]) <= IIR_FIXTURE_F32, (c[0], kind)
+        bank, y2 = make(), x.copy()
+        for lo in range(0, n, 32):
+            if lo == 512:  # checkpoint / resume on a fresh bank
+                mem, dif = bank.get_state(), bank.get_state_diff()
+                bank = make()
+                bank.set_state(mem)
+                bank.set_state_diff(dif)
+            part = np.ascontiguousarray(y2[:, lo:lo + 32])
+            bank.process(part)
+            y2[:, lo:lo + 32] = part
+        assert np.array_equal(y, y2), kind
+        # without the differences the resumed stream is still within rounding of the uninterrupted one
+        bank, y3 = make(), x.copy()
+        bank.process(y3[:, :512].copy())
+        mem = bank.get_state()
+        bank = make()
+        bank.set_state(mem)
+        tail = np.ascontiguousarray(y3[:, 512:])
+        bank.process(tail)
+        err = np.abs(tail - y[:, 512:]).max(axis=1) / np.abs(want).max(axis=1)
+        assert err.max() <= IIR_FIXTURE_F32, kind
+
+
 @pytest.mark.parametrize("prec", ["f64", "f32"])
 def test_golden_impulse_responses_and_block_streaming(prec):
-    # reference test/testIIR.cpp:32-77 (generic) and :223-430 (fixed numerators)
+    # reference test/testIIR.cpp:32-77 (generic) and :223-430 (fixed numerators), through the single-object classes: fp64
+    # ARITHMETIC for either sample type, as in the reference (casc_2o_iir.h:13-18, 45-71) -- float samples are rounded once
     code, dt = PREC[prec]
     for name, ftype, fs, f0, q, n, h in golden_impulses():
         for num in (0, ftype):
@@ -35,7 +85,7 @@ def test_golden_impulse_responses_and_block_streaming(prec):
             y = f.process(x.copy())
             if prec == "f64":
                 assert np.abs(y - h).max() < IIR_GOLDEN_ABS, (name, num)
-            assert peak_rel(y, h) <= IIR_TOL[prec], (name, num)
+            assert peak_rel(y, h) <= (IIR_TOL["f64"] if prec == "f64" else 1e-7), (name, num)
             y2 = x.copy()
             for i in range(0, n, 32):  # 32-sample blocks and the 8-sample tail: exact equality
                 f2.process(y2[i:i + 32])
@@ -75,8 +125,8 @@ def test_matches_reference_vectors_all_section_counts():
             y = x.astype(dt)
             f.process(y[:300])
             f.process(y[300:])
-            tol = IIR_TOL[prec] if f0 > 1e3 or prec == "f64" else 20 * IIR_TOL[prec]  # 500 Hz/100 kHz in fp32: SURVEY H3
-            assert peak_rel(y, z[key]) <= tol, (key, prec)
+            # single-object path: fp64 arithmetic, float samples rounded once on the way out (half an ulp of the peak)
+            assert peak_rel(y, z[key]) <= (IIR_TOL["f64"] if prec == "f64" else 1e-7), (key, prec)
 
 
 def _bank_case(n_channels, n_samples, prec, sections=4, seed=0):
@@ -205,18 +255,18 @@ def test_scan_single_long_channel_matches_sequential_reference(case, prec, how):
     bank.set_coeffs([g], [b], [a])
     assert ("time-split" in bank.describe(n, n, tp)) == (how == "split")
     y = bank.process(x.astype(dt), path=tp)
-    tol = 3 * IIR_TOL[prec] if (prec == "f32" and f0 < 1e3) else IIR_TOL[prec]  # SURVEY H3, as in the CPU test
+    tol = IIR_TOL[prec]
     assert peak_rel(y, ref) <= tol
     # the history left behind continues the stream exactly where the scan stopped
     nxt = f32_noise(rng, 1000)
     want = f.process(nxt)
     got = bank.process(nxt.astype(dt), path=K.IIR_SEQUENTIAL)
-    assert peak_rel(got, want) <= 10 * tol
+    assert peak_rel(got, want) <= tol
     # and a second scan call on the same bank (non-zero incoming history) too
     more = f32_noise(rng, 32 * chunk * 3)
     want2 = f.process(more)
     got2 = bank.process(more.astype(dt), path=K.IIR_SCAN if how == "split" else tp)  # (short: auto may pick either)
-    assert peak_rel(got2, want2) <= 10 * tol
+    assert peak_rel(got2, want2) <= tol
 
 
 def test_scan_general_carry_path_for_long_memory_filters():
@@ -346,7 +396,7 @@ def test_config3_full_size_sampled_parity_both_paths():
     torch.cuda.synchronize()
     got_tail = block[d_whole].cpu().numpy()
     for j in range(len(whole)):
-        assert peak_rel(got_tail[j], filters[j].process(tail[j])) <= 10 * IIR_TOL["f32"], whole[j]
+        assert peak_rel(got_tail[j], filters[j].process(tail[j])) <= IIR_TOL["f32"], whole[j]
 
 
 def test_config4_full_size_windows_against_the_oracle():
