@@ -7,6 +7,12 @@
 // TMA engine does that for free: a 2-D tensor map over (samples, channels) with boxes of 8 rows x 128
 // bytes (four per 32 channels) and SWIZZLE_128B lands each channel's 128-byte run in its own shared-memory row, XOR-swizzled so
 // that lane r reading 16-byte chunk c of row r (LDS.128 at r*128 + ((c ^ (r&7))<<4)) is conflict free.
+// A second, "blocked" view of the same memory -- (32-sample block interior, channel, block index), the block index being
+// the OUTERMOST tensor dimension with a stride of 128 bytes -- lets one TMA instruction fetch SUB consecutive 128-byte
+// pieces of 8 channels ([SUB][8 rows][128 B] in shared memory: every 1 KB unit is one swizzle atom, so the lane
+// addressing does not change).  A warp that has an SM sub-partition to itself pays for every instruction it issues,
+// TMA set-up included: the blocked view halves (SUB = 2) the TMA instructions per stage.  Whole stages use it; the
+// ragged last stage goes box by box through the plain view, whose extent clips at n_samples.
 // Every warp runs its own ring of stages with its own mbarriers -- no block-wide synchronisation -- and
 // writes results back with TMA stores from the same buffers (the filter runs in place, as in the
 // reference).  Out-of-range rows / samples are zero-filled on load and clipped on store by the TMA unit,
@@ -37,15 +43,18 @@ enum : int { ROWS_PLAIN = 0, ROWS_SEG = 1, ROWS_SEG_ACC = 2 };
 
 template <typename T, int M, int KIND, int SUB, int CSUB, int NST, int PF, int WARPS, int RG, int MODE, bool PACK = true>
 __global__ void __launch_bounds__(WARPS * 32)
-    iir_tma_kernel(const __grid_constant__ CUtensorMap map, int n_samples, const T *__restrict__ coef, T *__restrict__ state,
-                   size_t n_channels, size_t n_coef_channels, unsigned seg_per_ch)
+    iir_tma_kernel(const __grid_constant__ CUtensorMap map, const __grid_constant__ CUtensorMap bmap, int n_samples,
+                   const T *__restrict__ coef, T *__restrict__ state, size_t n_channels, size_t n_coef_channels, unsigned seg_per_ch,
+                   int use_blocked)
 {
     constexpr int TSB = 128 / (int)sizeof(T);
     constexpr int TS = TSB * SUB;   // samples per stage (what one mbarrier phase delivers)
     constexpr int CTS = TSB * CSUB; // samples per skewed compute tile
-    static_assert(SUB % CSUB == 0 && (RG == 32 || RG == 8), "stage = whole compute tiles; boxes of 32 or 8 rows");
-    constexpr int BOX_BYTES = 32 * 128;
-    constexpr int STAGE_BYTES = BOX_BYTES * SUB;
+    static_assert(SUB % CSUB == 0 && RG == 8, "stage = whole compute tiles; boxes of 8 rows (one 1 KB swizzle atom)");
+    // shared-memory layout of a stage: [row group g = 0..3][block u = 0..SUB-1][8 rows][128 B]
+    constexpr int UNIT_BYTES = RG * 128;          // one (g, u) unit = one TMA box of the plain view
+    constexpr int GROUP_BYTES = SUB * UNIT_BYTES; // one box of the blocked view
+    constexpr int STAGE_BYTES = 32 * 128 * SUB;
     constexpr int VN = Vec16<T>::N;
     using V = typename Vec16<T>::type;
     static_assert(PF >= 1 && PF < NST, "prefetch distance must leave room for stores in flight");
@@ -102,16 +111,25 @@ __global__ void __launch_bounds__(WARPS * 32)
         uint64_t *b = &bar[k % NST];
         unsigned char *dst = ring + (size_t)(k % NST) * STAGE_BYTES;
         mbar_expect_tx(b, STAGE_BYTES);
-        // RG = 8: boxes of 8 rows, the SUB boxes of one row group issued back to back, so that the requests
-        // for consecutive 128-byte pieces of a channel reach the memory system together (DRAM page locality)
+        if (use_blocked && (k + 1) * TS <= n_samples) { // whole stage: one box of the blocked view per row group
+#pragma unroll
+            for (int g = 0; g < 32 / RG; g++)
+                if constexpr (MODE == ROWS_PLAIN)
+                    tma_load_3d(dst + g * GROUP_BYTES, &bmap, 0, y0 + g * RG, k * SUB, b);
+                else
+                    tma_load_4d(dst + g * GROUP_BYTES, &bmap, 0, seg_of[g], chn_of[g], k * SUB, b);
+            return;
+        }
+        // ragged last stage: the SUB boxes of one row group issued back to back, so that the requests for consecutive
+        // 128-byte pieces of a channel reach the memory system together (DRAM page locality)
 #pragma unroll
         for (int g = 0; g < 32 / RG; g++)
 #pragma unroll
             for (int u = 0; u < SUB; u++)
                 if constexpr (MODE == ROWS_PLAIN)
-                    tma_load_2d(dst + u * BOX_BYTES + g * RG * 128, &map, k * TS + u * TSB, y0 + g * RG, b);
+                    tma_load_2d(dst + g * GROUP_BYTES + u * UNIT_BYTES, &map, k * TS + u * TSB, y0 + g * RG, b);
                 else
-                    tma_load_3d(dst + u * BOX_BYTES + g * RG * 128, &map, k * TS + u * TSB, seg_of[g], chn_of[g], b);
+                    tma_load_3d(dst + g * GROUP_BYTES + u * UNIT_BYTES, &map, k * TS + u * TSB, seg_of[g], chn_of[g], b);
     };
 
     if (lane == 0) {
@@ -119,8 +137,8 @@ __global__ void __launch_bounds__(WARPS * 32)
             issue_load(k);
     }
 
-    // this lane's row inside a box, and the XOR that un-swizzles 16-byte chunks
-    const uint32_t row_off = (uint32_t)lane * 128u;
+    // this lane's row inside its row group, and the XOR that un-swizzles 16-byte chunks
+    const uint32_t row_off = (uint32_t)(lane >> 3) * (uint32_t)GROUP_BYTES + (uint32_t)(lane & 7) * 128u;
     const uint32_t sw = (uint32_t)(lane & 7);
 
     for (int k = 0; k < n_stages; k++) {
@@ -136,7 +154,7 @@ __global__ void __launch_bounds__(WARPS * 32)
 
 #pragma unroll 1
         for (int ct = 0; ct < SUB / CSUB; ct++) {
-            unsigned char *cbuf = buf + ct * CSUB * BOX_BYTES;
+            unsigned char *cbuf = buf + ct * CSUB * UNIT_BYTES;
             const int rem = remaining - ct * CTS;
             if (rem >= CTS) {
                 V vin, vout;
@@ -147,7 +165,7 @@ __global__ void __launch_bounds__(WARPS * 32)
                             return (T)0;
                         if (i % VN == 0) {
                             const int box = i / TSB, chunk = (i % TSB) / VN;
-                            vin = *reinterpret_cast<const V *>(cbuf + box * BOX_BYTES + row_off + (((uint32_t)chunk ^ sw) << 4));
+                            vin = *reinterpret_cast<const V *>(cbuf + box * UNIT_BYTES + row_off + (((uint32_t)chunk ^ sw) << 4));
                         }
                         return vget(vin, i % VN);
                     },
@@ -155,21 +173,21 @@ __global__ void __launch_bounds__(WARPS * 32)
                         if constexpr (MODE == ROWS_SEG_ACC) {
                             if (i % VN == 0) {
                                 const int box = i / TSB, chunk = (i % TSB) / VN;
-                                vout = *reinterpret_cast<const V *>(cbuf + box * BOX_BYTES + row_off + (((uint32_t)chunk ^ sw) << 4));
+                                vout = *reinterpret_cast<const V *>(cbuf + box * UNIT_BYTES + row_off + (((uint32_t)chunk ^ sw) << 4));
                             }
                             y += vget(vout, i % VN);
                         }
                         vset(vout, i % VN, y);
                         if (i % VN == VN - 1) {
                             const int box = i / TSB, chunk = (i % TSB) / VN;
-                            *reinterpret_cast<V *>(cbuf + box * BOX_BYTES + row_off + (((uint32_t)chunk ^ sw) << 4)) = vout;
+                            *reinterpret_cast<V *>(cbuf + box * UNIT_BYTES + row_off + (((uint32_t)chunk ^ sw) << 4)) = vout;
                         }
                     });
             } else if (rem > 0) {
                 // ragged tail: plain sample-by-sample order (same arithmetic, see iir_core.cuh)
                 for (int i = 0; i < rem; i++) {
                     const int box = i / TSB, chunk = (i % TSB) / VN, e = i % VN;
-                    T *p = reinterpret_cast<T *>(cbuf + box * BOX_BYTES + row_off + (((uint32_t)chunk ^ sw) << 4)) + e;
+                    T *p = reinterpret_cast<T *>(cbuf + box * UNIT_BYTES + row_off + (((uint32_t)chunk ^ sw) << 4)) + e;
                     if constexpr (MODE == ROWS_SEG_ACC)
                         *p += iir_step<T, M, KIND>((T)0, c, st);
                     else
@@ -180,14 +198,23 @@ __global__ void __launch_bounds__(WARPS * 32)
         fence_proxy_async(); // generic-proxy writes above -> visible to the TMA store below
         __syncwarp();
         if (lane == 0) {
+            if (use_blocked && remaining >= TS) {
 #pragma unroll
-            for (int g = 0; g < 32 / RG; g++)
-#pragma unroll
-                for (int u = 0; u < SUB; u++)
+                for (int g = 0; g < 32 / RG; g++)
                     if constexpr (MODE == ROWS_PLAIN)
-                        tma_store_2d(&map, k * TS + u * TSB, y0 + g * RG, buf + u * BOX_BYTES + g * RG * 128);
+                        tma_store_3d(&bmap, 0, y0 + g * RG, k * SUB, buf + g * GROUP_BYTES);
                     else
-                        tma_store_3d(&map, k * TS + u * TSB, seg_of[g], chn_of[g], buf + u * BOX_BYTES + g * RG * 128);
+                        tma_store_4d(&bmap, 0, seg_of[g], chn_of[g], k * SUB, buf + g * GROUP_BYTES);
+            } else {
+#pragma unroll
+                for (int g = 0; g < 32 / RG; g++)
+#pragma unroll
+                    for (int u = 0; u < SUB; u++)
+                        if constexpr (MODE == ROWS_PLAIN)
+                            tma_store_2d(&map, k * TS + u * TSB, y0 + g * RG, buf + g * GROUP_BYTES + u * UNIT_BYTES);
+                        else
+                            tma_store_3d(&map, k * TS + u * TSB, seg_of[g], chn_of[g], buf + g * GROUP_BYTES + u * UNIT_BYTES);
+            }
             tma_commit();
         }
     }
@@ -195,6 +222,17 @@ __global__ void __launch_bounds__(WARPS * 32)
         tma_wait_all();
     if (active && MODE != ROWS_SEG_ACC) // (the correction pass ends in a history that is negligible by construction)
         iir_store_state<T, M>(st, state, n_channels, ch);
+}
+
+// SDSP_B200_IIR_BLOCKED=0 (comparison aid): every stage box by box through the plain view
+static int iir_tma_blocked_view()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("SDSP_B200_IIR_BLOCKED");
+        v = e ? atoi(e) != 0 : 1;
+    }
+    return v;
 }
 
 template <typename T, int M, int KIND, int SUB, int CSUB, int NST, int PF, int WARPS, int RG, bool PACK = true>
@@ -218,6 +256,21 @@ static int launch_tma_cfg(const IirBank &b, void *data, size_t n_samples, size_t
     if (r != CUDA_SUCCESS)
         return set_error(SDSP_B200_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d (n_samples=%zu channels=%zu pitch=%llu)", (int)r, n_samples,
                          b.n_channels, (unsigned long long)pitch);
+    // the blocked view: (sample inside a 128-byte block, channel, block index); whole blocks only
+    CUtensorMap bmap;
+    {
+        const cuuint64_t blocks = n_samples / TSB ? n_samples / TSB : 1;
+        const cuuint64_t bdim[3] = { (cuuint64_t)TSB, (cuuint64_t)b.n_channels, blocks };
+        const cuuint64_t bstride[2] = { pitch, 128 };
+        const cuuint32_t bbox[3] = { (cuuint32_t)TSB, (cuuint32_t)RG, (cuuint32_t)SUB };
+        const cuuint32_t bestr[3] = { 1, 1, 1 };
+        r = get_encode_fn()(&bmap, sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, data, bdim,
+                            bstride, bbox, bestr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, pr,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS)
+            return set_error(SDSP_B200_ERR_CUDA, "cuTensorMapEncodeTiled (blocked view) failed with %d (n_samples=%zu channels=%zu pitch=%llu)",
+                             (int)r, n_samples, b.n_channels, (unsigned long long)pitch);
+    }
     auto kern = iir_tma_kernel<T, M, KIND, SUB, CSUB, NST, PF, WARPS, RG, ROWS_PLAIN, PACK>;
     constexpr size_t smem = (size_t)WARPS * NST * SUB * 32 * 128;
     static bool configured_dev[64] = {};
@@ -228,8 +281,8 @@ static int launch_tma_cfg(const IirBank &b, void *data, size_t n_samples, size_t
     }
     const size_t groups = (b.n_channels + 31) / 32;
     const unsigned grid = (unsigned)((groups + WARPS - 1) / WARPS);
-    kern<<<grid, WARPS * 32, smem, stream>>>(map, (int)n_samples, static_cast<const T *>(b.d_coef), static_cast<T *>(b.d_state), b.n_channels,
-                                             b.n_channels, 1u);
+    kern<<<grid, WARPS * 32, smem, stream>>>(map, bmap, (int)n_samples, static_cast<const T *>(b.d_coef), static_cast<T *>(b.d_state),
+                                             b.n_channels, b.n_channels, 1u, iir_tma_blocked_view());
     SDSP_CUDA(cudaGetLastError());
     return SDSP_B200_OK;
 }
@@ -488,11 +541,26 @@ static int launch_rows_cfg(const IirBank &b, void *data, size_t seg_len, size_t 
     if (r != CUDA_SUCCESS)
         return set_error(SDSP_B200_ERR_CUDA, "cuTensorMapEncodeTiled (3-D) failed with %d (seg_len=%zu segs=%zu channels=%zu pitch=%llu)", (int)r,
                          seg_len, segs, b.n_channels, (unsigned long long)ch_pitch);
+    // blocked view: (sample inside a 128-byte block, segment, channel, block index inside the segment)
+    CUtensorMap bmap;
+    {
+        const cuuint64_t blocks = seg_len / TSB ? seg_len / TSB : 1;
+        const cuuint64_t bdim[4] = { (cuuint64_t)TSB, (cuuint64_t)segs, (cuuint64_t)b.n_channels, blocks };
+        const cuuint64_t bstride[3] = { (cuuint64_t)seg_len * sizeof(T), ch_pitch, 128 };
+        const cuuint32_t bbox[4] = { (cuuint32_t)TSB, (cuuint32_t)RG, 1, (cuuint32_t)SUB };
+        const cuuint32_t bestr[4] = { 1, 1, 1, 1 };
+        r = get_encode_fn()(&bmap, sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, data, bdim,
+                            bstride, bbox, bestr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS)
+            return set_error(SDSP_B200_ERR_CUDA, "cuTensorMapEncodeTiled (blocked 4-D) failed with %d (seg_len=%zu segs=%zu channels=%zu)", (int)r,
+                             seg_len, segs, b.n_channels);
+    }
     const size_t rows = b.n_channels * segs;
     const size_t groups = (rows + 31) / 32;
     const unsigned grid = (unsigned)((groups + WARPS - 1) / WARPS);
-    kern<<<grid, WARPS * 32, smem, stream>>>(map, (int)n_samples, static_cast<const T *>(b.d_coef), static_cast<T *>(row_state), rows,
-                                             b.n_channels, (unsigned)segs);
+    kern<<<grid, WARPS * 32, smem, stream>>>(map, bmap, (int)n_samples, static_cast<const T *>(b.d_coef), static_cast<T *>(row_state), rows,
+                                             b.n_channels, (unsigned)segs, iir_tma_blocked_view());
     SDSP_CUDA(cudaGetLastError());
     return SDSP_B200_OK;
 }
@@ -566,19 +634,38 @@ static int launch_tma(const IirBank &b, void *data, size_t n_samples, size_t str
         if (pipe == 1)
             return launch_tma_pipe<T, M, KIND, 2, 2, 6>(b, data, n_samples, stride, stream);
     }
-    // single-warp CTAs, 8-row boxes (measured best of the sweep in profiles/r01_iir_tma_config_sweep.txt).  fp32: scalar
-    // arithmetic while the bank leaves schedulers to spare (a warp alone on its scheduler is latency-bound), packed once
-    // every SM holds its four warps; SDSP_B200_IIR_PACK=0|1 pins the choice (comparison aid).  Same bits either way.
+    // single-warp CTAs, 8-row boxes; ring of three 128-byte x 4 stages, two in flight (profiles/r02_iir_tma_ring_sweep.txt;
+    // round 1's sweep, before the blocked view: profiles/r01_iir_tma_config_sweep.txt).  fp32: scalar arithmetic while the bank
+    // leaves schedulers to spare, packed once every SM holds its four warps; SDSP_B200_IIR_PACK=0|1 pins the choice
+    // (comparison aid).  Same bits either way.
+    bool pack = false;
     if constexpr (sizeof(T) == 4) {
         static int pin = -2;
         if (pin == -2) {
             const char *e = getenv("SDSP_B200_IIR_PACK");
             pin = e ? atoi(e) : -1;
         }
-        const bool pack = pin >= 0 ? pin != 0 : (b.n_channels + 31) / 32 >= (size_t)b.sm_count * 4;
-        if (!pack)
-            return launch_tma_cfg<T, M, KIND, 2, 2, 6, 3, 1, 8, false>(b, data, n_samples, stride, stream, promo);
+        pack = pin >= 0 ? pin != 0 : (b.n_channels + 31) / 32 >= (size_t)b.sm_count * 4;
     }
+    if constexpr (M == 4 && KIND == NUM_GENERIC) { // SDSP_B200_TMA_TUNE (kernel-tuning aid): ring shape of the plain pass
+        static int tune = -1;
+        if (tune < 0) {
+            const char *e = getenv("SDSP_B200_TMA_TUNE");
+            tune = e ? atoi(e) : 0;
+        }
+        switch (tune) { //                                  SUB CSUB NST PF
+        case 1: return launch_tma_cfg<T, M, KIND, 4, 2, 3, 1, 1, 8, false>(b, data, n_samples, stride, stream, promo);
+        case 2: return launch_tma_cfg<T, M, KIND, 2, 2, 6, 3, 1, 8, false>(b, data, n_samples, stride, stream, promo);
+        case 3: return launch_tma_cfg<T, M, KIND, 4, 2, 3, 2, 1, 8, false>(b, data, n_samples, stride, stream, promo);
+        case 4: return launch_tma_cfg<T, M, KIND, 2, 2, 4, 1, 1, 8, false>(b, data, n_samples, stride, stream, promo);
+        case 5: return launch_tma_cfg<T, M, KIND, 2, 2, 4, 2, 1, 8, false>(b, data, n_samples, stride, stream, promo);
+        case 6: return launch_tma_cfg<T, M, KIND, 2, 2, 6, 2, 1, 8, false>(b, data, n_samples, stride, stream, promo);
+        case 7: return launch_tma_cfg<T, M, KIND, 4, 2, 2, 1, 1, 8, false>(b, data, n_samples, stride, stream, promo);
+        default: break;
+        }
+    }
+    if (!pack)
+        return launch_tma_cfg<T, M, KIND, 4, 2, 3, 2, 1, 8, false>(b, data, n_samples, stride, stream, promo);
     return launch_tma_cfg<T, M, KIND, 2, 2, 6, 3, 1, 8, true>(b, data, n_samples, stride, stream, promo);
 }
 

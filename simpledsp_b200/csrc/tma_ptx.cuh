@@ -107,6 +107,19 @@ namespace
                      "r"(smem_u32(smem_src))
                      : "memory");
     }
+    __device__ __forceinline__ void tma_load_4d(void *smem_dst, const CUtensorMap *map, int x, int y, int z, int w, uint64_t *bar)
+    {
+        asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
+                         smem_u32(smem_dst)),
+                     "l"(map), "r"(x), "r"(y), "r"(z), "r"(w), "r"(smem_u32(bar))
+                     : "memory");
+    }
+    __device__ __forceinline__ void tma_store_4d(const CUtensorMap *map, int x, int y, int z, int w, const void *smem_src)
+    {
+        asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];" ::"l"(map), "r"(x), "r"(y), "r"(z),
+                     "r"(w), "r"(smem_u32(smem_src))
+                     : "memory");
+    }
     __device__ __forceinline__ void tma_commit()
     {
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
