@@ -12,9 +12,11 @@
 // bottom are additions -- the reference transforms one frame per call.
 #pragma once
 #include <array>
+#include <cmath>
 #include <complex>
 #include <cstddef>
 #include <cstdint>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <type_traits>
@@ -95,15 +97,15 @@ namespace detail
     template <class T, int RADIX, typename S>
     void run(std::complex<S> *frames, uint32_t n, size_t n_frames, int ptr_kind = SDSP_B200_PTR_HOST, void *stream = nullptr)
     {
-        // plans are keyed by size at run time for the pointer overloads
-        thread_local std::vector<std::pair<uint32_t, plan_holder *>> cache;
+        // plans are keyed by size at run time for the pointer overloads; the cache owns them (released at thread exit)
+        thread_local std::vector<std::pair<uint32_t, std::unique_ptr<plan_holder>>> cache;
         plan_holder *h = nullptr;
         for (auto &e : cache)
             if (e.first == n)
-                h = e.second;
+                h = e.second.get();
         if (!h) {
-            h = new plan_holder(n, RADIX, precision_of<S>(), T::Direction());
-            cache.emplace_back(n, h);
+            cache.emplace_back(n, std::make_unique<plan_holder>(n, RADIX, precision_of<S>(), T::Direction()));
+            h = cache.back().second.get();
         }
         check(sdsp_b200_fft_exec(h->plan, frames, n_frames, ptr_kind, stream), "sdsp_b200_fft_exec");
     }
@@ -111,18 +113,81 @@ namespace detail
     template <class T, int RADIX, typename S>
     void run_real(const S *real_frames, std::complex<S> *spectra, uint32_t n, size_t n_frames, int ptr_kind, void *stream)
     {
-        thread_local std::vector<std::pair<uint32_t, plan_holder *>> cache;
+        thread_local std::vector<std::pair<uint32_t, std::unique_ptr<plan_holder>>> cache;
         plan_holder *h = nullptr;
         for (auto &e : cache)
             if (e.first == n)
-                h = e.second;
+                h = e.second.get();
         if (!h) {
-            h = new plan_holder(n, RADIX, precision_of<S>(), T::Direction());
-            cache.emplace_back(n, h);
+            cache.emplace_back(n, std::make_unique<plan_holder>(n, RADIX, precision_of<S>(), T::Direction()));
+            h = cache.back().second.get();
         }
         check(sdsp_b200_fft_exec_real(h->plan, real_frames, spectra, n_frames, ptr_kind, stream), "sdsp_b200_fft_exec_real");
     }
 } // namespace detail
+
+// ---- trigonometric tables: reference fft.h:54-119, 148-214 --------------------------------------
+// The policy classes keep the reference's member names: the value at 0 and 90 degrees, the function itself, and the
+// sign a value picks up when the table walk is reflected at 0 / at 90 degrees.
+class sine_calculator {
+public:
+    constexpr static double Value0() { return 0.0; }
+    constexpr static double Value90() { return 1.0; }
+    constexpr static double Value(double rad) { return std::sin(rad); }
+    constexpr static double Sym0() { return -1.0; }
+    constexpr static double Sym90() { return 1.0; }
+};
+class cosine_calculator {
+public:
+    constexpr static double Value0() { return 1.0; }
+    constexpr static double Value90() { return 0.0; }
+    constexpr static double Value(double rad) { return std::cos(rad); }
+    constexpr static double Sym0() { return 1.0; }
+    constexpr static double Sym90() { return -1.0; }
+};
+
+// row i, column j: T(2 pi j / 2^(i+1)) straight from libm (fft.h:54-65; the reference keeps it as the unused alternative)
+template <size_t N, class T>
+constexpr trig_array<N> calc_trigs_naive()
+{
+    trig_array<N> t{};
+    for (size_t i{ 0 }; i < t.size(); i++)
+        for (size_t j{ 0 }; j < N; j++)
+            t[i][j] = T::Value(2 * M_PI * static_cast<double>(j) / static_cast<double>(size_t{ 2 } << i));
+    return t;
+}
+
+// The same table with libm evaluated on the first quarter wave only (fft.h:148-194): 0 and 90 degrees are exact, every
+// other entry is a first-quadrant value times the product of the reflection signs collected on the way there -- so the
+// table has the exact symmetries the butterflies rely on.  Written here in closed form per index (quadrant = j / quarter
+// wave) instead of the reference's running walk; an entry that falls ON a reflection point carries the sign of the
+// quadrant the walk arrives from, which reproduces the reference's table down to the sign of its zeros.
+template <size_t N, class T>
+constexpr trig_array<N> calc_trigs()
+{
+    trig_array<N> t{};
+    for (size_t i{ 0 }; i < t.size(); i++) {
+        const size_t period{ size_t{ 2 } << i }, quarter{ period / 4 };
+        for (size_t j{ 0 }; j < N; j++) {
+            if (i == 0) { // period 2: +v, -v, +v, ... (each entry the previous one negated)
+                t[i][j] = (j == 0) ? T::Value0() : t[i][j - 1] * -1.0;
+                continue;
+            }
+            // i == 1 has an empty first quadrant (quarter == 1): only the exact points exist
+            const size_t quad{ j / quarter }, r{ j % quarter };
+            const size_t from{ (r == 0 && quad > 0) ? quad - 1 : quad }; // reflection points belong to the quadrant before
+            const size_t fold{ (quad % 2 == 0) ? r : quarter - r };       // index on the first quarter wave, 0 .. quarter
+            const double v{ fold == 0 ? T::Value0() :
+                            fold == quarter ? T::Value90() :
+                                              T::Value(2 * M_PI * static_cast<double>(fold) / static_cast<double>(period)) };
+            double sign{ 1.0 };
+            for (size_t q{ 0 }; q < from % 4; q++) // quadrant signs: 1, Sym90, Sym90 Sym0, Sym90 Sym0 Sym90
+                sign *= (q % 2 == 0) ? T::Sym90() : T::Sym0();
+            t[i][j] = v * sign;
+        }
+    }
+    return t;
+}
 
 // ---- direction policies: reference fft.h:121-146 ---------------------------------------------
 // Sign() keeps the reference's meaning (+1 forward: e^{-i theta}; -1 reverse).  ScaleValues is kept
@@ -189,10 +254,23 @@ constexpr std::array<uint, N> calc_swap_lookup()
     return t;
 }
 
-// calc_wCoeffs<N, T>: W[i][j] = exp(-i * Sign * 2 pi j / 2^(i+1)) (fft.h:197-214).  Produced by the
-// library's table generator (the one that fills the device tables); not constexpr.
+// calc_wCoeffs<N, T>: W[i][j] = cos - i Sign sin of 2 pi j / 2^(i+1) (fft.h:197-214), from the two tables above -- constexpr
+// like the reference's, for callers that build their own tables from it.  (The transforms below do not read it: the
+// device tables come from the library's generator, whose host-side copy is calc_wCoeffs_library.)
 template <size_t N, class T>
-coeff_array<N> calc_wCoeffs()
+constexpr coeff_array<N> calc_wCoeffs()
+{
+    const trig_array<N> c{ calc_trigs<N, cosine_calculator>() };
+    const trig_array<N> s{ calc_trigs<N, sine_calculator>() };
+    coeff_array<N> w{};
+    for (size_t i{ 0 }; i < w.size(); i++)
+        for (size_t j{ 0 }; j < N; j++)
+            w[i][j] = std::complex<double>(c[i][j], T::Sign() * -1.0 * s[i][j]);
+    return w;
+}
+// addition: the same table as the library's own generator produces it (octant-symmetric, long double)
+template <size_t N, class T>
+coeff_array<N> calc_wCoeffs_library()
 {
     coeff_array<N> w{};
     detail::check(sdsp_b200_twiddle_table(static_cast<uint32_t>(N), T::Direction(), reinterpret_cast<double *>(w.data())),
@@ -205,6 +283,7 @@ template <class T = forward_fft, size_t N>
 void fft_radix2(complex_array<N> &data)
 {
     static_assert(isPowerOf2(N), "FFT size must be a power of 2!");
+    static_assert(N <= SDSP_B200_FFT_MAX_N_F64, "libsdsp_b200 transforms double frames of up to 2^17 points");
     static detail::plan_holder holder(static_cast<uint32_t>(N), 2, SDSP_B200_F64, T::Direction());
     detail::check(sdsp_b200_fft_exec(holder.plan, data.data(), 1, SDSP_B200_PTR_HOST, nullptr), "sdsp_b200_fft_exec");
 }
@@ -213,6 +292,7 @@ template <class T = forward_fft, size_t N>
 void fft_radix4(complex_array<N> &data)
 {
     static_assert(isPowerOf4(N), "FFT radix 4 size must be a power of 4!");
+    static_assert(N <= SDSP_B200_FFT_MAX_N_F64, "libsdsp_b200 transforms double frames of up to 2^17 points");
     static detail::plan_holder holder(static_cast<uint32_t>(N), 4, SDSP_B200_F64, T::Direction());
     detail::check(sdsp_b200_fft_exec(holder.plan, data.data(), 1, SDSP_B200_PTR_HOST, nullptr), "sdsp_b200_fft_exec");
 }
@@ -222,12 +302,14 @@ template <class T = forward_fft, size_t N>
 void fft_radix2(complex_array_f<N> &data)
 {
     static_assert(isPowerOf2(N), "FFT size must be a power of 2!");
+    static_assert(N <= SDSP_B200_FFT_MAX_N_F32, "libsdsp_b200 transforms float frames of up to 2^18 points");
     detail::run<T, 2, float>(data.data(), static_cast<uint32_t>(N), 1);
 }
 template <class T = forward_fft, size_t N>
 void fft_radix4(complex_array_f<N> &data)
 {
     static_assert(isPowerOf4(N), "FFT radix 4 size must be a power of 4!");
+    static_assert(N <= SDSP_B200_FFT_MAX_N_F32, "libsdsp_b200 transforms float frames of up to 2^18 points");
     detail::run<T, 4, float>(data.data(), static_cast<uint32_t>(N), 1);
 }
 // n_frames contiguous frames of n points (host memory), transformed in place

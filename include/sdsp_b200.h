@@ -34,6 +34,9 @@ extern "C" {
 #endif
 
 #define SDSP_B200_VERSION 200 /* 0.2.0 */
+/* largest frame sdsp_b200_fft_plan_create accepts (the reference takes any power of two its compiler can fold tables for) */
+#define SDSP_B200_FFT_MAX_N_F32 (1u << 18)
+#define SDSP_B200_FFT_MAX_N_F64 (1u << 17)
 
 enum sdsp_b200_status {
     SDSP_B200_OK = 0,

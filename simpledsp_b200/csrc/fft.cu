@@ -15,6 +15,7 @@
 #include <cuda_runtime.h>
 
 #include "fft_core.cuh"
+#include "host_stage.h"
 #include "tma_ptx.cuh"
 
 namespace sdsp_b200
@@ -376,6 +377,7 @@ struct FftPlan {
     // host staging (ptr_kind == HOST)
     void *d_stage = nullptr;
     size_t stage_bytes = 0;
+    HostStage host;
     std::mutex mu;
 };
 
@@ -1908,6 +1910,7 @@ int sdsp_b200_fft_plan_destroy(sdsp_b200_fft_plan plan)
         cudaFree(plan->p.d_tw);
     if (plan->p.d_stage)
         cudaFree(plan->p.d_stage);
+    plan->p.host.release();
     for (void *q : { plan->p.d_tw_cols, plan->p.d_tw_rows, plan->p.d_tw_hi, plan->p.d_tw_lo, plan->p.d_scratch, plan->p.d_fused_counters })
         if (q)
             cudaFree(q);
@@ -1934,58 +1937,63 @@ int sdsp_b200_fft_exec(sdsp_b200_fft_plan plan, void *data, size_t n_frames, int
     if (ptr_kind != SDSP_B200_PTR_HOST)
         return set_error(SDSP_B200_ERR_INVALID_ARG, "fft_exec: bad ptr_kind %d", ptr_kind);
 
-    // host data: stage through device memory in slabs so transfers of one slab overlap the transform
-    // of another (three streams would be overkill: H2D, kernel and D2H of consecutive slabs are chained
-    // on two alternating streams)
+    // host data (see host_stage.h): synchronous; anything the caller queued on `stream` is waited for first
     std::lock_guard<std::mutex> lock(p.mu);
+    if (s)
+        SDSP_CUDA(cudaStreamSynchronize(s));
+    int rc = p.host.ensure();
+    if (rc)
+        return rc;
     const size_t frame_bytes = (size_t)p.n * elem;
+    const size_t total = n_frames * frame_bytes;
+    if (total <= HostStage::BOUNCE_BYTES) { // one frame / a few frames: latency path through the pinned bounce buffer
+        rc = ensure_device_stage(p.d_stage, p.stage_bytes, total, "fft_exec");
+        if (rc)
+            return rc;
+        cudaStream_t cs = p.host.stream[0];
+        memcpy(p.host.bounce, data, total);
+        SDSP_CUDA(cudaMemcpyAsync(p.d_stage, p.host.bounce, total, cudaMemcpyHostToDevice, cs));
+        rc = p.launch(p, p.d_stage, nullptr, n_frames, cs);
+        if (rc)
+            return rc;
+        SDSP_CUDA(cudaMemcpyAsync(p.host.bounce, p.d_stage, total, cudaMemcpyDeviceToHost, cs));
+        SDSP_CUDA(cudaStreamSynchronize(cs));
+        memcpy(data, p.host.bounce, total);
+        return SDSP_B200_OK;
+    }
     size_t slab_frames = (64u << 20) / frame_bytes;
     if (slab_frames < 1)
         slab_frames = 1;
     if (slab_frames > n_frames)
         slab_frames = n_frames;
     const int nbuf = n_frames > slab_frames ? 2 : 1;
-    const size_t need = slab_frames * frame_bytes * nbuf;
-    if (p.stage_bytes < need) {
-        if (p.d_stage)
-            cudaFree(p.d_stage);
-        p.d_stage = nullptr;
-        p.stage_bytes = 0;
-        cudaError_t e = cudaMalloc(&p.d_stage, need);
-        if (e != cudaSuccess) {
-            cudaGetLastError();
-            return set_error(SDSP_B200_ERR_OOM, "fft_exec: cannot allocate %zu bytes of staging memory", need);
-        }
-        p.stage_bytes = need;
-    }
-    cudaStream_t st[2] = { nullptr, nullptr };
-    for (int i = 0; i < nbuf; i++)
-        SDSP_CUDA(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
-    int rc = SDSP_B200_OK;
+    rc = ensure_device_stage(p.d_stage, p.stage_bytes, slab_frames * frame_bytes * nbuf, "fft_exec");
+    if (rc)
+        return rc;
     size_t done = 0;
     int which = 0;
+    bool first = true;
     while (done < n_frames && rc == SDSP_B200_OK) {
         const size_t cnt = (n_frames - done) < slab_frames ? (n_frames - done) : slab_frames;
         char *h = static_cast<char *>(data) + done * frame_bytes;
         char *d = static_cast<char *>(p.d_stage) + (size_t)which * slab_frames * frame_bytes;
-        cudaStream_t cs = st[which];
+        cudaStream_t cs = p.host.stream[which];
         if (cudaMemcpyAsync(d, h, cnt * frame_bytes, cudaMemcpyHostToDevice, cs) != cudaSuccess)
             rc = cuda_fail((int)cudaGetLastError(), "H2D", __FILE__, __LINE__);
+        // the transforms of consecutive slabs share the plan's scratch ring and counters (n >= 32768): one at a time
+        if (rc == SDSP_B200_OK && !first && cudaStreamWaitEvent(cs, p.host.kernel_done[which ^ 1], 0) != cudaSuccess)
+            rc = cuda_fail((int)cudaGetLastError(), "cudaStreamWaitEvent", __FILE__, __LINE__);
         if (rc == SDSP_B200_OK)
             rc = p.launch(p, d, nullptr, cnt, cs);
+        if (rc == SDSP_B200_OK && cudaEventRecord(p.host.kernel_done[which], cs) != cudaSuccess)
+            rc = cuda_fail((int)cudaGetLastError(), "cudaEventRecord", __FILE__, __LINE__);
         if (rc == SDSP_B200_OK && cudaMemcpyAsync(h, d, cnt * frame_bytes, cudaMemcpyDeviceToHost, cs) != cudaSuccess)
             rc = cuda_fail((int)cudaGetLastError(), "D2H", __FILE__, __LINE__);
         done += cnt;
         which = (which + 1) % nbuf;
+        first = false;
     }
-    for (int i = 0; i < nbuf; i++) {
-        cudaError_t e = cudaStreamSynchronize(st[i]);
-        if (e != cudaSuccess && rc == SDSP_B200_OK)
-            rc = cuda_fail((int)e, "cudaStreamSynchronize", __FILE__, __LINE__);
-        cudaStreamDestroy(st[i]);
-    }
-    (void)s;
-    return rc;
+    return p.host.drain(rc);
 }
 
 // real frames in, spectra out (out of place): the imaginary part of the input is zero, as in every call site of
@@ -2008,34 +2016,42 @@ int sdsp_b200_fft_exec_real(sdsp_b200_fft_plan plan, const void *real_in, void *
         return p.launch(p, spectrum_out, real_in, n_frames, s);
     if (ptr_kind != SDSP_B200_PTR_HOST)
         return set_error(SDSP_B200_ERR_INVALID_ARG, "fft_exec_real: bad ptr_kind %d", ptr_kind);
-    // host buffers: slabs through the plan's staging memory (spectrum slab first, real slab behind it)
+    // host buffers (see host_stage.h): slabs through the plan's staging memory, each buffer = spectrum slab + real slab behind it
     std::lock_guard<std::mutex> lock(p.mu);
+    if (s)
+        SDSP_CUDA(cudaStreamSynchronize(s));
+    int rc = p.host.ensure();
+    if (rc)
+        return rc;
     const size_t in_bytes = (size_t)p.n * es, out_bytes = 2 * in_bytes;
     size_t slab = (64u << 20) / out_bytes;
     slab = slab < 1 ? 1 : slab > n_frames ? n_frames : slab;
-    const size_t need = slab * (in_bytes + out_bytes);
-    if (p.stage_bytes < need) {
-        if (p.d_stage)
-            cudaFree(p.d_stage);
-        p.d_stage = nullptr;
-        p.stage_bytes = 0;
-        if (cudaMalloc(&p.d_stage, need) != cudaSuccess) {
-            cudaGetLastError();
-            return set_error(SDSP_B200_ERR_OOM, "fft_exec_real: cannot allocate %zu bytes of staging memory", need);
-        }
-        p.stage_bytes = need;
-    }
-    char *d_out = static_cast<char *>(p.d_stage), *d_in = d_out + slab * out_bytes;
-    for (size_t done = 0; done < n_frames; done += slab) {
+    const int nbuf = n_frames > slab ? 2 : 1;
+    const size_t buf_bytes = slab * (in_bytes + out_bytes);
+    rc = ensure_device_stage(p.d_stage, p.stage_bytes, buf_bytes * nbuf, "fft_exec_real");
+    if (rc)
+        return rc;
+    int which = 0;
+    bool first = true;
+    for (size_t done = 0; done < n_frames && rc == SDSP_B200_OK; done += slab) {
         const size_t cnt = (n_frames - done) < slab ? (n_frames - done) : slab;
-        SDSP_CUDA(cudaMemcpyAsync(d_in, static_cast<const char *>(real_in) + done * in_bytes, cnt * in_bytes, cudaMemcpyHostToDevice, s));
-        const int rc = p.launch(p, d_out, d_in, cnt, s);
-        if (rc)
-            return rc;
-        SDSP_CUDA(cudaMemcpyAsync(static_cast<char *>(spectrum_out) + done * out_bytes, d_out, cnt * out_bytes, cudaMemcpyDeviceToHost, s));
-        SDSP_CUDA(cudaStreamSynchronize(s));
+        char *d_out = static_cast<char *>(p.d_stage) + (size_t)which * buf_bytes, *d_in = d_out + slab * out_bytes;
+        cudaStream_t cs = p.host.stream[which];
+        if (cudaMemcpyAsync(d_in, static_cast<const char *>(real_in) + done * in_bytes, cnt * in_bytes, cudaMemcpyHostToDevice, cs) != cudaSuccess)
+            rc = cuda_fail((int)cudaGetLastError(), "H2D", __FILE__, __LINE__);
+        if (rc == SDSP_B200_OK && !first && cudaStreamWaitEvent(cs, p.host.kernel_done[which ^ 1], 0) != cudaSuccess)
+            rc = cuda_fail((int)cudaGetLastError(), "cudaStreamWaitEvent", __FILE__, __LINE__);
+        if (rc == SDSP_B200_OK)
+            rc = p.launch(p, d_out, d_in, cnt, cs);
+        if (rc == SDSP_B200_OK && cudaEventRecord(p.host.kernel_done[which], cs) != cudaSuccess)
+            rc = cuda_fail((int)cudaGetLastError(), "cudaEventRecord", __FILE__, __LINE__);
+        if (rc == SDSP_B200_OK &&
+            cudaMemcpyAsync(static_cast<char *>(spectrum_out) + done * out_bytes, d_out, cnt * out_bytes, cudaMemcpyDeviceToHost, cs) != cudaSuccess)
+            rc = cuda_fail((int)cudaGetLastError(), "D2H", __FILE__, __LINE__);
+        which = (which + 1) % nbuf;
+        first = false;
     }
-    return SDSP_B200_OK;
+    return p.host.drain(rc);
 }
 
 int sdsp_b200_fft_plan_describe(sdsp_b200_fft_plan plan, char *buf, size_t buf_len)

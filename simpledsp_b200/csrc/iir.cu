@@ -442,6 +442,7 @@ int sdsp_b200_iir_bank_destroy(sdsp_b200_iir_bank bank)
         cudaFree(b.d_state);
     if (b.d_stage)
         cudaFree(b.d_stage);
+    b.host.release();
     delete bank;
     return SDSP_B200_OK;
 }
@@ -545,30 +546,69 @@ int sdsp_b200_iir_bank_process(sdsp_b200_iir_bank bank, void *data, size_t n_sam
     if (ptr_kind != SDSP_B200_PTR_HOST)
         return set_error(SDSP_B200_ERR_INVALID_ARG, "iir_bank_process: bad ptr_kind %d", ptr_kind);
 
+    // host data (see host_stage.h): synchronous; anything the caller queued on `stream` (device-pointer calls that
+    // moved this bank's history) is waited for first
     std::lock_guard<std::mutex> lock(b.mu);
-    // compact staging copy [channel][n_samples], row pitch rounded to 16 bytes so the TMA path applies
-    const size_t pitch_elems = (n_samples * es + 15) / 16 * 16 / es;
-    const size_t need = b.n_channels * pitch_elems * es;
-    if (b.stage_bytes < need) {
-        if (b.d_stage)
-            cudaFree(b.d_stage);
-        b.d_stage = nullptr;
-        b.stage_bytes = 0;
-        if (cudaMalloc(&b.d_stage, need) != cudaSuccess) {
-            cudaGetLastError();
-            return set_error(SDSP_B200_ERR_OOM, "iir_bank_process: cannot allocate %zu bytes of staging memory", need);
-        }
-        b.stage_bytes = need;
-    }
-    SDSP_CUDA(cudaMemcpy2DAsync(b.d_stage, pitch_elems * es, data, channel_stride * es, n_samples * es, b.n_channels,
-                                cudaMemcpyHostToDevice, s));
-    int rc = iir_dispatch(b, b.d_stage, n_samples, pitch_elems, path, s);
+    if (s)
+        SDSP_CUDA(cudaStreamSynchronize(s));
+    int rc = b.host.ensure();
     if (rc)
         return rc;
-    SDSP_CUDA(cudaMemcpy2DAsync(data, channel_stride * es, b.d_stage, pitch_elems * es, n_samples * es, b.n_channels,
-                                cudaMemcpyDeviceToHost, s));
-    SDSP_CUDA(cudaStreamSynchronize(s));
-    return SDSP_B200_OK;
+    // The stream is cut along TIME into chunks that span all channels; the bank's history carries from chunk to chunk
+    // exactly as it does from call to call, so on the sequential path the result is bit-identical to one uncut call.
+    // Staging memory is two chunks, whatever the size of the bank (config 3 would need 64 GiB for an uncut copy).
+    // Chunk rows are 256-byte multiples so every chunk takes the same kernel (TMA path: 16-byte aligned pitch).
+    const size_t row_quantum = 256 / es;
+    size_t chunk = ((size_t)64 << 20) / (b.n_channels * es) / row_quantum * row_quantum;
+    if (chunk < 4 * row_quantum)
+        chunk = 4 * row_quantum;
+    if (chunk > n_samples)
+        chunk = n_samples;
+    const size_t pitch_elems = (chunk * es + 15) / 16 * 16 / es;
+    const size_t chunk_bytes = b.n_channels * pitch_elems * es;
+    const int nbuf = n_samples > chunk ? 2 : 1;
+    rc = ensure_device_stage(b.d_stage, b.stage_bytes, chunk_bytes * nbuf, "iir_bank_process");
+    if (rc)
+        return rc;
+    const bool small = nbuf == 1 && b.n_channels * n_samples * es <= HostStage::BOUNCE_BYTES;
+    if (small) { // one filter object / a handful of channels: latency path through the pinned bounce buffer
+        cudaStream_t cs = b.host.stream[0];
+        char *bounce = static_cast<char *>(b.host.bounce);
+        for (size_t c = 0; c < b.n_channels; c++)
+            memcpy(bounce + c * n_samples * es, static_cast<char *>(data) + c * channel_stride * es, n_samples * es);
+        SDSP_CUDA(cudaMemcpy2DAsync(b.d_stage, pitch_elems * es, bounce, n_samples * es, n_samples * es, b.n_channels, cudaMemcpyHostToDevice, cs));
+        rc = iir_dispatch(b, b.d_stage, n_samples, pitch_elems, path, cs);
+        if (rc)
+            return rc;
+        SDSP_CUDA(cudaMemcpy2DAsync(bounce, n_samples * es, b.d_stage, pitch_elems * es, n_samples * es, b.n_channels, cudaMemcpyDeviceToHost, cs));
+        SDSP_CUDA(cudaStreamSynchronize(cs));
+        for (size_t c = 0; c < b.n_channels; c++)
+            memcpy(static_cast<char *>(data) + c * channel_stride * es, bounce + c * n_samples * es, n_samples * es);
+        return SDSP_B200_OK;
+    }
+    int which = 0;
+    bool first = true;
+    for (size_t done = 0; done < n_samples && rc == SDSP_B200_OK; done += chunk) {
+        const size_t cnt = (n_samples - done) < chunk ? (n_samples - done) : chunk;
+        char *h = static_cast<char *>(data) + done * es;
+        char *d = static_cast<char *>(b.d_stage) + (size_t)which * chunk_bytes;
+        cudaStream_t cs = b.host.stream[which];
+        if (cudaMemcpy2DAsync(d, pitch_elems * es, h, channel_stride * es, cnt * es, b.n_channels, cudaMemcpyHostToDevice, cs) != cudaSuccess)
+            rc = cuda_fail((int)cudaGetLastError(), "H2D", __FILE__, __LINE__);
+        // the filter history is one object: chunk k + 1 starts where chunk k ended
+        if (rc == SDSP_B200_OK && !first && cudaStreamWaitEvent(cs, b.host.kernel_done[which ^ 1], 0) != cudaSuccess)
+            rc = cuda_fail((int)cudaGetLastError(), "cudaStreamWaitEvent", __FILE__, __LINE__);
+        if (rc == SDSP_B200_OK)
+            rc = iir_dispatch(b, d, cnt, pitch_elems, path, cs);
+        if (rc == SDSP_B200_OK && cudaEventRecord(b.host.kernel_done[which], cs) != cudaSuccess)
+            rc = cuda_fail((int)cudaGetLastError(), "cudaEventRecord", __FILE__, __LINE__);
+        if (rc == SDSP_B200_OK &&
+            cudaMemcpy2DAsync(h, channel_stride * es, d, pitch_elems * es, cnt * es, b.n_channels, cudaMemcpyDeviceToHost, cs) != cudaSuccess)
+            rc = cuda_fail((int)cudaGetLastError(), "D2H", __FILE__, __LINE__);
+        which = (which + 1) % nbuf;
+        first = false;
+    }
+    return b.host.drain(rc);
 }
 
 int sdsp_b200_iir_bank_describe(sdsp_b200_iir_bank bank, size_t n_samples, size_t channel_stride, int path, char *buf, size_t buf_len)
@@ -641,6 +681,58 @@ int sdsp_b200_iir_process_once(int sections, int numerator, int precision, doubl
         it = g_once_cache.emplace(key, nb).first;
     }
     sdsp_b200_iir_bank bk = it->second;
+    IirBank &ob = bk->b;
+    // coefficients: uploaded only when they differ from what the cached bank holds (a filter object is designed once and
+    // then called many times)
+    const int m = sections;
+    bool same = ob.h_gain.size() == 1 && ob.h_gain[0] == gain;
+    for (int k = 0; same && k < 3 * m; k++)
+        same = ob.h_a[k] == aco[k] && ob.h_b[k] == (bco ? bco[k] : 0.0);
+    if (!same) {
+        rc = sdsp_b200_iir_bank_set_coeffs(bk, 0, 1, &gain, bco, aco);
+        if (rc)
+            return rc;
+    }
+    const int hist = iir_hist_count(m);
+    const size_t data_bytes = n_samples * sizeof(double), hist_bytes = (size_t)hist * sizeof(double);
+    if (hist_bytes + data_bytes <= HostStage::BOUNCE_BYTES) {
+        // latency path: history and samples bounce through pinned memory, five asynchronous operations, one synchronisation.
+        // (one channel: the device rows [2r + i][1] are laid out exactly like mem[r][i])
+        std::lock_guard<std::mutex> bank_lock(ob.mu);
+        SDSP_CUDA(cudaSetDevice(ob.device));
+        rc = ob.host.ensure();
+        if (!rc)
+            rc = ensure_device_stage(ob.d_stage, ob.stage_bytes, (data_bytes + 15) / 16 * 16, "iir_process_once");
+        if (rc)
+            return rc;
+        cudaStream_t cs = ob.host.stream[0];
+        double *bounce = static_cast<double *>(ob.host.bounce);
+        memcpy(bounce, mem, hist_bytes);
+        if (precision == SDSP_B200_F32) {
+            const float *src = static_cast<const float *>(data);
+            for (size_t i = 0; i < n_samples; i++)
+                bounce[hist + i] = (double)src[i];
+        } else {
+            memcpy(bounce + hist, data, data_bytes);
+        }
+        SDSP_CUDA(cudaMemcpyAsync(ob.d_state, bounce, hist_bytes, cudaMemcpyHostToDevice, cs));
+        SDSP_CUDA(cudaMemcpyAsync(ob.d_stage, bounce + hist, data_bytes, cudaMemcpyHostToDevice, cs));
+        rc = iir_dispatch(ob, ob.d_stage, n_samples, (n_samples + 1) / 2 * 2, SDSP_B200_IIR_SEQUENTIAL, cs);
+        if (rc)
+            return rc;
+        SDSP_CUDA(cudaMemcpyAsync(bounce, ob.d_state, hist_bytes, cudaMemcpyDeviceToHost, cs));
+        SDSP_CUDA(cudaMemcpyAsync(bounce + hist, ob.d_stage, data_bytes, cudaMemcpyDeviceToHost, cs));
+        SDSP_CUDA(cudaStreamSynchronize(cs));
+        memcpy(mem, bounce, hist_bytes);
+        if (precision == SDSP_B200_F32) {
+            float *dst = static_cast<float *>(data);
+            for (size_t i = 0; i < n_samples; i++)
+                dst[i] = (float)bounce[hist + i];
+        } else {
+            memcpy(data, bounce + hist, data_bytes);
+        }
+        return SDSP_B200_OK;
+    }
     std::vector<double> wide;
     double *work = static_cast<double *>(data);
     if (precision == SDSP_B200_F32) {
@@ -648,9 +740,7 @@ int sdsp_b200_iir_process_once(int sections, int numerator, int precision, doubl
         wide.assign(src, src + n_samples);
         work = wide.data();
     }
-    rc = sdsp_b200_iir_bank_set_coeffs(bk, 0, 1, &gain, bco, aco);
-    if (!rc)
-        rc = sdsp_b200_iir_bank_set_state(bk, 0, 1, mem);
+    rc = sdsp_b200_iir_bank_set_state(bk, 0, 1, mem);
     if (!rc)
         rc = sdsp_b200_iir_bank_process(bk, work, n_samples, n_samples, SDSP_B200_PTR_HOST, SDSP_B200_IIR_SEQUENTIAL, nullptr);
     if (!rc)

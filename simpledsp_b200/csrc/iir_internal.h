@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include "common.h"
+#include "host_stage.h"
 
 namespace sdsp_b200
 {
@@ -41,6 +42,7 @@ struct IirBank {
     // host staging
     void *d_stage = nullptr;
     size_t stage_bytes = 0;
+    HostStage host;
     std::mutex mu;
 };
 

@@ -286,3 +286,29 @@ def test_fused_queue_with_and_without_the_data_mover_warp_agree(n, tmp_path):
     gen = torch.Generator(device="cuda").manual_seed(7)
     x = torch.view_as_complex(torch.randn(97, n, 2, device="cuda", generator=gen, dtype=torch.float32)).cpu().numpy()
     assert rel_l2(outs["1"][g], oracle_fft(x[g])) <= FFT_TOL["f32"]
+
+
+@pytest.mark.parametrize("n,frames", [(65536, 300), (4096, 6000), (1024, 3)])
+def test_host_buffers_in_slabs_match_the_device_resident_call(n, frames):
+    """Host-pointer calls stage the batch through device memory in 64 MB slabs on two alternating streams
+    (simpledsp_b200/csrc/host_stage.h).  The transforms of consecutive slabs share the plan's scratch ring and counters
+    for n >= 32768, so they are chained by events; the result must be the bits of one device-resident call.  (300 frames
+    of 65536 points = 157 MB = three slabs; three frames of 1024 points take the pinned bounce buffer.)"""
+    torch = pytest.importorskip("torch")
+    rng = np.random.default_rng(n + frames)
+    x = (rng.standard_normal((frames, n)) + 1j * rng.standard_normal((frames, n))).astype(np.complex64)
+    plan = S.FftPlan(n, 4, K.F32, K.FORWARD)
+    d = torch.from_numpy(x).cuda()
+    plan(d)
+    torch.cuda.synchronize()
+    want = d.cpu().numpy()
+    for _ in range(2):  # twice: the second call reuses the plan's streams, events and staging memory
+        got = x.copy()
+        plan(got)
+        assert np.array_equal(got, want)
+    real = np.ascontiguousarray(x.real)
+    spec = plan.real(real)
+    d2 = torch.from_numpy(real.astype(np.complex64)).cuda()
+    plan(d2)
+    torch.cuda.synchronize()
+    assert np.array_equal(spec, d2.cpu().numpy())

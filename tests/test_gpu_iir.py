@@ -503,3 +503,32 @@ def test_time_split_random_shapes_against_the_sequential_kernel(seed):
     assert float(a[:, n:].abs().max() if pitch > n else 0.0) == 0.0 and float(base[ch * pitch:].abs().max()) == 0.0, plan
     st_a, st_b = banks[0].get_state(), banks[1].get_state()
     assert np.abs(st_a - st_b).max() <= (1e-10 if prec == "f64" else 2e-5) * max(1.0, float(peak.max())), plan
+
+
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+def test_host_buffers_cut_along_time_match_the_device_resident_call(prec):
+    """A host-pointer call stages the bank through device memory in chunks of time across all channels (64 MB, two
+    streams, simpledsp_b200/csrc/host_stage.h); the history carries from chunk to chunk as from call to call, so the
+    sequential path must give the bits of ONE device-resident call -- and the same history afterwards.  300 channels x
+    150000 samples = 180 MB (fp32) / 360 MB (fp64): three / six chunks, ragged last one, host row pitch != chunk pitch."""
+    torch = pytest.importorskip("torch")
+    code, dt = PREC[prec]
+    ch, n, pitch = 300, 150_000, 150_016
+    bank, x, ref = _bank_case(ch, n, prec, seed=5)
+    d = torch.from_numpy(x).cuda()
+    bank.process(d)
+    torch.cuda.synchronize()
+    want, st = d.cpu().numpy(), (bank.get_state(), bank.get_state_diff())
+    assert peak_rel(want, ref) <= IIR_TOL[prec]
+    host = np.zeros((ch, pitch), dtype=dt)
+    host[:, :n] = x
+    bank.reset_state()
+    bank.process_ptr(host.ctypes.data, n, pitch, K.PTR_HOST, K.IIR_AUTO, None)
+    assert np.array_equal(host[:, :n], want)
+    assert not host[:, n:].any()
+    assert np.array_equal(bank.get_state(), st[0]) and np.array_equal(bank.get_state_diff(), st[1])
+    # the time-parallel request through host buffers: every chunk is split again; same stream within the tolerance
+    bank.reset_state()
+    host[:, :n] = x
+    bank.process_ptr(host.ctypes.data, n, pitch, K.PTR_HOST, K.IIR_SCAN, None)
+    assert peak_rel(host[:, :n], ref) <= IIR_TOL[prec]

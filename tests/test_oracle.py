@@ -101,6 +101,37 @@ def test_fft_against_numpy_and_compiled_reference():
                 assert rel_l2(O.fft(x, radix), O.fft(x, radix, impl="reference")) < 4 * EPS
 
 
+@pytest.mark.parametrize("n", [16384, 65536])
+def test_fft_port_pinned_above_4096(n):
+    """The sizes BASELINE configs 2 and 5 are parity-checked at beyond the reference-vector fixtures: the port against
+    the UNMODIFIED reference headers compiled for N = 16384 / 65536 (oracle/_ref/libsdsp_ref_big.so, `make refbig`:
+    minutes of constexpr table folding, so it is built once and travels) and against numpy's pocketfft."""
+    import os
+
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal((2, n)) + 1j * rng.standard_normal((2, n))
+    have_big = os.path.exists(O.REF_BIG_SO)
+    for radix in (2, 4):
+        for inv in (False, True):
+            got = O.fft(x, radix, inv)
+            want = np.fft.ifft(x) if inv else np.fft.fft(x)
+            assert rel_l2(got, want) < 4 * EPS, (n, radix, inv)
+            if have_big:
+                assert rel_l2(got, O.fft(x, radix, inv, impl="reference")) < 4 * EPS, (n, radix, inv)
+    if not have_big:
+        pytest.skip("oracle/_ref/libsdsp_ref_big.so not built: numpy only")
+    for base in (2, 4):
+        assert np.array_equal(O.swap_lookup(n, base), _ref_big_swap(n, base))
+
+
+def _ref_big_swap(n, base):
+    import ctypes as C
+
+    out = np.zeros(n, dtype=np.uint32)
+    assert O.ref_lib(big=True).sdsp_ref_swap_lookup(n, base, out.ctypes.data_as(C.POINTER(C.c_uint32))) == 0
+    return out
+
+
 def test_fft_rejects_bad_sizes():
     with pytest.raises(ValueError):
         O.fft(np.zeros(12, dtype=np.complex128), 2)
