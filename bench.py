@@ -59,6 +59,11 @@ WORKLOADS = {
     # IIR along every channel (time-split path), then every frame transformed (real in, spectrum out)
     "pipeline65536_f32": dict(kind="pipeline", channels=512, frames_per_channel=64, n=65536, precision="f32", sections=4,
                               bytes_per_sample=20),
+    # BASELINE config 5 as stated: 262144 frames of 65536 points = 4096 channels x 64 frames, IIR then real-input FFT, the
+    # WHOLE job divided over the ranks (strong scaling): rank r filters its 4096/N channels in one call and transforms
+    # them in waves of 32768 frames (one 16 GiB spectrum buffer)
+    "pipeline_cfg5_f32": dict(kind="pipeline", channels=4096, frames_per_channel=64, n=65536, precision="f32", sections=4,
+                              bytes_per_sample=20, strong=True, wave_frames=32768),
     "iir16384_f32_scan": dict(kind="iir", channels=16384, samples=1 << 20, precision="f32", sections=4, bytes_per_sample=8, path="scan"),
     # same bank, channel pitch not a power of two (2^20 + 8256 samples): separates DRAM channel effects from kernel effects
     "iir16384_f32_pitch": dict(kind="iir", channels=16384, samples=1 << 20, pitch=(1 << 20) + 8256, precision="f32", sections=4,
@@ -75,7 +80,7 @@ NCU_TRAFFIC = {
     "fft4096_f32": (4.2705e9, "profiles/r01_ncu_fft4096_f32_v2.txt"),
     "fft4096_f64": (8.683e9, "profiles/r01_ncu_fft4096_f64_v2.txt"),
     "fft65536_f32": (4.3077e9, "profiles/r01_ncu_fft65536_f32_fused_tma_v2.txt"),
-    "iir16384_f32": (1.37386e11, "profiles/r01_ncu_iir16384_f32_tma_v5.txt"),
+    "iir16384_f32": (1.37387e11, "profiles/r02_ncu_iir16384_f32_delta_v1.txt"),
     "iir4096_f32_scan": (1.37408e11, "profiles/r01_ncu_iir4096_f32_split_v1.txt (main pass)"),
     "iirscan_f64": (1.7126e10, "profiles/r01_launches_iir_split_v1.txt (main pass)"),
 }
@@ -336,18 +341,44 @@ class IirWorkload:
         self.torch.cuda.synchronize()
         return float(self.torch.isfinite(self.data[:: max(1, self.ch // 64), :4096]).all().item() == 0)
 
+    # ---- end to end through the host-buffer API: a bounded stretch of the same bank (E2E_SAMPLES per channel) in pinned
+    # host memory, staged in chunks of time by sdsp_b200_iir_bank_process(PTR_HOST)
+    E2E_BYTES = 4 << 30
+
     def e2e_prepare(self):
-        return None
+        K = self.K
+        es = 4 if self.prec == K.F32 else 8
+        self.e2e_n = min(self.n, max(4096, self.E2E_BYTES // (self.ch * es)))
+        nbytes = self.ch * self.e2e_n * es
+        ptr = C.c_void_p()
+        K.check(K.lib().sdsp_b200_host_alloc(C.byref(ptr), nbytes))
+        self._pinned = ptr
+        buf = (C.c_char * nbytes).from_address(ptr.value)
+        self.host = np.frombuffer(buf, dtype=np.float32 if self.prec == K.F32 else np.float64).reshape(self.ch, self.e2e_n)
+        rng = np.random.default_rng(99)
+        blk = rng.standard_normal((min(self.ch, 256), self.e2e_n)).astype(self.host.dtype)
+        for lo in range(0, self.ch, blk.shape[0]):
+            self.host[lo:lo + blk.shape[0]] = blk[: min(blk.shape[0], self.ch - lo)]
+        self.e2e_samples_per_step = self.ch * self.e2e_n
+        self.bank.reset_state()
+        return nbytes, nbytes
+
+    def e2e_step(self):
+        self.bank.process_ptr(self.host.ctypes.data, self.e2e_n, self.e2e_n, self.K.PTR_HOST, self.path, None)
+
+    def e2e_check(self):
+        return float(np.isfinite(self.host[:: max(1, self.ch // 64), :4096]).all() == 0)
 
     def e2e_release(self):
-        pass
+        self.host = None
+        self.K.lib().sdsp_b200_host_free(self._pinned)
 
 
 class PipelineWorkload:
     """IIR bank over [channels][frames*n] real samples in place, then a real-input FFT of every n-sample frame into
     a spectrum buffer.  Algorithmic bytes per sample: 8 (filter, read + write) + 4 + 8 (transform, real in, complex out)."""
 
-    def __init__(self, spec, device):
+    def __init__(self, spec, device, world=1):
         import torch
 
         import simpledsp_b200 as S
@@ -355,6 +386,9 @@ class PipelineWorkload:
 
         self.spec, self.S, self.K, self.torch = spec, S, K, torch
         self.ch, self.fpc, self.n, self.m = spec["channels"], spec["frames_per_channel"], spec["n"], spec["sections"]
+        if spec.get("strong"):  # the stated job divided over the ranks
+            assert self.ch % world == 0
+            self.ch //= world
         self.prec = K.F32
         self.len = self.fpc * self.n
         self.bank = S.IirBank(self.m, self.ch, self.prec, K.NUM_GENERIC, device)
@@ -366,34 +400,41 @@ class PipelineWorkload:
         rows = max(1, (1 << 28) // self.len)
         for lo in range(0, self.ch, rows):
             self.signal[lo:lo + rows].normal_(generator=g)
-        self.spectra = torch.empty(self.ch * self.fpc, self.n, device="cuda", dtype=torch.complex64)
+        self.frames = self.ch * self.fpc
+        self.wave = min(self.frames, spec.get("wave_frames", self.frames))
+        self.spectra = torch.empty(self.wave, self.n, device="cuda", dtype=torch.complex64)
         self.samples_per_step = self.ch * self.len
         self.stream = torch.cuda.current_stream().cuda_stream
 
     def describe(self):
-        return self.bank.describe(self.len, self.len, self.K.IIR_SCAN) + " | then real-input " + self.plan.describe()
+        return (self.bank.describe(self.len, self.len, self.K.IIR_SCAN) + f" | then real-input, {self.frames} frames in waves of {self.wave}: "
+                + self.plan.describe())
 
     def launches_per_step(self):
         return 1
 
     def gpu_launches_per_step(self):
-        return 5  # filter: gather, row pass, carry, correction pass; transform: one cluster kernel
+        # filter: gather, row pass, carry, correction pass; transform: one persistent kernel per wave
+        return 4 + (self.frames + self.wave - 1) // self.wave
 
     def step(self):
         K = self.K
         self.bank.process_ptr(self.signal.data_ptr(), self.len, self.len, K.PTR_DEVICE, K.IIR_SCAN, self.stream)
-        self.plan.exec_real_ptr(self.signal.data_ptr(), self.spectra.data_ptr(), self.ch * self.fpc, K.PTR_DEVICE, self.stream)
+        for lo in range(0, self.frames, self.wave):
+            cnt = min(self.wave, self.frames - lo)
+            self.plan.exec_real_ptr(self.signal.data_ptr() + lo * self.n * 4, self.spectra.data_ptr(), cnt, K.PTR_DEVICE, self.stream)
 
     def self_check(self):
         """A sampled frame of the spectrum buffer equals the transform of the filtered signal it was made from."""
         torch = self.torch
         torch.cuda.synchronize()
         worst = 0.0
-        for c, f in ((0, 0), (self.ch // 2, self.fpc // 2), (self.ch - 1, self.fpc - 1)):
-            x = self.signal[c, f * self.n:(f + 1) * self.n].double()
+        last_wave = (self.frames - 1) // self.wave * self.wave  # the spectrum buffer holds the last wave
+        for fr in (last_wave, last_wave + (self.frames - last_wave) // 2, self.frames - 1):
+            x = self.signal.view(-1)[fr * self.n:(fr + 1) * self.n].double()
             ref = torch.fft.fft(x)
-            got = self.spectra[c * self.fpc + f].to(torch.complex128)
-            worst = max(worst, float((got - ref).abs().pow(2).sum().sqrt() / ref.abs().pow(2).sum().sqrt()))
+            got = self.spectra[fr - last_wave].to(torch.complex128)
+            worst = max(worst, float((got - ref).abs().pow(2).sum().sqrt() / ref.abs().pow(2).sum().sqrt().clamp_min(1e-300)))
         return worst
 
     def e2e_prepare(self):
@@ -404,6 +445,15 @@ class PipelineWorkload:
 
 
 # --------------------------------------------------------------------------------------------------
+def config_of(name, spec):
+    """The `config` object of the JSON line -- built the same way by both arms (b200 and --impl reference)."""
+    cfg = {"workload": name, **{k: v for k, v in spec.items() if k != "kind"}}
+    cfg["per_gpu"] = not spec.get("strong", False)
+    cfg["in_place"] = True
+    cfg["l2"] = "no flush needed: the working set of one step is far larger than the 126 MB L2"
+    return cfg
+
+
 def cpu_reference_rate(spec, threads: int, target_seconds: float = 6.0):
     """The reference's own CPU implementation on a bounded sample of the workload.
     -> (Msamples/s, kind, cores, sample description, single-thread Msamples/s)"""
@@ -422,16 +472,18 @@ def cpu_reference_rate(spec, threads: int, target_seconds: float = 6.0):
     if spec["kind"] == "fft":
         n = spec["n"]
         radix = 4 if (n.bit_length() - 1) % 2 == 0 else 2
-        impl = "reference" if kind == "reference" and n <= 4096 else "port"
-        kind = "reference" if impl == "reference" else "port"
-        probe = rng.standard_normal((64, n)) + 1j * rng.standard_normal((64, n))
-        O.fft(probe[:2], radix, False, impl)  # builds the tables
+        # the compiled reference covers every power of two up to 4096 and, in the _big library, 16384 and 65536
+        compiled = kind == "reference" and (n <= 4096 or (n in (16384, 65536) and os.path.exists(O.REF_BIG_SO)))
+        impl = "reference" if compiled else "port"
+        kind = impl
+        probe = rng.standard_normal((16 if n > 4096 else 64, n)) + 1j * rng.standard_normal((16 if n > 4096 else 64, n))
+        O.fft(probe[:2], radix, False, impl)  # builds / pages in the tables
         t0 = time.perf_counter()
         O.fft(probe, radix, False, impl, threads=1)
-        one = (time.perf_counter() - t0) / 64
+        one = (time.perf_counter() - t0) / probe.shape[0]
         use_threads = threads if impl == "reference" else 1
-        frames = int(min(65536, max(use_threads * 4, target_seconds * use_threads / one)))
-        x = np.ascontiguousarray(np.tile(probe, (frames // 64 + 1, 1))[:frames])
+        frames = int(min(65536, (1 << 30) // (16 * n), max(use_threads * 4, target_seconds * use_threads / one)))
+        x = np.ascontiguousarray(np.tile(probe, (frames // probe.shape[0] + 1, 1))[:frames])
         t0 = time.perf_counter()
         O.fft(x, radix, False, impl, threads=use_threads)
         dt = time.perf_counter() - t0
@@ -449,51 +501,65 @@ def cpu_reference_rate(spec, threads: int, target_seconds: float = 6.0):
         O.iir_bank_reference(x[:1], ftype[:1], f0[:1], 100e3, sections=m, threads=1)
         one = time.perf_counter() - t0
         t0 = time.perf_counter()
-        O.iir_bank_reference(x, ftype, f0, 100e3, sections=m, threads=threads)
+        O.iir_bank_reference(x, ftype, f0, 100e3, sections=m, threads=threads)  # also sizes the sample
+        reps = max(1, int(target_seconds / max(time.perf_counter() - t0, 1e-3)))
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            O.iir_bank_reference(x, ftype, f0, 100e3, sections=m, threads=threads)
         dt = time.perf_counter() - t0
-        use_threads = threads
+        use_threads = min(threads, ch)
     else:
         t0 = time.perf_counter()
         O.iir_bank_port(x[:1], ftype[:1], f0[:1], 100e3, sections=m)
         one = time.perf_counter() - t0
+        reps = 1
         t0 = time.perf_counter()
         O.iir_bank_port(x, ftype, f0, 100e3, sections=m)
         dt = time.perf_counter() - t0
         use_threads = 1
-    return (ch * n / dt / 1e6, kind, use_threads,
-            f"{ch} channels x {n} samples casc_2o_iir<{m}> fp64, one object per channel, {use_threads} threads, {dt:.2f} s",
+    return (reps * ch * n / dt / 1e6, kind, use_threads,
+            f"{reps} x {ch} channels x {n} samples casc_2o_iir<{m}> fp64, one object per channel, {use_threads} threads, {dt:.2f} s",
             n / one / 1e6)
 
 
 def run_reference(args, spec, workload_name):
+    """--impl reference: the reference's own CPU implementation (oracle/_ref = the unmodified headers compiled by
+    oracle/Makefile) on this box's host cores, same `config`, `metric`, `unit`; every step is a bounded sample of the
+    workload sized so that W + K steps end within about 90 s.  Rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    for _ in range(max(1, min(args.warmup, 1))):
-        cpu_reference_rate(spec, threads, target_seconds=1.0)
-    rates = []
+    warmup, steps = max(args.warmup, 0), max(args.steps, 1)
+    per_step = min(4.0, max(0.4, 90.0 / (warmup + steps)))
+    for _ in range(warmup):
+        cpu_reference_rate(spec, threads, target_seconds=per_step)
+    rates, last = [], None
     t0 = time.perf_counter()
-    steps = max(1, min(args.steps, 5))
-    last = None
     for _ in range(steps):
-        last = cpu_reference_rate(spec, threads, target_seconds=4.0)
+        last = cpu_reference_rate(spec, threads, target_seconds=per_step)
         rates.append(last[0])
     wall = time.perf_counter() - t0
     value = float(np.mean(rates))
     out = {
         "impl": "reference", "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": args.gpus,
-        "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": wall / steps * 1e3, "higher_is_better": True,
+        "steps": steps, "warmup": warmup, "ms_per_step": wall / steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name, **{k: v for k, v in spec.items() if k != "kind"}},
+        "config": config_of(workload_name, spec),
         "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": last[2], "kind": last[1], "sample": last[3],
                          "single_thread": last[4]},
         "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "details": {"dtype_note": "the reference computes in fp64 whatever the workload's precision; the b200 arm's fp64 "
+                                  "numbers are in its `secondary` entries fft4096_f64 / iir16384_f64"},
     }
     print(json.dumps(out))
 
 
 # --------------------------------------------------------------------------------------------------
+SECONDARY = ("fft4096_f64", "iir16384_f32", "iir16384_f32_scan", "iir4096_f32", "iirscan_f64", "fft65536_f32", "pipeline_cfg5_f32")
+E2E_SECONDARY = ("fft4096_f64", "iir16384_f32")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -503,7 +569,7 @@ def main():
     ap.add_argument("--workload", default="fft4096_f32", choices=sorted(WORKLOADS))
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-secondary", action="store_true", help="default workload only: skip the IIR (config 3) lines measured beside it")
+    ap.add_argument("--no-secondary", action="store_true", help="default workload only: skip the other BASELINE configs measured beside it")
     ap.add_argument("--frames", type=int, default=0, help="override frames (fft) for quick runs")
     args = ap.parse_args()
     spec = dict(WORKLOADS[args.workload])
@@ -521,9 +587,14 @@ def main():
     rank, local, world = dist_setup(args.gpus)
     peak, peak_src = hbm_peak()
 
+    def build(spec):
+        if spec["kind"] == "pipeline":
+            return PipelineWorkload(spec, local, world)
+        return {"fft": FftWorkload, "iir": IirWorkload}[spec["kind"]](spec, local)
+
     def measure(name, spec, steps):
         """W warm-up steps, then `steps` timed steps between barriers; CUDA events on the launching stream, max over ranks."""
-        wl = {"fft": FftWorkload, "iir": IirWorkload, "pipeline": PipelineWorkload}[spec["kind"]](spec, local)
+        wl = build(spec)
         for _ in range(warmup):
             wl.step()
         barrier(world)
@@ -558,12 +629,8 @@ def main():
         }
         return wl, res
 
-    wl, res = measure(args.workload, spec, steps)
-    value, launches = res["value"], wl.launches_per_step()
-
-    # ---- end to end (host buffers through the public API), rank-local, max over ranks
-    e2e = None
-    if not args.no_e2e and spec["kind"] == "fft":
+    def measure_e2e(wl, spec, steps):
+        """The same metric through the public host-buffer API: pinned host memory, H2D + D2H inside the timed region."""
         h2d, d2h = wl.e2e_prepare()
         e2e_steps = max(2, min(steps, 6))
         wl.e2e_step()  # warm-up (allocates staging)
@@ -574,11 +641,23 @@ def main():
             wl.e2e_step()
         barrier(world)
         e2e_s = max_over_ranks(time.perf_counter() - t0, world)
-        e2e_err = wl.e2e_check()
+        err = wl.e2e_check()
+        samples = getattr(wl, "e2e_samples_per_step", wl.samples_per_step)
         wl.e2e_release()
-        e2e = {"value": wl.samples_per_step * e2e_steps * world / e2e_s / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3, "roundtrip_rel_err": e2e_err,
-               "api": "simpledsp_b200.FftPlan.__call__(numpy view of pinned host memory) -> sdsp_b200_fft_exec(PTR_HOST)"}
+        api = ("simpledsp_b200.FftPlan.__call__(numpy view of pinned host memory) -> sdsp_b200_fft_exec(PTR_HOST)" if spec["kind"] == "fft" else
+               "simpledsp_b200.IirBank.process_ptr(pinned host memory) -> sdsp_b200_iir_bank_process(PTR_HOST), staged in chunks of time")
+        return {"value": samples * e2e_steps * world / e2e_s / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3, "samples_per_step": samples,
+                "pcie_GBps_each_way": h2d * e2e_steps / e2e_s / 1e9,
+                ("roundtrip_rel_err" if spec["kind"] == "fft" else "nonfinite"): err, "api": api}
+
+    wl, res = measure(args.workload, spec, steps)
+    value = res["value"]
+
+    # ---- end to end (host buffers through the public API), rank-local, max over ranks
+    e2e = None
+    if not args.no_e2e and spec["kind"] in ("fft", "iir"):
+        e2e = measure_e2e(wl, spec, steps)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -587,34 +666,37 @@ def main():
         r = cpu_reference_rate(spec, os.cpu_count() or 1)
         cpu = {"value": r[0], "unit": "Msamples/s", "cores": r[2], "kind": r[1], "sample": r[3], "single_thread": r[4]}
 
-    # ---- the other half of the metric ("batched FFT & biquad IIR"): BASELINE config 3 measured in the same run
+    # ---- the rest of the metric ("batched FFT & biquad IIR", every BASELINE config) measured in the same run
     secondary = []
     if args.workload == "fft4096_f32" and not args.no_secondary:
         wl.data = None
         del wl
         torch.cuda.empty_cache()
-        # config 3 on the bit-exact streaming path and on the time-split path, and north_star's ">= 4096 channels" point
-        for name in ("iir16384_f32", "iir16384_f32_scan", "iir4096_f32_scan"):
+        for name in SECONDARY:
             sp = dict(WORKLOADS[name])
             w2, r2 = measure(name, sp, 5)
-            secondary.append({"workload": name, "metric": "Msamples/s", "value": r2["value"], "ms_per_step": r2["ms_per_step"],
-                              "steps": 5, "dtype": sp["precision"], "roofline": r2["roofline"], "gpu_launches": r2["gpu_launches"],
-                              "self_check": r2["self_check"], "plan": r2["plan"],
-                              "config": {k: v for k, v in sp.items() if k != "kind"}})
-            w2.data = None
+            entry = {"workload": name, "metric": "Msamples/s", "value": r2["value"], "unit": "Msamples/s", "ms_per_step": r2["ms_per_step"],
+                     "steps": 5, "n_gpus": world, "scaling": "strong" if sp.get("strong") else "weak", "dtype": sp["precision"],
+                     "roofline": r2["roofline"], "gpu_launches": r2["gpu_launches"], "self_check": r2["self_check"], "clocks": r2["clocks"],
+                     "plan": r2["plan"], "config": config_of(name, sp)}
+            if name in E2E_SECONDARY and not args.no_e2e:
+                entry["e2e"] = measure_e2e(w2, sp, 4)
+            secondary.append(entry)
+            for attr in ("data", "signal", "spectra"):
+                if hasattr(w2, attr):
+                    setattr(w2, attr, None)
             del w2
             torch.cuda.empty_cache()
 
     if rank == 0:
         out = {
             "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": steps, "warmup": warmup,
-            "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": spec["precision"], "data": "synthetic",
-            "config": {"workload": args.workload, **{k: v for k, v in spec.items() if k != "kind"},
-                       "per_gpu": True, "in_place": True, "l2": "working set per step is far larger than the 126 MB L2",
-                       "steps_alternate": "forward/reverse" if spec["kind"] == "fft" else "n/a", "plan": res["plan"]},
+            "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "strong" if spec.get("strong") else "weak",
+            "vs_baseline": None, "dtype": spec["precision"], "data": "synthetic", "config": config_of(args.workload, spec),
             "roofline": res["roofline"], "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": res["gpu_launches"], "clocks": res["clocks"],
-            "self_check": res["self_check"], "step_ms": res["step_ms"], "secondary": secondary,
+            "self_check": res["self_check"], "step_ms": res["step_ms"],
+            "details": {"plan": res["plan"], "steps_alternate": "forward/reverse" if spec["kind"] == "fft" else "n/a"},
+            "secondary": secondary,
         }
         print(json.dumps(out))
     if world > 1:

@@ -58,7 +58,11 @@ enum sdsp_b200_filter_type { SDSP_B200_FILTER_NONE = 0, SDSP_B200_LOW_PASS = 1, 
 enum sdsp_b200_numerator { SDSP_B200_NUM_GENERIC = 0, SDSP_B200_NUM_LP = 1, SDSP_B200_NUM_HP = 2, SDSP_B200_NUM_BP = 3 };
 /* how a bank walks the time axis */
 enum sdsp_b200_iir_path {
-    SDSP_B200_IIR_AUTO = 0,       /* pure function of the bank configuration, never of call length alone */
+    SDSP_B200_IIR_AUTO = 0,       /* a sequential kernel (bit-identical however a stream is cut into calls), EXCEPT for banks too small to
+                                     fill the GPU on calls far longer than block streaming uses: ceil(channels/32) <= 2 x SM count (9472
+                                     channels on a B200) AND n_samples >= 65536 AND the time-split path applies -> time-split (reassociates
+                                     within the parity tolerance).  SDSP_B200_IIR_SEQUENTIAL, or SDSP_B200_IIR_AUTO_SPLIT=0 in the
+                                     environment, keeps such calls on the sequential kernels. */
     SDSP_B200_IIR_SEQUENTIAL = 1, /* lane per channel, samples in order; bit-identical however a stream is cut into calls */
     SDSP_B200_IIR_SCAN = 2,       /* time axis split into chunks that carry boundary state (reassociates; fp64 error ~1e-13 of peak):
                                      the time-split kernel when the filter's memory fits a segment, else the look-back scan; where neither

@@ -1,10 +1,16 @@
 // iir_dispatch.cu -- chooses how a bank walks the time axis.
 //
-// The choice is a pure function of the bank configuration and the memory layout of the call
-// (channel count, alignment), never of the call length alone: reference test/testIIR.cpp:61-75 cuts a
-// stream into 32-sample calls and demands bit-identical output, and every sequential kernel evaluates
-// iir_step() in the same order, so SDSP_B200_IIR_AUTO only ever resolves to a sequential kernel unless
-// the caller opts into the (reassociating) scan with SDSP_B200_IIR_SCAN.
+// Reference test/testIIR.cpp:61-75 cuts a stream into 32-sample calls and demands bit-identical output.  Every
+// sequential kernel evaluates iir_step() in the same order, so any mix of them keeps that promise; the time-parallel
+// kernels reassociate (within the parity tolerance, not bit for bit).  SDSP_B200_IIR_AUTO therefore resolves to a
+// sequential kernel EXCEPT where that kernel cannot use the machine and the call is far longer than anything a
+// block-streaming caller issues -- the rule (iir_auto_time_split):
+//     warps = ceil(channels / 32) <= 2 x SMs   (fewer than half the GPU's 4 x SMs warp schedulers would have a warp:
+//                                               9472 channels on a B200; such a bank runs below 45 % of the roofline)
+//     AND  n_samples >= 65536                  (16 x the 4096-sample buffers of the reference's tests and benchmarks)
+//     AND  the time-split path applies         (aligned layout, filter memory << call length, see iir_segment.cu)
+// -> time-split.  Both conditions are properties of the bank and of the call length only; a caller that needs
+// bit-identical re-blocking at such lengths asks for SDSP_B200_IIR_SEQUENTIAL (or sets SDSP_B200_IIR_AUTO_SPLIT=0).
 #include <cstdio>
 #include <cstdlib>
 
@@ -23,6 +29,17 @@ static bool iir_use_tma(const IirBank &b, const void *data, size_t n_samples, si
     if (n_samples < 256)
         return false;
     return iir_tma_applicable(b, data, n_samples, stride);
+}
+
+static bool iir_auto_time_split(IirBank &b, const void *data, size_t n_samples, size_t stride)
+{
+    static const bool enabled = []() {
+        const char *e = getenv("SDSP_B200_IIR_AUTO_SPLIT");
+        return !e || atoi(e) != 0;
+    }();
+    if (!enabled || n_samples < 65536 || (b.n_channels + 31) / 32 > (size_t)2 * b.sm_count)
+        return false;
+    return iir_segment_applicable(b, data, n_samples, stride);
 }
 
 int iir_dispatch(IirBank &b, void *data, size_t n_samples, size_t stride, int path, cudaStream_t stream)
@@ -45,6 +62,8 @@ int iir_dispatch(IirBank &b, void *data, size_t n_samples, size_t stride, int pa
                                                         "vanishes within a segment, and fewer channels than the GPU has lanes");
         return iir_launch_segmented(b, data, n_samples, stride, stream);
     }
+    if (path == SDSP_B200_IIR_AUTO && iir_auto_time_split(b, data, n_samples, stride))
+        return iir_launch_segmented(b, data, n_samples, stride, stream);
     if (iir_use_tma(b, data, n_samples, stride))
         return iir_launch_tma(b, data, n_samples, stride, stream);
     return iir_launch_sequential(b, data, n_samples, stride, stream);
@@ -53,10 +72,16 @@ int iir_dispatch(IirBank &b, void *data, size_t n_samples, size_t stride, int pa
 int iir_describe(IirBank &b, size_t n_samples, size_t stride, int path, char *buf, size_t buf_len)
 {
     // alignment of the (unknown here) base pointer is assumed: describe() reports the kernel a 16-byte aligned call gets
-    const bool timepar = path == SDSP_B200_IIR_SCAN || path == SDSP_B200_IIR_SCAN_LOOKBACK || path == SDSP_B200_IIR_SCAN_SPLIT;
+    bool timepar = path == SDSP_B200_IIR_SCAN || path == SDSP_B200_IIR_SCAN_LOOKBACK || path == SDSP_B200_IIR_SCAN_SPLIT;
+    const bool auto_split = path == SDSP_B200_IIR_AUTO && b.h_gain.size() == b.n_channels && iir_use_tma(b, nullptr, n_samples, stride) &&
+                            iir_auto_time_split(b, nullptr, n_samples, stride);
+    if (auto_split) {
+        timepar = true;
+        path = SDSP_B200_IIR_SCAN;
+    }
     const bool tma = !timepar && iir_use_tma(b, nullptr, n_samples, stride);
     char how[512];
-    snprintf(how, sizeof how, "%s", tma ? "sequential/tma (warp per 32 channels, skewed sections, 6-stage TMA ring per warp)" : "sequential/generic");
+    snprintf(how, sizeof how, "%s", tma ? "sequential/tma (warp per 32 channels, skewed sections, TMA ring per warp through the blocked view)" : "sequential/generic");
     if (timepar) {
         const bool split = path != SDSP_B200_IIR_SCAN_LOOKBACK && b.h_gain.size() == b.n_channels && iir_use_tma(b, nullptr, n_samples, stride) &&
                            iir_segment_describe(b, n_samples, how, sizeof how) == 0;
@@ -70,7 +95,7 @@ int iir_describe(IirBank &b, size_t n_samples, size_t stride, int path, char *bu
     }
     snprintf(buf, buf_len, "iir bank: %zu channels x %d sections %s numerator=%d; n_samples=%zu stride=%zu path=%s -> %s", b.n_channels,
              b.sections, b.precision == SDSP_B200_F32 ? "f32" : "f64", b.numerator, n_samples, stride,
-             timepar ? "time-parallel" : path == SDSP_B200_IIR_SEQUENTIAL ? "sequential" : "auto", how);
+             auto_split ? "auto (few channels, long call)" : timepar ? "time-parallel" : path == SDSP_B200_IIR_SEQUENTIAL ? "sequential" : "auto", how);
     return SDSP_B200_OK;
 }
 

@@ -516,14 +516,14 @@ def test_host_buffers_cut_along_time_match_the_device_resident_call(prec):
     ch, n, pitch = 300, 150_000, 150_016
     bank, x, ref = _bank_case(ch, n, prec, seed=5)
     d = torch.from_numpy(x).cuda()
-    bank.process(d)
+    bank.process(d, path=K.IIR_SEQUENTIAL)
     torch.cuda.synchronize()
     want, st = d.cpu().numpy(), (bank.get_state(), bank.get_state_diff())
     assert peak_rel(want, ref) <= IIR_TOL[prec]
     host = np.zeros((ch, pitch), dtype=dt)
     host[:, :n] = x
     bank.reset_state()
-    bank.process_ptr(host.ctypes.data, n, pitch, K.PTR_HOST, K.IIR_AUTO, None)
+    bank.process_ptr(host.ctypes.data, n, pitch, K.PTR_HOST, K.IIR_SEQUENTIAL, None)
     assert np.array_equal(host[:, :n], want)
     assert not host[:, n:].any()
     assert np.array_equal(bank.get_state(), st[0]) and np.array_equal(bank.get_state_diff(), st[1])
@@ -532,3 +532,31 @@ def test_host_buffers_cut_along_time_match_the_device_resident_call(prec):
     host[:, :n] = x
     bank.process_ptr(host.ctypes.data, n, pitch, K.PTR_HOST, K.IIR_SCAN, None)
     assert peak_rel(host[:, :n], ref) <= IIR_TOL[prec]
+
+
+def test_auto_goes_time_parallel_only_for_small_banks_on_long_calls():
+    """SDSP_B200_IIR_AUTO (include/sdsp_b200.h): sequential kernels -- bit-identical re-blocking -- unless the bank has
+    at most 2 x SMs warps of channels AND the call is at least 65536 samples long; then the time-split path."""
+    torch = pytest.importorskip("torch")
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    small, n_long = 64, 1 << 19
+    bank, x, ref = _bank_case(small, n_long, "f32", seed=21)
+    assert "time-split" in bank.describe(n_long) and "auto" in bank.describe(n_long)
+    assert "sequential" in bank.describe(65535)
+    assert "sequential" in bank.describe(n_long, path=K.IIR_SEQUENTIAL)
+    y = bank.process(torch.from_numpy(x).cuda()).cpu().numpy()
+    assert peak_rel(y, ref) <= IIR_TOL["f32"]
+    # the same stream in 32-sample blocks (reference test/testIIR.cpp:61-75) stays on the sequential kernels and is
+    # bit-identical to one SEQUENTIAL call -- and within the tolerance of what AUTO gave for the long call
+    bank.reset_state()
+    whole = bank.process(torch.from_numpy(x[:, :4096].copy()).cuda(), path=K.IIR_SEQUENTIAL).cpu().numpy()
+    bank.reset_state()
+    blocks = x[:, :4096].copy()
+    for lo in range(0, 4096, 32):
+        part = np.ascontiguousarray(blocks[:, lo:lo + 32])
+        bank.process(part)
+        blocks[:, lo:lo + 32] = part
+    assert np.array_equal(whole, blocks)
+    assert peak_rel(y[:, :4096], whole) <= IIR_TOL["f32"]
+    big = S.IirBank(4, 32 * (2 * sms + 1), K.F32)  # one warp of channels past the threshold
+    assert "sequential" in big.describe(n_long)
