@@ -526,6 +526,30 @@ struct TwiddleSeq {
     }
 };
 
+// The same sixteen factors w_e = w0 * r^e from their first term and ratio alone (no table look-ups: the look-ups of TwiddleSeq
+// are lane-divergent, up to 32 shared-memory wavefronts each -- a third of all the shared-memory wavefronts of the data-mover
+// kernel, profiles/r01_ncu_fft65536_f32_fused_tma_v2.txt).  Eight more complex products per item; the deepest product chain
+// is w0 * r^12 * r^3: w_e is good to ~8 ulp, two orders of magnitude inside the fp32 parity bound.
+template <typename T>
+struct TwiddleGeo {
+    cplx<T> qh[4], ql[3];
+    __device__ __forceinline__ TwiddleGeo(cplx<T> w0, cplx<T> r)
+    {
+        ql[0] = r;
+        ql[1] = cmul(r, r);
+        ql[2] = cmul(ql[1], r);
+        const cplx<T> r4 = cmul(ql[1], ql[1]), r8 = cmul(r4, r4);
+        qh[0] = w0;
+        qh[1] = cmul(w0, r4);
+        qh[2] = cmul(w0, r8);
+        qh[3] = cmul(qh[2], r4);
+    }
+    __device__ __forceinline__ cplx<T> get(int e) const
+    {
+        return (e & 3) == 0 ? qh[e >> 2] : cmul(qh[e >> 2], ql[(e & 3) - 1]);
+    }
+};
+
 template <class Cfg>
 struct LargeStride { // odd frame pitch: the 16 frames a warp touches together land in different banks
     static constexpr int value = Cfg::PADDED_N + 1;
@@ -1093,6 +1117,8 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 3 : 1)
     }
     __syncthreads();
     q = s_ticket;
+    // this thread's share of the inter-transform factors (see fft_fused_tma_kernel: same arithmetic, same bits)
+    const cplx<T> w_a = s_lo[(unsigned)ccol * (unsigned)ct], w_b = s_lo[(unsigned)ccol * (unsigned)CCfg::S];
     for (;;) {
         if (q >= total)
             break;
@@ -1135,7 +1161,8 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 3 : 1)
                 spin_until(row_done + (f - RING), TILES, seen);
             // (the barriers inside the passes sit between thread 0's check above and every thread's stores below)
             fft_kernel_passes<CCfg, T, 256, MINB, 0>(v, xbuf + (size_t)ccol * CPITCH, tw_cols, t);
-            const TwiddleSeq<T> wseq(b * (unsigned)t, b * (unsigned)CCfg::S, s_hi, s_lo);
+            const unsigned xt = (unsigned)COLS * (unsigned)tile * (unsigned)t;
+            const TwiddleGeo<T> wseq(cmul(w_a, cmul(s_hi[xt >> 8], s_lo[xt & 255u])), cmul(w_b, s_hi[tile]));
             cplx<T> *op = sc + b;
 #pragma unroll
             for (int e = 0; e < CCfg::E; e++)
@@ -1395,6 +1422,10 @@ __global__ void __launch_bounds__(288, MINB)
     // ordered by a split barrier (xfree: arrive after the exchange reads, wait before the next item's exchange writes)
     const int lo16 = threadIdx.x & 15, hi16 = threadIdx.x >> 4;
     const int ccol = threadIdx.x % COLS, ct = threadIdx.x / COLS;
+    // inter-transform factor of a column tile: W_N^(b (ct + S e)), b = COLS tile + ccol, = w0 r^e with
+    //   w0 = W^(ccol ct) W^(COLS tile ct)   and   r = W^(S ccol) W^(S COLS tile) = W^(S ccol) W_N1^tile     (S COLS = 256)
+    // the first factor of each is this thread's for the whole launch (indices below COLS S = 256: the W_N^i table)
+    const cplx<T> w_a = s_lo[(unsigned)ccol * (unsigned)ct], w_b = s_lo[(unsigned)ccol * (unsigned)CCfg::S];
     unsigned n_real = 0;
     for (unsigned it = 0;; it++) {
         const int s = it % NST;
@@ -1453,7 +1484,9 @@ __global__ void __launch_bounds__(288, MINB)
                 fft_kernel_passes<CCfg, T, 256, MINB, 0, false, 1>(v, fs, tw_cols, t);
                 mbar_arrive(xfree);
             }
-            const TwiddleSeq<T> wseq(b * (unsigned)t, b * (unsigned)CCfg::S, s_hi, s_lo);
+            // (the per-tile factors are looked up with at most two distinct addresses per warp: broadcasts, no bank conflicts)
+            const unsigned xt = (unsigned)COLS * (unsigned)tile * (unsigned)t;
+            const TwiddleGeo<T> wseq(cmul(w_a, cmul(s_hi[xt >> 8], s_lo[xt & 255u])), cmul(w_b, s_hi[tile]));
             cplx<T> *op = sc + b;
 #pragma unroll
             for (int e = 0; e < CCfg::E; e++)
