@@ -358,6 +358,7 @@ struct FftPlan {
     int ctas_per_sm = 0, sm_count = 0;
     bool double_buffered = false;
     bool staged = false; // next group staged into the exchange buffer by cp.async (fft_cta_alias_kernel)
+    bool two_slot = false; // data-mover kernel with two tile slots that double as exchange buffers (fft_fused_tma2_kernel)
     void *d_tw = nullptr;
     size_t tw_bytes = 0;
     fft_launch_fn launch = nullptr;
@@ -992,6 +993,9 @@ static int setup_cluster64k(FftPlan &p)
 #ifndef SDSP_FUSED_TMA_NST
 #define SDSP_FUSED_TMA_NST 1
 #endif
+#ifndef SDSP_FUSED_TMA_DEFAULT
+#define SDSP_FUSED_TMA_DEFAULT 1
+#endif
 #ifndef SDSP_FUSED_TMA_MINB
 #define SDSP_FUSED_TMA_MINB 3
 #endif
@@ -1533,6 +1537,255 @@ __global__ void __launch_bounds__(288, MINB)
     }
 }
 
+// -------------------------------------------------------------------------------------------------
+// The data-mover kernel with TWO tile slots and no separate exchange buffer: the compute threads exchange IN the slot whose tile
+// they have just taken into registers (each slot is as large as the padded exchange layout), so a second slot costs 3 KB instead
+// of 32 and the kernel keeps three CTAs per SM.  The data mover is then a whole item ahead: ticket, dependency look-up and copy of
+// item i + 1 run while item i is transformed, and the compute threads' wait for their next tile (17 % of the stall samples of the
+// one-slot kernel, profiles/r01_ncu_fft65536_f32_fused_tma_v2.txt) disappears.
+//   full[s]  : the producer's arrive (+ the tile's bytes)            -> the compute threads may read slot s and mailbox s_item[s]
+//   empty[s] : 256 arrivals, each thread after its last exchange read -> the producer may overwrite slot s (generic-proxy accesses
+//              are ordered before the TMA's async-proxy write by fence.proxy.async in every arriving thread)
+// Between a thread's register loads from the slot and the first exchange write into it sits one CTA barrier (all 256 have loaded).
+template <typename T, int N1, int MINB>
+__global__ void __launch_bounds__(288, MINB)
+    fft_fused_tma2_kernel(const __grid_constant__ CUtensorMap in_map, cplx<T> *__restrict__ data, int real_in, cplx<T> *__restrict__ scratch,
+                         const cplx<T> *__restrict__ tw_cols, const cplx<T> *__restrict__ tw, const cplx<T> *__restrict__ tw_hi,
+                         const cplx<T> *__restrict__ tw_lo, unsigned *__restrict__ ticket, unsigned *__restrict__ col_done,
+                         unsigned *__restrict__ row_done, size_t n_frames, int inverse, T scale)
+{
+    using Cfg = FftCfg<256, 16, 16, 16>;          // rows
+    using CCfg = typename FusedCols<N1>::Cfg;     // columns
+    constexpr int BOXES = N1 <= 256 ? 1 : N1 / 256; // a TMA box holds at most 256 rows
+    constexpr int PITCH = LargeStride<Cfg>::value, CPITCH = LargeStride<CCfg>::value;
+    constexpr int N2 = 256, TILES = FusedRing<T, N1>::TILES, COLS = FusedRing<T, N1>::COLS;
+    constexpr int LAG = FusedRing<T, N1>::LAG, RING = FusedRing<T, N1>::RING;
+    constexpr int XBUF = 16 * PITCH > COLS * CPITCH ? 16 * PITCH : COLS * CPITCH;
+    constexpr size_t FRAME = (size_t)N1 * N2;
+    constexpr uint32_t TILE_BYTES = 4096 * sizeof(cplx<T>);
+    constexpr int NST = 2, ND = NST + 1; // completion barriers in rotation
+    constexpr int SLOT = (XBUF + 15) / 16 * 16; // complex elements per slot (128-byte multiple: the second slot stays TMA-aligned)
+    extern __shared__ __align__(128) unsigned char smem_raw128[];
+    cplx<T> *stage0 = reinterpret_cast<cplx<T> *>(smem_raw128);
+    cplx<T> *s_hi = stage0 + (size_t)NST * SLOT, *s_lo = s_hi + N1;
+    // (no static shared memory in this kernel: the dynamic area then starts at the window's aligned base, as the TMA boxes need)
+    uint64_t *full = reinterpret_cast<uint64_t *>(s_lo + 256), *empty = full + NST, *done_bar = empty + NST;
+    unsigned *s_item = reinterpret_cast<unsigned *>(done_bar + ND);
+    for (int i = threadIdx.x; i < N1; i += 288)
+        s_hi[i] = tw_hi[i];
+    if (threadIdx.x < 256)
+        s_lo[threadIdx.x] = tw_lo[threadIdx.x];
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NST; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 256);
+        }
+        for (int s = 0; s < ND; s++)
+            mbar_init(&done_bar[s], 256);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    const size_t total = ((size_t)LAG + 2 * n_frames) * TILES;
+
+    if (threadIdx.x >= 256) { // ---- the data mover; it also counts finished tiles, so no compute warp ever waits on a fence
+        if (threadIdx.x != 256)
+            return;
+        // Finished tiles are counted as soon as their barrier completes -- in particular from inside every wait below: a tile that is
+        // done but not yet counted may be exactly what another CTA's (or this CTA's next) item is waiting for.
+        unsigned *pend[ND];
+        for (int i = 0; i < ND; i++)
+            pend[i] = nullptr;
+        unsigned it = 0, next_pub = 0; // items issued so far = it; items counted so far = next_pub
+        auto count_tile = [&](unsigned j) {
+            unsigned *d = pend[j % ND];
+            if (d)
+                asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(d) : "memory");
+        };
+        auto try_publish = [&]() {
+            while (next_pub < it && mbar_test(&done_bar[next_pub % ND], (next_pub / ND) & 1)) {
+                count_tile(next_pub);
+                next_pub++;
+            }
+        };
+        auto wait_dep = [&](const unsigned *ctr) {
+            while (ld_acquire_gpu(ctr) < (unsigned)TILES) {
+                try_publish();
+                __nanosleep(32);
+            }
+        };
+        // When to draw the next ticket: as late as possible -- once the stage is free.  A ticket held without being worked on delays
+        // every item that depends on it: drawing a whole item early, or when the compute threads pass the exchange of the item
+        // before, were both measured slower although they take the ticket's round trip off the path (profiles/r01_fft65536_variants.txt).
+        for (;; it++) {
+            const int s = it % NST;
+            if (it >= (unsigned)NST) {
+                // (counting here, promptly, matters: leaving it until the next copy is out was measured 3 % slower -- other CTAs'
+                // row tiles follow their frame's column tiles by barely more than an item's latency)
+                while (!SDSP_FUSED_POLL(&empty[s], ((it / NST) - 1) & 1)) // until item it - NST has finished exchanging in the slot
+                    try_publish();
+                while (next_pub + ND <= it) { // this item's completion barrier is free again once item it - ND is counted
+                    mbar_wait(&done_bar[next_pub % ND], (next_pub / ND) & 1);
+                    count_tile(next_pub);
+                    next_pub++;
+                }
+            }
+            const size_t q = atomicAdd(ticket, 1u);
+            bool cols = false;
+            size_t f = n_frames;
+            int tile = 0;
+            if (q < total)
+                fused_decode<LAG, TILES>(q, cols, f, tile);
+            const bool real = q < total && f < n_frames;
+            if (real && !cols)
+                wait_dep(col_done + f); // the frame's column tiles are all in the ring
+            s_item[s] = q < total ? (unsigned)q : 0xffffffffu;
+            if (q >= total) {
+                mbar_arrive(&full[s]);
+                break;
+            }
+            cplx<T> *dst = stage0 + (size_t)s * SLOT;
+            unsigned *d = nullptr;
+            if (!real) {
+                mbar_arrive(&full[s]); // empty slot
+            } else if (cols) {
+                // the dependency of a column tile guards the compute threads' stores into the ring, not this copy: start the copy,
+                // then look at the counter, and only then hand the stage over
+                mbar_expect_tx_only(&full[s], real_in ? TILE_BYTES / 2 : TILE_BYTES);
+#pragma unroll
+                for (int bx = 0; bx < BOXES; bx++) {
+                    void *bd = real_in ? static_cast<void *>(reinterpret_cast<T *>(dst) + (size_t)bx * 256 * COLS)
+                                       : static_cast<void *>(dst + (size_t)bx * 256 * COLS);
+                    tma_load_3d(bd, &in_map, real_in ? COLS * tile : 2 * COLS * tile, 256 * bx, (int)f, &full[s]);
+                }
+                if (f >= (size_t)RING)
+                    wait_dep(row_done + (f - RING)); // the ring slot's previous tenant has been read out
+                mbar_arrive(&full[s]);
+                d = col_done + f;
+            } else {
+                asm volatile("fence.proxy.async.global;" ::: "memory");
+                mbar_expect_tx(&full[s], TILE_BYTES);
+                bulk_load_1d(dst, scratch + (f % RING) * FRAME + (size_t)(16 * tile) * N2, TILE_BYTES, &full[s]);
+                d = row_done + f;
+            }
+            pend[it % ND] = d;
+        }
+        for (; next_pub < it; next_pub++) { // the tail: the last items are still to be counted
+            mbar_wait(&done_bar[next_pub % ND], (next_pub / ND) & 1);
+            count_tile(next_pub);
+        }
+        return;
+    }
+
+    // ---- the 256 compute threads: two CTA-wide barriers per item (slot taken into registers; the exchange)
+    const int lo16 = threadIdx.x & 15, hi16 = threadIdx.x >> 4;
+    const int ccol = threadIdx.x % COLS, ct = threadIdx.x / COLS;
+    // inter-transform factor of a column tile: W_N^(b (ct + S e)), b = COLS tile + ccol, = w0 r^e with
+    //   w0 = W^(ccol ct) W^(COLS tile ct)   and   r = W^(S ccol) W^(S COLS tile) = W^(S ccol) W_N1^tile     (S COLS = 256)
+    // the first factor of each is this thread's for the whole launch (indices below COLS S = 256: the W_N^i table)
+    const cplx<T> w_a = s_lo[(unsigned)ccol * (unsigned)ct], w_b = s_lo[(unsigned)ccol * (unsigned)CCfg::S];
+    for (unsigned it = 0;; it++) {
+        const int s = it % NST;
+        mbar_wait(&full[s], (it / NST) & 1);
+        const unsigned q = s_item[s];
+        if (q == 0xffffffffu)
+            break;
+        bool cols;
+        size_t f;
+        int tile;
+        fused_decode<LAG, TILES>(q, cols, f, tile);
+        cplx<T> *st = stage0 + (size_t)s * SLOT, *xbuf = st;
+        cplx<T> *sc = scratch + (f % RING) * (FRAME);
+        cplx<T> v[Cfg::E];
+        if (f >= n_frames) {
+            mbar_arrive(&empty[s]);
+            mbar_arrive(&done_bar[it % ND]);
+            continue;
+        }
+        if (cols) {
+            const int t = ct;
+            const unsigned b = (unsigned)COLS * (unsigned)tile + (unsigned)ccol;
+            if (real_in) {
+                const T *rs = reinterpret_cast<const T *>(st);
+#pragma unroll
+                for (int e = 0; e < CCfg::E; e++)
+                    v[e] = cplx<T>{ rs[(t + CCfg::S * e) * COLS + ccol], (T)0 };
+            } else {
+#pragma unroll
+                for (int e = 0; e < CCfg::E; e++)
+                    v[e] = st[(t + CCfg::S * e) * COLS + ccol];
+            }
+            cta_sync<1, 256>(); // every thread has its points: the slot becomes the exchange buffer
+            if (inverse) {
+#pragma unroll
+                for (int e = 0; e < CCfg::E; e++)
+                    v[e] = cplx<T>{ v[e].y, v[e].x };
+            }
+            cplx<T> *fs = xbuf + (size_t)ccol * CPITCH;
+            if constexpr (CCfg::NPASS == 2) {
+                fft_pass<CCfg, 0, T>(v, t, tw_cols);
+#pragma unroll
+                for (int e = 0; e < CCfg::E; e++)
+                    fs[fft_out_phys<CCfg, 0>(t, e)] = v[e];
+                cta_sync<1, 256>();
+#pragma unroll
+                for (int e = 0; e < CCfg::E; e++)
+                    v[e] = fs[fft_read_phys<CCfg>(t, e)];
+                fence_proxy_async();
+                mbar_arrive(&empty[s]);
+                fft_pass<CCfg, 1, T>(v, t, tw_cols);
+            } else { // three passes: two exchanges with the usual barriers between them
+                fft_kernel_passes<CCfg, T, 256, MINB, 0, false, 1>(v, fs, tw_cols, t);
+                fence_proxy_async();
+                mbar_arrive(&empty[s]);
+            }
+            // (the per-tile factors are looked up with at most two distinct addresses per warp: broadcasts, no bank conflicts)
+            const unsigned xt = (unsigned)COLS * (unsigned)tile * (unsigned)t;
+            const TwiddleGeo<T> wseq(cmul(w_a, cmul(s_hi[xt >> 8], s_lo[xt & 255u])), cmul(w_b, s_hi[tile]));
+            cplx<T> *op = sc + b;
+#pragma unroll
+            for (int e = 0; e < CCfg::E; e++)
+                op[(size_t)(t + CCfg::S * e) * N2] = cmul(v[e], wseq.get(e));
+        } else {
+            const int t = lo16, row = hi16;
+            const cplx<T> *gp = st + row * N2 + t;
+#pragma unroll
+            for (int e = 0; e < Cfg::E; e++)
+                v[e] = gp[Cfg::S * e];
+            cta_sync<1, 256>(); // every thread has its points: the slot becomes the exchange buffer
+            // the tile's 32 KB of the ring are dead now (256 lines of 128 bytes, one per thread): drop them from L2 instead of
+            // letting them be written back to HBM when they are evicted -- that is what makes a 48 MB ring affordable
+            // (profiles/r01_fft65536_variants.txt)
+            if constexpr (sizeof(cplx<T>) == 8)
+                asm volatile("discard.global.L2 [%0], 128;" ::"l"(sc + (size_t)(16 * tile) * N2 + (size_t)threadIdx.x * 16) : "memory");
+            fft_pass<Cfg, 0, T>(v, t, tw);
+            cplx<T> *fs = xbuf + (size_t)row * PITCH;
+#pragma unroll
+            for (int e = 0; e < Cfg::E; e++)
+                fs[fft_out_phys<Cfg, 0>(t, e)] = v[e];
+            cta_sync<1, 256>();
+            const int row2 = lo16, t2 = hi16;
+            const cplx<T> *rs = xbuf + (size_t)row2 * PITCH;
+#pragma unroll
+            for (int e = 0; e < Cfg::E; e++)
+                v[e] = rs[fft_read_phys<Cfg>(t2, e)];
+            fence_proxy_async();
+            mbar_arrive(&empty[s]);
+            fft_pass<Cfg, 1, T>(v, t2, tw);
+            if (inverse) {
+#pragma unroll
+                for (int e = 0; e < Cfg::E; e++)
+                    v[e] = cplx<T>{ v[e].y * scale, v[e].x * scale };
+            }
+            cplx<T> *op = data + f * (FRAME) + 16 * tile + row2;
+#pragma unroll
+            for (int e = 0; e < Cfg::E; e++)
+                st_stream(op + (size_t)(t2 + Cfg::S * e) * N1, v[e]);
+        }
+        mbar_arrive(&done_bar[it % ND]); // (release: this thread's stores are ordered before the data mover's count)
+    }
+}
+
+
 template <typename T, int N1>
 struct FusedTmaCfg {
     static constexpr int NST = SDSP_FUSED_TMA_NST, MINB = SDSP_FUSED_TMA_MINB;
@@ -1584,20 +1837,28 @@ static int launch_fused_tma(const FftPlan &p, void *data, const void *real_in, s
     unsigned *a_col = ctr + 1, *a_row = ctr + 1 + n_frames;
     const int a_real = real_in ? 1 : 0, a_inv = p.direction == SDSP_B200_REVERSE ? 1 : 0;
     const T a_scale = (T)(1.0 / ((double)N1 * 256.0));
-    fft_fused_tma_kernel<T, N1, NST, MINB><<<(unsigned)grid, 288, p.smem_bytes, stream>>>(map, a_data, a_real, a_scratch, a_twc, a_twr, a_hi, a_lo, ctr,
+    if (p.two_slot)
+        fft_fused_tma2_kernel<T, N1, MINB><<<(unsigned)grid, 288, p.smem_bytes, stream>>>(map, a_data, a_real, a_scratch, a_twc, a_twr, a_hi, a_lo, ctr,
                                                                                          a_col, a_row, n_frames, a_inv, a_scale);
+    else
+        fft_fused_tma_kernel<T, N1, NST, MINB><<<(unsigned)grid, 288, p.smem_bytes, stream>>>(map, a_data, a_real, a_scratch, a_twc, a_twr, a_hi, a_lo,
+                                                                                             ctr, a_col, a_row, n_frames, a_inv, a_scale);
     SDSP_CUDA(cudaGetLastError());
     return SDSP_B200_OK;
 }
 
-static bool fused_tma_wanted()
+static int fused_tma_mode() // SDSP_B200_FFT_FUSED_TMA = 0: compute threads load their own tiles; 1: data mover, one slot; 2: two slots
 {
     static int w = -1;
     if (w < 0) {
-        const char *e = getenv("SDSP_B200_FFT_FUSED_TMA"); // =0: the variant whose compute threads load their own tiles
-        w = ((!e || atoi(e) > 0) && get_encode_fn()) ? 1 : 0;
+        const char *e = getenv("SDSP_B200_FFT_FUSED_TMA");
+        w = !get_encode_fn() ? 0 : e ? atoi(e) : SDSP_FUSED_TMA_DEFAULT;
     }
-    return w == 1;
+    return w;
+}
+static bool fused_tma_wanted()
+{
+    return fused_tma_mode() > 0;
 }
 
 template <typename T, int N1>
@@ -1670,6 +1931,25 @@ static int setup_fused(FftPlan &p)
                 p.threads = 288;
                 p.staged = true;
                 p.launch = &launch_fused_tma<T, N1>;
+            }
+            // two slots that double as exchange buffers: measured +1.5 % (2^16) / +3.6 % (2^15), -1.7 % at 2^17 (profiles/r02_fft_fused_variants.txt):
+            // the default up to N1 = 256; SDSP_B200_FFT_FUSED_TMA=1 / 2 pins the one- / two-slot kernel
+            const int mode = fused_tma_mode();
+            if (mode == 2 || (mode == SDSP_FUSED_TMA_DEFAULT && !getenv("SDSP_B200_FFT_FUSED_TMA") && N1 <= 256)) {
+                auto tk2 = fft_fused_tma2_kernel<T, N1, MINB>;
+                const size_t slot = (XBUF + 15) / 16 * 16;
+                const size_t smem2 = (2 * slot + N1 + 256) * sizeof(cplx<T>) + 128;
+                SDSP_CUDA(cudaFuncSetAttribute(tk2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+                int occ2 = 0;
+                SDSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, tk2, 288, smem2));
+                if (occ2 >= 1) {
+                    p.smem_bytes = smem2;
+                    p.ctas_per_sm = occ2;
+                    p.threads = 288;
+                    p.staged = true;
+                    p.two_slot = true;
+                    p.launch = &launch_fused_tma<T, N1>;
+                }
             }
         }
     }

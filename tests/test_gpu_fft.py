@@ -262,9 +262,10 @@ np.save(sys.argv[3], x.cpu().numpy())
 
 @pytest.mark.parametrize("n", [32768, 65536])
 def test_fused_queue_with_and_without_the_data_mover_warp_agree(n, tmp_path):
-    """fp32 frames of 2^15 / 2^16 points run the work queue fed by a TMA data-mover warp by default; SDSP_B200_FFT_FUSED_TMA=0
-    selects the variant whose compute threads load their own tiles.  Same arithmetic in the same order: the two must give the
-    same bits (each in its own process: the choice is read once per process)."""
+    """fp32 frames of 2^15 / 2^16 points run the work queue fed by a TMA data-mover warp (two tile slots that double as exchange
+    buffers) by default; SDSP_B200_FFT_FUSED_TMA=1 selects the one-slot data-mover kernel, =0 the variant whose compute threads
+    load their own tiles.  Same arithmetic in the same order: all three must give the same bits (each in its own process: the
+    choice is read once per process)."""
     import os
     import subprocess
     import sys
@@ -272,14 +273,14 @@ def test_fused_queue_with_and_without_the_data_mover_warp_agree(n, tmp_path):
     from tests.util import ROOT
 
     outs = {}
-    for flag in ("1", "0"):
+    for flag in ("2", "1", "0"):
         path = str(tmp_path / f"out_{flag}.npy")
         env = dict(os.environ, SDSP_B200_FFT_FUSED_TMA=flag, PYTHONPATH=ROOT)
         r = subprocess.run([sys.executable, "-c", _OTHER_QUEUE_SNIPPET, str(n), "97", path], env=env, capture_output=True, text=True, timeout=300, cwd=ROOT)
         assert r.returncode == 0, r.stderr[-2000:]
-        assert ("data-mover" in r.stdout) == (flag == "1"), r.stdout
+        assert ("data-mover" in r.stdout) == (flag != "0"), r.stdout
         outs[flag] = np.load(path)
-    assert np.array_equal(outs["1"], outs["0"])
+    assert np.array_equal(outs["1"], outs["0"]) and np.array_equal(outs["2"], outs["0"])
     g = np.random.default_rng(0).integers(0, 97, 3)
     # and against the oracle, for a few frames, using the same generator seed as the snippet
     torch = pytest.importorskip("torch")
