@@ -287,215 +287,6 @@ static int launch_tma_cfg(const IirBank &b, void *data, size_t n_samples, size_t
     return SDSP_B200_OK;
 }
 
-// =================================================================================================
-// Section-pipelined variant of the plain path (an experiment kept as an opt-in, SDSP_B200_IIR_PIPE): M/2 compute warps
-// share one group of 32 channels and one ring; warp w runs sections (2w, 2w+1) over a stage in place and hands the
-// stage to warp w+1 through an mbarrier; a data-mover warp loads, stores and refills.  Every (section, sample) update
-// is the same iir_section() call on the same operands, so the output is bit-identical to the single-warp kernel.
-// The idea was to double the warps of a 16384-channel bank (512 warps for 592 schedulers).  The measurement said the
-// single-warp kernel was bound by the LATENCY of its loop-carried recurrence (3 dependent packed operations per
-// sample with the evaluation order then in use), which splitting by sections does not shorten: same 25 ms
-// (profiles/r01_ncu_iir16384_f32_pipe_v1.txt).  Re-ordering the section update into a pure FMA chain -- one FMA on
-// the recurrence -- is what moved the number (82 % -> 85 %), and with it this variant is the slower one.
-template <typename T, int M, int KIND, int SUB, int CSUB, int NST>
-__global__ void __launch_bounds__((M / 2 + 1) * 32)
-    iir_tma_pipe_kernel(const __grid_constant__ CUtensorMap map, int n_samples, const T *__restrict__ coef, T *__restrict__ state,
-                        size_t n_channels)
-{
-    constexpr int W = M / 2; // compute warps = pipeline depth; warp W moves the data (one lane)
-    constexpr int TSB = 128 / (int)sizeof(T);
-    constexpr int TS = TSB * SUB;
-    constexpr int CTS = TSB * CSUB;
-    constexpr int RG = 8;
-    constexpr int BOX_BYTES = 32 * 128;
-    constexpr int STAGE_BYTES = BOX_BYTES * SUB;
-    constexpr int VN = Vec16<T>::N;
-    using V = typename Vec16<T>::type;
-    static_assert(M % 2 == 0 && M >= 4 && SUB % CSUB == 0 && NST >= 4, "two sections per warp, at least two compute warps");
-
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    __shared__ uint64_t full_bar[NST];    // stage loaded (TMA transaction count)          -> compute warp 0
-    __shared__ uint64_t done_bar[W][NST]; // compute warp w has finished the stage         -> warp w+1 (w = W-1: the data mover)
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const size_t ch0 = (size_t)blockIdx.x * 32;
-    const size_t ch = ch0 + lane;
-    const bool active = ch < n_channels && warp < W;
-    unsigned char *ring = smem_raw;
-
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int s = 0; s < NST; s++) {
-            mbar_init(&full_bar[s], 1);
-#pragma unroll
-            for (int w = 0; w < W; w++)
-                mbar_init(&done_bar[w][s], 1);
-        }
-        fence_mbar_init();
-        fence_proxy_async();
-    }
-
-    // this warp's two sections of this lane's channel: a 2-section cascade whose "input" is the previous warp's output
-    IirCoef<T, 2> c;
-    IirState<T, 2> st;
-    const int j0 = 2 * (warp < W ? warp : 0);
-    if (active) {
-        c.gain = warp == 0 ? coef[ch] : (T)1; // x * 1 is exact: the stream passes from warp to warp unchanged
-#pragma unroll
-        for (int j = 0; j < 2; j++) {
-            c.b1[j] = coef[(size_t)(1 + j0 + j) * n_channels + ch];
-            c.b2[j] = coef[(size_t)(1 + M + j0 + j) * n_channels + ch];
-            c.fa[j] = coef[(size_t)(1 + 2 * M + j0 + j) * n_channels + ch];
-            c.fb[j] = coef[(size_t)(1 + 3 * M + j0 + j) * n_channels + ch];
-        }
-#pragma unroll
-        for (int r = 0; r <= 2; r++) { // rows j0 .. j0+2 of the history: input of section j0, outputs of j0 and j0+1
-            st.h[r][0] = state[(size_t)(2 * (j0 + r)) * n_channels + ch];
-            st.h[r][1] = state[(size_t)(2 * (j0 + r) + 1) * n_channels + ch];
-        }
-#pragma unroll
-        for (int j = 0; j < 2; j++)
-            st.d[j] = IirDelta<T>::value ? state[(size_t)(2 * (M + 1) + j0 + j) * n_channels + ch] : (T)0;
-    } else {
-        iir_zero_coef<T, 2>(c);
-        iir_zero_state<T, 2>(st);
-    }
-    // the only block-wide barrier: mbarriers are initialised, and every warp has read its share of the bank's history
-    // before a faster neighbour can write its own back at the end of a short stream
-    __syncthreads();
-
-    const int n_stages = (n_samples + TS - 1) / TS;
-    const int y0 = (int)ch0;
-
-    if (warp == W) {
-        // ---- data mover: loads NST stages ahead, stores what the last compute warp hands over, refills what has been read out
-        if (lane != 0)
-            return;
-        auto issue_load = [&](int k) {
-            uint64_t *b = &full_bar[k % NST];
-            unsigned char *dst = ring + (size_t)(k % NST) * STAGE_BYTES;
-            mbar_expect_tx(b, STAGE_BYTES);
-#pragma unroll
-            for (int g = 0; g < 32 / RG; g++)
-#pragma unroll
-                for (int u = 0; u < SUB; u++)
-                    tma_load_2d(dst + u * BOX_BYTES + g * RG * 128, &map, k * TS + u * TSB, y0 + g * RG, b);
-        };
-        for (int k = 0; k < NST && k < n_stages; k++)
-            issue_load(k);
-        for (int k = 0; k < n_stages; k++) {
-            const int slot = k % NST;
-            mbar_wait(&done_bar[W - 1][slot], (uint32_t)((k / NST) & 1));
-            unsigned char *buf = ring + (size_t)slot * STAGE_BYTES;
-#pragma unroll
-            for (int g = 0; g < 32 / RG; g++)
-#pragma unroll
-                for (int u = 0; u < SUB; u++)
-                    tma_store_2d(&map, k * TS + u * TSB, y0 + g * RG, buf + u * BOX_BYTES + g * RG * 128);
-            tma_commit();
-            // the buffer stored one stage ago has been read out by now (or nearly): refill it
-            if (k >= 1 && k - 1 + NST < n_stages) {
-                tma_wait_read<1>();
-                issue_load(k - 1 + NST);
-            }
-        }
-        tma_wait_all();
-        return;
-    }
-
-    const uint32_t row_off = (uint32_t)lane * 128u;
-    const uint32_t sw = (uint32_t)(lane & 7);
-    for (int k = 0; k < n_stages; k++) {
-        const int slot = k % NST;
-        const uint32_t parity = (uint32_t)((k / NST) & 1);
-        if (warp == 0)
-            mbar_wait(&full_bar[slot], parity);
-        else
-            mbar_wait(&done_bar[warp - 1][slot], parity);
-        unsigned char *buf = ring + (size_t)slot * STAGE_BYTES;
-        const int remaining = n_samples - k * TS;
-#pragma unroll 1
-        for (int ct = 0; ct < SUB / CSUB; ct++) {
-            unsigned char *cbuf = buf + ct * CSUB * BOX_BYTES;
-            const int rem = remaining - ct * CTS;
-            if (rem >= CTS) {
-                V vin, vout;
-                iir_tile_dispatch<T, 2, KIND, CTS>(
-                    c, st,
-                    [&](int i) -> T {
-                        if (i % VN == 0) {
-                            const int box = i / TSB, chunk = (i % TSB) / VN;
-                            vin = *reinterpret_cast<const V *>(cbuf + box * BOX_BYTES + row_off + (((uint32_t)chunk ^ sw) << 4));
-                        }
-                        return vget(vin, i % VN);
-                    },
-                    [&](int i, T y) {
-                        vset(vout, i % VN, y);
-                        if (i % VN == VN - 1) {
-                            const int box = i / TSB, chunk = (i % TSB) / VN;
-                            *reinterpret_cast<V *>(cbuf + box * BOX_BYTES + row_off + (((uint32_t)chunk ^ sw) << 4)) = vout;
-                        }
-                    });
-            } else if (rem > 0) {
-                for (int i = 0; i < rem; i++) {
-                    const int box = i / TSB, chunk = (i % TSB) / VN, e = i % VN;
-                    T *p = reinterpret_cast<T *>(cbuf + box * BOX_BYTES + row_off + (((uint32_t)chunk ^ sw) << 4)) + e;
-                    *p = iir_step<T, 2, KIND>(*p, c, st);
-                }
-            }
-        }
-        if (warp == W - 1)
-            fence_proxy_async(); // the data mover's TMA store reads these writes through the async proxy
-        __syncwarp();            // every lane's stores of this stage precede the hand-over
-        if (lane == 0)
-            mbar_arrive(&done_bar[warp][slot]);
-    }
-    if (active) { // warp w owns history rows j0+1, j0+2 (its sections' outputs); warp 0 also row 0 (the scaled input)
-#pragma unroll
-        for (int r = 0; r <= 2; r++) {
-            if (r > 0 || warp == 0) {
-                state[(size_t)(2 * (j0 + r)) * n_channels + ch] = st.h[r][0];
-                state[(size_t)(2 * (j0 + r) + 1) * n_channels + ch] = st.h[r][1];
-            }
-        }
-        if (IirDelta<T>::value) {
-#pragma unroll
-            for (int j = 0; j < 2; j++)
-                state[(size_t)(2 * (M + 1) + j0 + j) * n_channels + ch] = st.d[j];
-        }
-    }
-}
-
-template <typename T, int M, int KIND, int SUB, int CSUB, int NST>
-static int launch_tma_pipe(const IirBank &b, void *data, size_t n_samples, size_t stride, cudaStream_t stream)
-{
-    constexpr int TSB = 128 / (int)sizeof(T);
-    CUtensorMap map;
-    const cuuint64_t gdim[2] = { (cuuint64_t)n_samples, (cuuint64_t)b.n_channels };
-    const cuuint64_t pitch = b.n_channels > 1 ? (cuuint64_t)stride * sizeof(T) : (((cuuint64_t)n_samples * sizeof(T) + 15) / 16) * 16;
-    const cuuint64_t gstride[1] = { pitch };
-    const cuuint32_t box[2] = { (cuuint32_t)TSB, 8 };
-    const cuuint32_t estr[2] = { 1, 1 };
-    CUresult r = get_encode_fn()(&map, sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, data, gdim,
-                                 gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS)
-        return set_error(SDSP_B200_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d (n_samples=%zu channels=%zu pitch=%llu)", (int)r, n_samples,
-                         b.n_channels, (unsigned long long)pitch);
-    auto kern = iir_tma_pipe_kernel<T, M, KIND, SUB, CSUB, NST>;
-    constexpr size_t smem = (size_t)NST * SUB * 32 * 128;
-    static bool configured_dev[64] = {};
-    bool &configured = configured_dev[b.device & 63]; // (the attribute is per device; a process may hold banks on several)
-    if (!configured) {
-        SDSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
-    const unsigned grid = (unsigned)((b.n_channels + 31) / 32);
-    kern<<<grid, (M / 2 + 1) * 32, smem, stream>>>(map, (int)n_samples, static_cast<const T *>(b.d_coef), static_cast<T *>(b.d_state), b.n_channels);
-    SDSP_CUDA(cudaGetLastError());
-    return SDSP_B200_OK;
-}
-
 // ---- segment rows (time-split path): `segs` segments of seg_len samples per channel, each a row of its own
 static int rows_tune()
 {
@@ -572,18 +363,21 @@ static int launch_rows_ring(const IirBank &b, void *data, size_t seg_len, size_t
     if constexpr (M == 4 && KIND == NUM_GENERIC) { // alternatives exist for the headline instantiations only
         switch (rows_tune()) { //                                         SUB CSUB NST PF   ring per warp
         case 1: return launch_rows_cfg<T, M, KIND, MODE, 2, 2, 4, 2>(b, data, seg_len, segs, stride, row_state, n_samples, stream, slots); // 32 KB
+        case 2: return launch_rows_cfg<T, M, KIND, MODE, 4, 2, 2, 1>(b, data, seg_len, segs, stride, row_state, n_samples, stream, slots); // 32 KB
+        case 3: return launch_rows_cfg<T, M, KIND, MODE, 4, 2, 3, 1>(b, data, seg_len, segs, stride, row_state, n_samples, stream, slots); // 48 KB
+        case 4: return launch_rows_cfg<T, M, KIND, MODE, 4, 2, 3, 2>(b, data, seg_len, segs, stride, row_state, n_samples, stream, slots); // 48 KB
         case 5: return launch_rows_cfg<T, M, KIND, MODE, 2, 2, 6, 3>(b, data, seg_len, segs, stride, row_state, n_samples, stream, slots); // 48 KB
         case 6: return launch_rows_cfg<T, M, KIND, MODE, 2, 2, 2, 1>(b, data, seg_len, segs, stride, row_state, n_samples, stream, slots); // 16 KB
         case 7: return launch_rows_cfg<T, M, KIND, MODE, 2, 2, 3, 1>(b, data, seg_len, segs, stride, row_state, n_samples, stream, slots); // 24 KB
         default: break;
         }
     }
-    // defaults (ring sweeps: profiles/r01_iir_split_ring_sweep.txt): a single warp is issue/latency-bound, the memory system is
-    // filled by having many on an SM -- fp32: two 8 KB stages per warp (12 row-warps per SM), fp64: three (8 per SM)
+    // defaults (ring sweeps with the blocked view: profiles/r02_iir_rows_ring_sweep.txt; round 1, before it: r01_iir_split_ring_sweep.txt):
+    // fp32: three 8 KB stages per row-warp (9 row-warps per SM), fp64: six with three in flight (4 per SM)
     if constexpr (sizeof(T) == 4)
-        return launch_rows_cfg<T, M, KIND, MODE, 2, 2, 2, 1>(b, data, seg_len, segs, stride, row_state, n_samples, stream, slots); // 16 KB
-    else
         return launch_rows_cfg<T, M, KIND, MODE, 2, 2, 3, 1>(b, data, seg_len, segs, stride, row_state, n_samples, stream, slots); // 24 KB
+    else
+        return launch_rows_cfg<T, M, KIND, MODE, 2, 2, 6, 3>(b, data, seg_len, segs, stride, row_state, n_samples, stream, slots); // 48 KB
 }
 
 template <typename T, int M, int KIND>
@@ -624,16 +418,8 @@ template <typename T, int M, int KIND>
 static int launch_tma(const IirBank &b, void *data, size_t n_samples, size_t stride, cudaStream_t stream)
 {
     const int promo = 128; // TMA L2 promotion bytes (64 / 256 measured equal, profiles/r01_iir_tma_config_sweep.txt)
-    if constexpr (M >= 4) { // SDSP_B200_IIR_PIPE=1: the section-pipelined kernel (bit-identical output).  Measured slower than the
-                            // single-warp kernel once the recurrence was shortened to one FMA (profiles/r01_iir_pipe_vs_single.txt): off.
-        static int pipe = -1;
-        if (pipe < 0) {
-            const char *e = getenv("SDSP_B200_IIR_PIPE");
-            pipe = e ? atoi(e) : 0;
-        }
-        if (pipe == 1)
-            return launch_tma_pipe<T, M, KIND, 2, 2, 6>(b, data, n_samples, stride, stream);
-    }
+    // (A section-pipelined variant -- M/2 compute warps per 32 channels handing stages to one another -- was measured in
+    // round 1 and dropped: the bound is the issue rate of the recurrence, not its length; profiles/r01_iir_pipe_vs_single.txt.)
     // single-warp CTAs, 8-row boxes; ring of three 128-byte x 4 stages, two in flight (profiles/r02_iir_tma_ring_sweep.txt;
     // round 1's sweep, before the blocked view: profiles/r01_iir_tma_config_sweep.txt).  fp32: scalar arithmetic while the bank
     // leaves schedulers to spare, packed once every SM holds its four warps; SDSP_B200_IIR_PACK=0|1 pins the choice
