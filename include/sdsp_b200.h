@@ -89,6 +89,13 @@ int sdsp_b200_device_free(void *ptr, int device);
 int sdsp_b200_memcpy(void *dst, const void *src, size_t bytes, int device); /* any direction, synchronous */
 int sdsp_b200_device_synchronize(int device);
 
+/* Multi-GPU sharding (host only, no device needed).  Frames and channels are independent objects in the reference (one
+ * complex_array per call, fft.h:258-360; one casc_2o_iir object per channel, casc_2o_iir.h:8-20), so device `rank` of `world`
+ * owns the contiguous block [*first, *first + *count) of `total` units -- the first total % world ranks hold one unit more --
+ * together with its share of the coefficient / history bank; there is no collective on the data path.  A process drives
+ * several GPUs by creating one plan / bank per device (the `device` argument) over these ranges. */
+int sdsp_b200_shard_range(size_t total, int rank, int world, size_t *first, size_t *count);
+
 /* ---------------------------------------------------------------- FFT
  * Replaces sdsp::fft_radix2<T,N>(complex_array<N>&) (reference include/sdsp/fft.h:258-299) and
  * sdsp::fft_radix4<T,N>(complex_array<N>&) (:301-360), batched over n_frames frames.

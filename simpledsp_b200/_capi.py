@@ -51,6 +51,7 @@ SIGNATURES = {
     "sdsp_b200_iir_bank_set_state": (C.c_int, [_vp, _sz, _sz, _dp]),
     "sdsp_b200_iir_bank_get_state": (C.c_int, [_vp, _sz, _sz, _dp]),
     "sdsp_b200_iir_bank_reset_state": (C.c_int, [_vp]),
+    "sdsp_b200_shard_range": (C.c_int, [_sz, C.c_int, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "sdsp_b200_iir_bank_set_state_diff": (C.c_int, [_vp, _sz, _sz, _dp]),
     "sdsp_b200_iir_bank_get_state_diff": (C.c_int, [_vp, _sz, _sz, _dp]),
     "sdsp_b200_iir_bank_process": (C.c_int, [_vp, _vp, _sz, _sz, C.c_int, C.c_int, _vp]),

@@ -118,6 +118,16 @@ int sdsp_b200_shutdown(void)
     return SDSP_B200_OK;
 }
 
+int sdsp_b200_shard_range(size_t total, int rank, int world, size_t *first, size_t *count)
+{
+    if (!first || !count || world < 1 || rank < 0 || rank >= world)
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "shard_range: rank %d of %d", rank, world);
+    const size_t base = total / (size_t)world, extra = total % (size_t)world, r = (size_t)rank;
+    *first = r * base + (r < extra ? r : extra);
+    *count = base + (r < extra ? 1 : 0);
+    return SDSP_B200_OK;
+}
+
 int sdsp_b200_host_alloc(void **ptr, size_t bytes)
 {
     if (!ptr)

@@ -10,6 +10,21 @@ import pytest
 from simpledsp_b200.shard import shard_range, shard_sizes
 
 
+def test_c_abi_shard_range_matches_the_python_sharder():
+    import ctypes as C
+
+    from simpledsp_b200 import _capi as K
+
+    for total in (0, 1, 7, 64, 65536, 262144):
+        for world in (1, 2, 3, 8):
+            for rank in range(world):
+                first, count = C.c_size_t(), C.c_size_t()
+                K.check(K.lib().sdsp_b200_shard_range(total, rank, world, C.byref(first), C.byref(count)))
+                lo, hi = shard_range(total, rank, world)
+                assert (first.value, first.value + count.value) == (lo, hi)
+    assert K.lib().sdsp_b200_shard_range(10, 2, 2, C.byref(first), C.byref(count)) == K.lib().sdsp_b200_shard_range(10, -1, 2, C.byref(first), C.byref(count)) != 0
+
+
 def test_shard_ranges_partition_exactly():
     for total in (0, 1, 7, 8, 65536, 16385):
         for world in (1, 2, 3, 4, 8):
