@@ -84,7 +84,7 @@ public:
     casc_2o_iir()
     {
         static_assert(m_t % 2 == 0, "M must be even!"); // casc_2o_iir.h:25
-        static_assert(m_t <= 8, "libsdsp_b200 is built for up to 8 sections");
+        static_assert(m_t <= SDSP_B200_IIR_MAX_SECTIONS_ONCE, "libsdsp_b200 chains at most 64 sections per filter object");
     }
 
     // coefficients and type, never the history: casc_2o_iir.h:28-34
@@ -156,7 +156,7 @@ public:
         CLASS()                                                                                                \
         {                                                                                                      \
             static_assert(m_t % 2 == 0, "M must be even!");                                                    \
-            static_assert(m_t <= 8, "libsdsp_b200 is built for up to 8 sections");                             \
+            static_assert(m_t <= SDSP_B200_IIR_MAX_SECTIONS_ONCE, "libsdsp_b200 chains at most 64 sections per filter object");                             \
         }                                                                                                      \
         void copy_coeff_from(const CLASS<m_t> &other_filter)                                                   \
         {                                                                                                      \
@@ -190,6 +190,7 @@ SDSP_B200_FIXED_IIR(casc_2o_iir_bp, SDSP_B200_NUM_BP, set_bp_coeff(double f0, do
 // [channel][sample]; V is float or double.
 template <size_t m_t, typename V = float>
 class iir_bank {
+    static_assert(m_t >= 1 && m_t <= 8, "a device-resident bank holds 1..8 sections per channel");
     sdsp_b200_iir_bank m_bank{ nullptr };
     size_t m_channels{ 0 };
 

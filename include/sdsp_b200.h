@@ -37,6 +37,9 @@ extern "C" {
 /* largest frame sdsp_b200_fft_plan_create accepts (the reference takes any power of two its compiler can fold tables for) */
 #define SDSP_B200_FFT_MAX_N_F32 (1u << 18)
 #define SDSP_B200_FFT_MAX_N_F64 (1u << 17)
+/* section counts: a device-resident bank holds 1..8 sections per channel; the single-object entry points (designers, preload,
+ * sdsp_b200_iir_process_once) chain groups of eight and take up to this many */
+#define SDSP_B200_IIR_MAX_SECTIONS_ONCE 64
 
 enum sdsp_b200_status {
     SDSP_B200_OK = 0,
@@ -186,7 +189,8 @@ int sdsp_b200_iir_preload_state(int sections, int filter_type, double gain, cons
  * uploads {gain,b,a,mem}, filters data[0..n) in place on the device (sequential path), downloads the
  * new history.  precision is that of `data` ONLY: the arithmetic is fp64 either way, as in the reference, whose
  * object computes and keeps m_mem in double for any sample type (casc_2o_iir.h:13-18, 45-71); float samples are
- * widened on the way in and rounded once on the way out.  (fp32 arithmetic: sdsp_b200_iir_bank_* with SDSP_B200_F32.) */
+ * widened on the way in and rounded once on the way out.  (fp32 arithmetic: sdsp_b200_iir_bank_* with SDSP_B200_F32.)
+ * sections: 1 .. SDSP_B200_IIR_MAX_SECTIONS_ONCE; more than eight run as a chain of groups of eight over the block. */
 int sdsp_b200_iir_process_once(int sections, int numerator, int precision, double gain, const double *b,
                                const double *a, double *mem, void *data, size_t n_samples, int device);
 

@@ -4,6 +4,7 @@
 // include/sdsp/casc_2o_iir.h:8-468) for banks of independent channels resident in HBM.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -179,6 +180,7 @@ static void emulate_seq_kind(int kind, double gain, const double *b, const doubl
     case NUM_GENERIC: emulate_seq<T, M, NUM_GENERIC>(gain, b, a, mem, diff, data, n); break;
     case NUM_LP: emulate_seq<T, M, NUM_LP>(gain, b, a, mem, diff, data, n); break;
     case NUM_HP: emulate_seq<T, M, NUM_HP>(gain, b, a, mem, diff, data, n); break;
+    case NUM_GENERIC_B2ONE: emulate_seq<T, M, NUM_GENERIC_B2ONE>(gain, b, a, mem, diff, data, n); break;
     default: emulate_seq<T, M, NUM_BP>(gain, b, a, mem, diff, data, n); break;
     }
 }
@@ -210,7 +212,7 @@ static void design_section(double dk, double e, double &beta, double &gamma)
 
 static int design_lp_hp(int m, double f0, double fs, double gain_in, bool hp, double *gain, double *b, double *a)
 {
-    if (m < 1 || m > 8 || !gain || !b || !a)
+    if (m < 1 || m > SDSP_B200_IIR_MAX_SECTIONS_ONCE || !gain || !b || !a)
         return set_error(SDSP_B200_ERR_INVALID_ARG, "iir_design: bad arguments (sections=%d)", m);
     double g = gain_in;
     const double e0 = 2 * M_PI * f0 / fs;
@@ -233,8 +235,8 @@ static int design_lp_hp(int m, double f0, double fs, double gain_in, bool hp, do
 
 static int design_bp(int m, double f0, double fs, double q, double gain_in, double *gain, double *b, double *a)
 {
-    if (m < 2 || m > 8 || (m % 2) || !gain || !b || !a)
-        return set_error(SDSP_B200_ERR_INVALID_ARG, "iir_design_bp: sections must be even, 2..8 (got %d)", m);
+    if (m < 2 || m > SDSP_B200_IIR_MAX_SECTIONS_ONCE || (m % 2) || !gain || !b || !a)
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "iir_design_bp: sections must be even, 2..%d (got %d)", SDSP_B200_IIR_MAX_SECTIONS_ONCE, m);
     double g = gain_in;
     const double e0 = 2 * M_PI * f0 / fs;
     const double de = 2 * std::tan(e0 / (2 * q)) / std::sin(e0);
@@ -487,6 +489,10 @@ int sdsp_b200_iir_bank_set_coeffs(sdsp_b200_iir_bank bank, size_t first, size_t 
             }
         }
         b.coef_version++;
+        static const int b2one_mode = getenv("SDSP_B200_IIR_B2ONE") ? atoi(getenv("SDSP_B200_IIR_B2ONE")) : -1; // comparison aid: 0 off, 1 on
+        b.b2_all_one = b.numerator == NUM_GENERIC && b.precision == SDSP_B200_F32 && b2one_mode != 0;
+        for (size_t i = 0; b.b2_all_one && i < b.n_channels * (size_t)m; i++)
+            b.b2_all_one = b.h_b[3 * i + 2] == 1.0;
     }
     return rc;
 }
@@ -637,7 +643,7 @@ int sdsp_b200_iir_design_bp(int sections, double f0, double fs, double q, double
 int sdsp_b200_iir_preload_state(int sections, int filter_type, double gain, const double *b, const double *a, double value,
                                 double *mem)
 {
-    if (sections < 1 || sections > 8 || !mem || (filter_type == SDSP_B200_LOW_PASS && (!a || !b)))
+    if (sections < 1 || sections > SDSP_B200_IIR_MAX_SECTIONS_ONCE || !mem || (filter_type == SDSP_B200_LOW_PASS && (!a || !b)))
         return set_error(SDSP_B200_ERR_INVALID_ARG, "iir_preload_state: bad arguments");
     double v = value * gain;
     for (int k = 0; k < 2 * (sections + 1); k++)
@@ -658,18 +664,13 @@ int sdsp_b200_iir_preload_state(int sections, int filter_type, double gain, cons
 // (casc_2o_iir.h:13-18, 45-71), so float samples are widened on the way in and rounded once on the way out, and the
 // history the caller holds (double mem[sections+1][2]) round-trips exactly -- block-wise calls stay bit-identical to
 // one whole-buffer call (test/testIIR.cpp:61-75).  fp32 ARITHMETIC is what sdsp_b200_iir_bank_* with SDSP_B200_F32 is for.
-int sdsp_b200_iir_process_once(int sections, int numerator, int precision, double gain, const double *bco, const double *aco,
-                               double *mem, void *data, size_t n_samples, int device)
+// one group of at most 8 sections (what the kernels are built for)
+static int process_once_group(int sections, int numerator, int precision, double gain, const double *bco, const double *aco, double *mem,
+                              void *data, size_t n_samples, int device)
 {
     int rc = check_bank_args(sections, precision, numerator);
     if (rc)
         return rc;
-    if (!aco || !mem || (numerator == NUM_GENERIC && !bco))
-        return set_error(SDSP_B200_ERR_INVALID_ARG, "iir_process_once: null argument");
-    if (n_samples == 0)
-        return SDSP_B200_OK;
-    if (!data)
-        return set_error(SDSP_B200_ERR_INVALID_ARG, "iir_process_once: null data");
     std::lock_guard<std::mutex> lock(g_once_mu);
     auto key = std::make_tuple(sections, numerator, device);
     auto it = g_once_cache.find(key);
@@ -753,16 +754,69 @@ int sdsp_b200_iir_process_once(int sections, int numerator, int precision, doubl
     return rc;
 }
 
+int sdsp_b200_iir_process_once(int sections, int numerator, int precision, double gain, const double *bco, const double *aco,
+                               double *mem, void *data, size_t n_samples, int device)
+{
+    if (sections < 1 || sections > SDSP_B200_IIR_MAX_SECTIONS_ONCE)
+        return set_error(SDSP_B200_ERR_UNSUPPORTED, "iir_process_once: sections=%d (1..%d)", sections, SDSP_B200_IIR_MAX_SECTIONS_ONCE);
+    if ((precision != SDSP_B200_F32 && precision != SDSP_B200_F64) || numerator < 0 || numerator > 3)
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "iir_process_once: bad precision / numerator");
+    if (!aco || !mem || (numerator == NUM_GENERIC && !bco))
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "iir_process_once: null argument");
+    if (n_samples == 0)
+        return SDSP_B200_OK;
+    if (!data)
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "iir_process_once: null data");
+    if (sections <= 8)
+        return process_once_group(sections, numerator, precision, gain, bco, aco, mem, data, n_samples, device);
+    // More sections than a kernel holds (the reference's template takes any even m_t, casc_2o_iir.h:23-26): a cascade is a chain,
+    // so groups of eight run one after another over the block -- group g + 1 with gain 1 (x * 1 is exact) on group g's output.
+    // Row `first` of the history belongs to both neighbours (output history of one, input history of the other): the later
+    // group must start from its value BEFORE this block, which the earlier group has overwritten by then.
+    std::vector<double> wide;
+    double *work = static_cast<double *>(data);
+    if (precision == SDSP_B200_F32) { // keep fp64 between the groups; round once at the end
+        const float *src = static_cast<const float *>(data);
+        wide.assign(src, src + n_samples);
+        work = wide.data();
+    }
+    double shared_before[2] = { 0, 0 };
+    for (int first = 0; first < sections; first += 8) {
+        const int cnt = sections - first < 8 ? sections - first : 8;
+        double gmem[2 * 9];
+        memcpy(gmem, mem + 2 * first, sizeof(double) * 2 * (size_t)(cnt + 1));
+        if (first > 0) {
+            gmem[0] = shared_before[0];
+            gmem[1] = shared_before[1];
+        }
+        shared_before[0] = mem[2 * (first + cnt)];
+        shared_before[1] = mem[2 * (first + cnt) + 1];
+        const int rc = process_once_group(cnt, numerator, SDSP_B200_F64, first == 0 ? gain : 1.0, bco ? bco + 3 * first : nullptr,
+                                          aco + 3 * first, gmem, work, n_samples, device);
+        if (rc)
+            return rc;
+        memcpy(mem + 2 * (first + (first > 0 ? 1 : 0)), gmem + (first > 0 ? 2 : 0), sizeof(double) * 2 * (size_t)(cnt + (first > 0 ? 0 : 1)));
+    }
+    if (precision == SDSP_B200_F32) {
+        float *dst = static_cast<float *>(data);
+        for (size_t i = 0; i < n_samples; i++)
+            dst[i] = (float)wide[i];
+    }
+    return SDSP_B200_OK;
+}
+
 // host emulation of the sequential kernels.  diff (may be null): the running differences of the fp32 delta form,
 // [sections] doubles in / out next to mem -- with them a stream cut into calls reproduces the uncut run bit for bit;
 // without, each call starts them at v[n-1] - v[n-2] as sdsp_b200_iir_bank_set_state does.
 int sdsp_b200_debug_emulate_iir_diff(int sections, int numerator, int precision, double gain, const double *bco, const double *aco,
                                      double *mem, double *diff, void *data, size_t n_samples)
 {
-    int rc = check_bank_args(sections, precision, numerator);
+    // (numerator 4 = the kernels' internal "generic with every b2 == 1" kind, so that its bit-identity with the generic kind
+    // can be checked on the host)
+    int rc = check_bank_args(sections, precision, numerator == NUM_GENERIC_B2ONE ? NUM_GENERIC : numerator);
     if (rc)
         return rc;
-    if (!aco || !mem || !data || (numerator == NUM_GENERIC && !bco))
+    if (!aco || !mem || !data || ((numerator == NUM_GENERIC || numerator == NUM_GENERIC_B2ONE) && !bco))
         return set_error(SDSP_B200_ERR_INVALID_ARG, "emulate_iir: null argument");
     if (precision == SDSP_B200_F32)
         return emulate_seq_sections<float>(sections, numerator, gain, bco, aco, mem, diff, data, n_samples);

@@ -29,7 +29,11 @@
 
 namespace sdsp_b200
 {
-enum : int { NUM_GENERIC = 0, NUM_LP = 1, NUM_HP = 2, NUM_BP = 3 };
+enum : int { NUM_GENERIC = 0, NUM_LP = 1, NUM_HP = 2, NUM_BP = 3,
+              // internal: a generic bank whose every b2 is exactly 1 (all Butterworth low-/high-pass designs, in any mix).  fma(1, in2, t)
+              // IS t + in2, so the result has the same bits; an add has two register operands and issues at full rate where a
+              // three-register FFMA takes 1.83 cycles of a warp that is alone on its sub-partition (profiles/r02_ubench_fp32_issue.txt)
+              NUM_GENERIC_B2ONE = 4 };
 
 // does precision T run the difference form (and carry d next to the history)?
 template <typename T>
@@ -178,6 +182,8 @@ SDSP_HD T iir_numerator(T in0, T in1, T in2, T b1, T b2)
 {
     if (KIND == NUM_GENERIC)
         return fma_t(b2, in2, fma_t(b1, in1, in0));
+    if (KIND == NUM_GENERIC_B2ONE)
+        return add_t(fma_t(b1, in1, in0), in2);
     if (KIND == NUM_LP)
         return fma_t((T)2, in1, in0) + in2;
     if (KIND == NUM_HP)
@@ -330,6 +336,8 @@ SDSP_HD f32x2 iir_numerator_x2(f32x2 in0, f32x2 in1, f32x2 in2, f32x2 b1, f32x2 
 {
     if (KIND == NUM_GENERIC)
         return fma2(b2, in2, fma2(b1, in1, in0));
+    if (KIND == NUM_GENERIC_B2ONE)
+        return add2(fma2(b1, in1, in0), in2);
     if (KIND == NUM_LP)
         return add2(fma2(mk2(2.f, 2.f), in1, in0), in2);
     if (KIND == NUM_HP)

@@ -19,6 +19,7 @@ struct IirBank {
     // host copy of the coefficients in double (scan tables are derived from it)
     std::vector<double> h_gain, h_b, h_a;
     unsigned long coef_version = 0;
+    bool b2_all_one = false; // generic bank, every b2 == 1: the kernels skip that multiply (same bits), see NUM_GENERIC_B2ONE
     // scan path: per-channel propagation tables on the device, rebuilt when the coefficients change
     void *d_scan_tables = nullptr;
     size_t scan_tables_bytes = 0;

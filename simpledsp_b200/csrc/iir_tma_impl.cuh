@@ -393,6 +393,8 @@ template <typename T, int M>
 static int launch_rows_kind(const IirBank &b, void *data, size_t seg_len, size_t segs, size_t stride, void *row_state, size_t n_samples,
                             bool accumulate, cudaStream_t stream, int *slots)
 {
+    // (the b2 == 1 specialisation of the plain pass is not used here: measured neutral when several row-warps share a
+    // scheduler, profiles/r02_iir_b2one_ab.txt)
     switch (b.numerator) {
     case NUM_GENERIC: return launch_rows_mode<T, M, NUM_GENERIC>(b, data, seg_len, segs, stride, row_state, n_samples, accumulate, stream, slots);
     case NUM_LP: return launch_rows_mode<T, M, NUM_LP>(b, data, seg_len, segs, stride, row_state, n_samples, accumulate, stream, slots);
@@ -458,6 +460,10 @@ static int launch_tma(const IirBank &b, void *data, size_t n_samples, size_t str
 template <typename T, int M>
 static int launch_tma_kind(const IirBank &b, void *data, size_t n_samples, size_t stride, cudaStream_t stream)
 {
+    if constexpr (sizeof(T) == 4) { // fp32 only: +3.8 % on config 3; in fp64 an add costs the FP64 pipe what an fma does and the kernel got slower
+        if (b.numerator == NUM_GENERIC && b.b2_all_one)
+            return launch_tma<T, M, NUM_GENERIC_B2ONE>(b, data, n_samples, stride, stream);
+    }
     switch (b.numerator) {
     case NUM_GENERIC: return launch_tma<T, M, NUM_GENERIC>(b, data, n_samples, stride, stream);
     case NUM_LP: return launch_tma<T, M, NUM_LP>(b, data, n_samples, stride, stream);

@@ -275,3 +275,23 @@ def test_fft_work_queue_order_makes_every_wait_point_at_a_smaller_ticket(n1, pre
                 assert first_row - min(q for q, _ in col_ticket[f]) >= (2 * lag - 1) * tiles or f < lag
     # sizes the queue kernels do not take are refused
     assert L.sdsp_b200_debug_fft_queue_item(4096, p, 0, geom, item) != 0
+
+
+def test_generic_kernel_without_the_b2_multiply_gives_the_same_bits():
+    """A generic bank whose every b2 is exactly 1 (all Butterworth low-/high-pass designs) runs kernels that add in2 instead of
+    multiplying it by b2 (iir_core.cuh, NUM_GENERIC_B2ONE = 4): fma(1, in2, t) is t + in2, so nothing may change."""
+    L = K.lib()
+    rng = np.random.default_rng(4)
+    for ftype in (1, 2):
+        for sections in (2, 4, 8):
+            g, b, a = S.design(ftype, sections, 700.0 * ftype, 39e3)
+            assert (b[:, 2] == 1.0).all()
+            for prec, dt in ((K.F64, np.float64), (K.F32, np.float32)):
+                x = rng.standard_normal(777).astype(dt)
+                outs = []
+                for kind in (0, 4):
+                    y, mem, dif = x.copy(), np.zeros((sections + 1, 2)), np.zeros(sections)
+                    K.check(L.sdsp_b200_debug_emulate_iir_diff(sections, kind, prec, g, b.ctypes.data_as(dp), a.ctypes.data_as(dp),
+                                                               mem.ctypes.data_as(dp), dif.ctypes.data_as(dp), y.ctypes.data, y.size))
+                    outs.append((y, mem, dif))
+                assert all(np.array_equal(p, q) for p, q in zip(*outs))

@@ -560,3 +560,28 @@ def test_auto_goes_time_parallel_only_for_small_banks_on_long_calls():
     assert peak_rel(y[:, :4096], whole) <= IIR_TOL["f32"]
     big = S.IirBank(4, 32 * (2 * sms + 1), K.F32)  # one warp of channels past the threshold
     assert "sequential" in big.describe(n_long)
+
+
+@pytest.mark.parametrize("sections,ftype", [(12, 1), (16, 2), (10, 3)])
+def test_single_object_with_more_sections_than_a_kernel_holds(sections, ftype):
+    """The reference's template takes any even m_t (casc_2o_iir.h:23-26).  The kernels hold up to eight sections, so the
+    single-object path chains groups of eight (sdsp_b200_iir_process_once); against the oracle's filter of the same order,
+    whole buffer and 32-sample blocks (bit-identical, reference test/testIIR.cpp:61-75), float samples included."""
+    rng = np.random.default_rng(sections)
+    fs, f0, q = 100e3, 12e3, 1.3
+    x = f32_noise(rng, 3000)
+    f = O.Iir(sections)
+    f.design(ftype, f0, fs, q)
+    ref = f.process(x)
+    for prec in ("f64", "f32"):
+        code, dt = PREC[prec]
+        g = S.casc_2o_iir(sections, code)
+        _design(g, ftype, f0, fs, q)
+        g2 = g.copy()
+        y = g.process(x.astype(dt))
+        assert peak_rel(y, ref) <= (IIR_TOL["f64"] if prec == "f64" else 1e-7), (sections, prec)
+        y2 = x.astype(dt)
+        for lo in range(0, x.size, 32):
+            g2.process(y2[lo:lo + 32])
+        assert np.array_equal(y, y2), (sections, prec)
+        assert np.array_equal(g.mem, g2.mem)
