@@ -1,10 +1,5 @@
 mkdir -p gpurun_out
-run() { timeout 300 python bench.py --steps $2 --warmup 3 --no-e2e --no-cpu --no-secondary --workload $1 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$3', d['config']['workload'], round(d['ms_per_step'],3), round(d['value']), round(d['roofline']['achieved'],1), round(d['roofline']['frac'],4), d['self_check'], d['clocks']['sm_mhz'], d['clocks']['reasons'])" >> gpurun_out/r02_fft_lead.log 2>&1; }
-rm -f gpurun_out/r02_fft_lead.log
-for rep in 1 2; do
-for lib in lib lib_lead1152 lib_lead1536 lib_lead2304; do
-for m in 1 2; do
-for w in fft65536_f32 fft32768_f32; do
-SDSP_B200_LIB=$PWD/simpledsp_b200/$lib/libsdsp_b200.so SDSP_B200_FFT_FUSED_TMA=$m run $w 20 "$lib mode=$m"
-done; done; done; done
-cat gpurun_out/r02_fft_lead.log
+timeout 600 python -m pytest tests/test_gpu_reference_tests.py -m gpu -q -s --timeout 600 > gpurun_out/r02_reference_tests_through_dropin.log 2>&1; echo "rc=$?" >> gpurun_out/r02_reference_tests_through_dropin.log
+grep -E "benchmark|failed|passed|rc=" gpurun_out/r02_reference_tests_through_dropin.log
+timeout 600 python -m pytest tests/test_gpu_fft.py -m gpu -q --timeout 600 -x -k "all_sizes or fused or large_frames or host_buffers or real_input" 2>&1 | tail -3
+timeout 300 python -m pytest tests/test_gpu_iir.py -m gpu -q --timeout 600 -x -k "more_sections or golden" 2>&1 | tail -3
