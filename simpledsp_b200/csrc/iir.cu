@@ -137,11 +137,121 @@ static int launch_seq_sections(const IirBank &b, void *data, size_t n_samples, s
     }
 }
 
+// =================================================================================================
+// One channel, a few thousand samples: the single filter object of the drop-in header (BASELINE config 1: casc_2o_iir<4> on a
+// 4096-sample buffer, reference test/testIIR.cpp:465-496).  Nothing is parallel but the SECTIONS: warp j runs section j, one lane
+// each, over tiles of CH_TILE samples held in shared memory; in step s warp j filters tile s - j in place (the output of section
+// j - 1 written one step earlier), a CTA barrier between steps.  One warp doing all sections issues 4 x 5 fp64 operations per
+// sample on one FP64 pipe (~90 us for 4096 samples); m warps on m sub-partitions are bound by the recurrence's one-FMA latency
+// instead (~20 us).  Every update is the same iir_section() call on the same operands as iir_step(): same bits.
+constexpr int CH_TILE = 32;
+template <typename T, int KIND>
+__global__ void __launch_bounds__(256)
+    iir_chain_kernel(T *__restrict__ data, int n_samples, const T *__restrict__ coef, T *__restrict__ state, int m)
+{
+    extern __shared__ __align__(16) unsigned char chain_smem[];
+    T *sx = reinterpret_cast<T *>(chain_smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < n_samples; i += blockDim.x)
+        sx[i] = data[i];
+    // section `warp` of the one channel (bank rows of a one-channel bank are contiguous: pitch 1)
+    T gain = 1, b1 = 0, b2 = 0, fa = 0, fb = 0, in1 = 0, in2 = 0, v1 = 0, v2 = 0, d = 0;
+    if (lane == 0 && warp < m) {
+        gain = warp == 0 ? coef[0] : (T)1; // x * 1 is exact: the stream passes from section to section unchanged
+        b1 = coef[1 + warp];
+        b2 = coef[1 + m + warp];
+        fa = coef[1 + 2 * m + warp];
+        fb = coef[1 + 3 * m + warp];
+        in1 = state[2 * warp];
+        in2 = state[2 * warp + 1];
+        v1 = state[2 * (warp + 1)];
+        v2 = state[2 * (warp + 1) + 1];
+        d = IirDelta<T>::value ? state[2 * (m + 1) + warp] : (T)0;
+    }
+    __syncthreads();
+    const int n_tiles = (n_samples + CH_TILE - 1) / CH_TILE;
+    for (int s = 0; s < n_tiles + m - 1; s++) {
+        const int k = s - warp;
+        if (lane == 0 && warp < m && k >= 0 && k < n_tiles) {
+            T *p = sx + k * CH_TILE;
+            const int cnt = n_samples - k * CH_TILE < CH_TILE ? n_samples - k * CH_TILE : CH_TILE;
+            if (cnt == CH_TILE) {
+#pragma unroll
+                for (int i = 0; i < CH_TILE; i++) {
+                    const T in0 = mul_t(p[i], gain);
+                    const T v = iir_section<KIND>(in0, in1, in2, v1, v2, d, b1, b2, fa, fb);
+                    in2 = in1, in1 = in0, v2 = v1, v1 = v;
+                    p[i] = v;
+                }
+            } else {
+                for (int i = 0; i < cnt; i++) {
+                    const T in0 = mul_t(p[i], gain);
+                    const T v = iir_section<KIND>(in0, in1, in2, v1, v2, d, b1, b2, fa, fb);
+                    in2 = in1, in1 = in0, v2 = v1, v1 = v;
+                    p[i] = v;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < n_samples; i += blockDim.x)
+        data[i] = sx[i];
+    if (lane == 0 && warp < m) {
+        if (warp == 0) {
+            state[0] = in1; // row 0: the scaled input
+            state[1] = in2;
+        }
+        state[2 * (warp + 1)] = v1;
+        state[2 * (warp + 1) + 1] = v2;
+        if (IirDelta<T>::value)
+            state[2 * (m + 1) + warp] = d;
+    }
+}
+
+template <typename T>
+static int launch_chain(const IirBank &b, void *data, size_t n_samples, cudaStream_t stream)
+{
+    const size_t smem = n_samples * sizeof(T);
+    const int threads = 32 * (b.sections < 4 ? 4 : b.sections); // at least four warps for the copies
+#define SDSP_CHAIN(KK)                                                                                                        \
+    {                                                                                                                         \
+        auto kern = iir_chain_kernel<T, KK>;                                                                                   \
+        static bool configured_dev[64] = {};                                                                                  \
+        if (!configured_dev[b.device & 63]) {                                                                                 \
+            SDSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IIR_CHAIN_MAX_BYTES));      \
+            configured_dev[b.device & 63] = true;                                                                             \
+        }                                                                                                                     \
+        kern<<<1, threads, smem, stream>>>(static_cast<T *>(data), (int)n_samples, static_cast<const T *>(b.d_coef),          \
+                                           static_cast<T *>(b.d_state), b.sections);                                          \
+    }
+    switch (b.numerator) {
+    case NUM_GENERIC: SDSP_CHAIN(NUM_GENERIC) break;
+    case NUM_LP: SDSP_CHAIN(NUM_LP) break;
+    case NUM_HP: SDSP_CHAIN(NUM_HP) break;
+    default: SDSP_CHAIN(NUM_BP) break;
+    }
+#undef SDSP_CHAIN
+    SDSP_CUDA(cudaGetLastError());
+    return SDSP_B200_OK;
+}
+
 int iir_launch_sequential(const IirBank &b, void *data, size_t n_samples, size_t stride, cudaStream_t stream)
 {
     if (b.precision == SDSP_B200_F32)
         return launch_seq_sections<float>(b, data, n_samples, stride, stream);
     return launch_seq_sections<double>(b, data, n_samples, stride, stream);
+}
+
+// one channel whose samples fit shared memory: sections spread over warps (same bits as every other sequential kernel)
+bool iir_chain_applicable(const IirBank &b, size_t n_samples)
+{
+    static const bool disabled = getenv("SDSP_B200_NO_CHAIN") != nullptr;
+    const size_t es = b.precision == SDSP_B200_F32 ? 4 : 8;
+    return !disabled && b.n_channels == 1 && b.sections >= 2 && n_samples >= 2 * CH_TILE && n_samples * es <= IIR_CHAIN_MAX_BYTES;
+}
+int iir_launch_chain(const IirBank &b, void *data, size_t n_samples, cudaStream_t stream)
+{
+    return b.precision == SDSP_B200_F32 ? launch_chain<float>(b, data, n_samples, stream) : launch_chain<double>(b, data, n_samples, stream);
 }
 
 // =================================================================================================

@@ -64,6 +64,8 @@ int iir_dispatch(IirBank &b, void *data, size_t n_samples, size_t stride, int pa
     }
     if (path == SDSP_B200_IIR_AUTO && iir_auto_time_split(b, data, n_samples, stride))
         return iir_launch_segmented(b, data, n_samples, stride, stream);
+    if (iir_chain_applicable(b, n_samples)) // one channel, a few thousand samples: sections spread over warps (same bits)
+        return iir_launch_chain(b, data, n_samples, stream);
     if (iir_use_tma(b, data, n_samples, stride))
         return iir_launch_tma(b, data, n_samples, stride, stream);
     return iir_launch_sequential(b, data, n_samples, stride, stream);
@@ -79,9 +81,12 @@ int iir_describe(IirBank &b, size_t n_samples, size_t stride, int path, char *bu
         timepar = true;
         path = SDSP_B200_IIR_SCAN;
     }
-    const bool tma = !timepar && iir_use_tma(b, nullptr, n_samples, stride);
+    const bool chain = !timepar && iir_chain_applicable(b, n_samples);
+    const bool tma = !timepar && !chain && iir_use_tma(b, nullptr, n_samples, stride);
     char how[512];
-    snprintf(how, sizeof how, "%s", tma ? "sequential/tma (warp per 32 channels, skewed sections, TMA ring per warp through the blocked view)" : "sequential/generic");
+    snprintf(how, sizeof how, "%s", chain ? "sequential/chain (one channel in shared memory, one warp per section)" :
+                                    tma   ? "sequential/tma (warp per 32 channels, skewed sections, TMA ring per warp through the blocked view)" :
+                                            "sequential/generic");
     if (timepar) {
         const bool split = path != SDSP_B200_IIR_SCAN_LOOKBACK && b.h_gain.size() == b.n_channels && iir_use_tma(b, nullptr, n_samples, stride) &&
                            iir_segment_describe(b, n_samples, how, sizeof how) == 0;

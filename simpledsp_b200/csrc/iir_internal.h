@@ -56,6 +56,9 @@ inline int iir_bank_state_rows(const IirBank &b)
 // iir.cu
 void iir_release_process_once_cache(); // sdsp_b200_shutdown()
 int iir_launch_sequential(const IirBank &b, void *data, size_t n_samples, size_t stride, cudaStream_t stream);
+constexpr size_t IIR_CHAIN_MAX_BYTES = 160 * 1024; // samples of the one channel held in shared memory
+bool iir_chain_applicable(const IirBank &b, size_t n_samples);
+int iir_launch_chain(const IirBank &b, void *data, size_t n_samples, cudaStream_t stream);
 // iir_tma.cu -- the fast sequential path (needs 16-byte aligned base and pitch, even section count)
 bool iir_tma_applicable(const IirBank &b, const void *data, size_t n_samples, size_t stride);
 bool iir_tma_built_for(int sections);
