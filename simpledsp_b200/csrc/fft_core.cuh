@@ -20,6 +20,13 @@
 #pragma once
 #include "common.h"
 
+#ifndef SDSP_FFT_TW4_F32
+#define SDSP_FFT_TW4_F32 1 // first-pass factors from four loads + products in fp32 as well as in fp64 (see fft_pass)
+#endif
+#ifndef SDSP_FFT_TW4_MIN_M
+#define SDSP_FFT_TW4_MIN_M 64 // ... for tables of at least this many entries per row (1024-point frames and up; 256 and 64 measured: profiles/r02_fft_twiddle_loads_ab.txt)
+#endif
+
 namespace sdsp_b200
 {
 // ------------------------------------------------------------------------------------------------
@@ -209,11 +216,29 @@ SDSP_HD void fft_pass(cplx<T> (&v)[Cfg::E], int t, const cplx<T> *__restrict__ t
             const int b = t + Cfg::S * q;
             const int m = b / PP;
             const cplx<T> *row = tw + Cfg::tw_offset(P) + m;
+            if ((sizeof(T) == 8 || SDSP_FFT_TW4_F32) && R == 16 && M >= SDSP_FFT_TW4_MIN_M) {
+                // fp64 frames of 4096 points and more, first pass: the 15 factors W^(m k) of a butterfly come from a table of
+                // 15 x M x 16 bytes (61 KB at 4096 points) that does not stay in what the exchange buffers leave of L1, and
+                // loading them all costs as many bytes from L2 as the frame itself.  Four of them are loaded (k = 1, 4, 8, 12),
+                // the rest are products W^(4j m) W^(m r) with r = k mod 4 -- two roundings deep; eleven more complex products on
+                // an FP64 pipe that is a third busy (profiles/r01_ncu_fft4096_f64_v3.txt).
+                const cplx<T> w1 = row[0], w4 = row[3 * M], w8 = row[7 * M], w12 = row[11 * M];
+                const cplx<T> w2 = cmul(w1, w1), w3 = cmul(w2, w1);
+                const cplx<T> lo[4] = { w1, w1, w2, w3 }, hi[4] = { w1, w4, w8, w12 };
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-            for (int k = 1; k < R; k++)
-                a[k] = cmul(a[k], row[(k - 1) * M]);
+                for (int k = 1; k < R; k++) {
+                    const cplx<T> w = k < 4 ? lo[k] : (k % 4 == 0 ? hi[k / 4] : cmul(hi[k / 4], lo[k % 4]));
+                    a[k] = cmul(a[k], w);
+                }
+            } else {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+                for (int k = 1; k < R; k++)
+                    a[k] = cmul(a[k], row[(k - 1) * M]);
+            }
         }
 #if defined(__CUDA_ARCH__)
 #pragma unroll
