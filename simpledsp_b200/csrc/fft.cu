@@ -2119,11 +2119,9 @@ static int setup_plan(FftPlan &p)
     static const bool fused_small = getenv("SDSP_B200_FFT_FUSED_SMALL") && atoi(getenv("SDSP_B200_FFT_FUSED_SMALL")) != 0; // comparison aid: 8192 / 16384 through the fused kernel
     if (fused_small && (lg == 13 || lg == 14))
         return p.precision == SDSP_B200_F32 ? setup_large_n1<float>(p) : setup_large_n1<double>(p);
-    // fp32 frames of 16384 points: the two-slot data-mover queue (n = 64 x 256) beats one 1024-thread CTA per frame, 0.60 against
-    // 0.57 (profiles/r02_fft_fused_variants.txt); 8192 points stay in one CTA (0.66 against 0.60).  SDSP_B200_FFT_FUSED_SMALL=0 pins one CTA.
-    static const bool single_cta_16k = getenv("SDSP_B200_FFT_FUSED_SMALL") && atoi(getenv("SDSP_B200_FFT_FUSED_SMALL")) == 0;
-    if (lg == 14 && p.precision == SDSP_B200_F32 && !single_cta_16k && fused_tma_wanted())
-        return setup_large_n1<float>(p);
+    // (fp32 frames of 16384 points: one 1024-thread CTA per frame, 0.64 of the copy peak since the first pass loads four twiddles
+    // instead of fifteen; the two-slot data-mover queue, n = 64 x 256, reaches 0.60 -- profiles/r02_fft_fused_variants.txt,
+    // r02_bench_workloads_v1.txt.  8192 points: 0.68 against 0.60.)
     if (lg > (p.precision == SDSP_B200_F32 ? MAX_LOG2N_F32 : MAX_LOG2N_F64))
         return p.precision == SDSP_B200_F32 ? setup_large_n1<float>(p) : setup_large_n1<double>(p);
     switch (lg) {
