@@ -359,6 +359,8 @@ struct FftPlan {
     bool double_buffered = false;
     bool staged = false; // next group staged into the exchange buffer by cp.async (fft_cta_alias_kernel)
     bool two_slot = false; // data-mover kernel with two tile slots that double as exchange buffers (fft_fused_tma2_kernel)
+    int real64k_ctas = 0;  // > 0: forward real-input frames of 65536 points take fft_real64k_kernel (resident CTAs per SM)
+    size_t real64k_smem = 0;
     void *d_tw = nullptr;
     size_t tw_bytes = 0;
     fft_launch_fn launch = nullptr;
@@ -1786,10 +1788,314 @@ __global__ void __launch_bounds__(288, MINB)
 }
 
 
+// -------------------------------------------------------------------------------------------------
+// REAL frames of 65536 points (sdsp_b200_fft_exec_real, forward): the two-slot work queue again, doing half the work.
+// The reference's callers put a real signal into the real part of a complex_array and leave the imaginary part zero
+// (test/testFFT.cpp:24, :86); the spectrum of such a frame is conjugate-symmetric, X[N - k] = conj(X[k]), and so is every
+// column transform Y_b[k1] over a.  Hence
+//   column tile (8 per frame, 32 real columns): columns b, b + 1 ride one complex 256-point transform as real and imaginary
+//     part, z = x_b + i x_(b+1); Y_b[k1] = (Z[k1] + conj Z[256 - k1]) / 2, Y_(b+1)[k1] = -i (Z[k1] - conj Z[256 - k1]) / 2 -- the
+//     mirror term comes from the thread that holds it through one more exchange in the slot -- and only k1 = 0 .. 128 go to the
+//     ring (times W_N^(b k1)), two neighbouring columns per 16-byte store;
+//   row tile (9 per frame: rows 0 .. 127 in eight tiles, row 128 in a ninth): the usual 256-point transform over b gives
+//     X[k1 + 256 k2]; rows 1 .. 127 also store conj to the mirror bin (256 - k1) + 256 (255 - k2), rows 0 and 128 mirror into
+//     themselves.  Rows 129 .. 255 are never computed.
+// 17 items per frame instead of 32, the output is conjugate-symmetric to the bit.  Queue order: column tiles of frame f + LAG, then
+// row tiles of frame f; a row tile waits for its frame's 8 column tiles, a column tile for the 9 row tiles of the ring slot's
+// previous tenant -- both hold smaller tickets.
+constexpr int REAL_CT = 8, REAL_RT = 9, REAL_LAG = 88, REAL_RING = 176, REAL_ROWS = 129;
+__host__ __device__ __forceinline__ void real_decode(size_t q, bool &cols, size_t &f, int &tile)
+{
+    if (q < (size_t)REAL_LAG * REAL_CT) {
+        cols = true;
+        f = q / REAL_CT;
+        tile = (int)(q % REAL_CT);
+        return;
+    }
+    const size_t r = q - (size_t)REAL_LAG * REAL_CT, u = r / (REAL_CT + REAL_RT);
+    const int w = (int)(r % (REAL_CT + REAL_RT));
+    cols = w < REAL_CT;
+    f = cols ? REAL_LAG + u : u;
+    tile = cols ? w : w - REAL_CT;
+}
+
+template <typename T, int MINB>
+__global__ void __launch_bounds__(288, MINB)
+    fft_real64k_kernel(const __grid_constant__ CUtensorMap in_map, cplx<T> *__restrict__ data, cplx<T> *__restrict__ scratch,
+                       const cplx<T> *__restrict__ tw, const cplx<T> *__restrict__ tw_hi, const cplx<T> *__restrict__ tw_lo,
+                       unsigned *__restrict__ ticket, unsigned *__restrict__ col_done, unsigned *__restrict__ row_done, size_t n_frames)
+{
+    using Cfg = FftCfg<256, 16, 16, 16>; // rows and (packed) columns alike
+    constexpr int N1 = 256, N2 = 256, PITCH = LargeStride<Cfg>::value;
+    constexpr int XBUF = 16 * PITCH;
+    constexpr size_t FRAME = (size_t)N1 * N2, RFRAME = (size_t)REAL_ROWS * N2; // output frame; ring frame (rows 0 .. 128)
+    constexpr uint32_t TILE_BYTES = 4096 * sizeof(cplx<T>);
+    constexpr int NST = 2, ND = NST + 1;
+    constexpr int SLOT = (XBUF + 15) / 16 * 16;
+    extern __shared__ __align__(128) unsigned char smem_raw128[];
+    cplx<T> *stage0 = reinterpret_cast<cplx<T> *>(smem_raw128);
+    cplx<T> *s_hi = stage0 + (size_t)NST * SLOT, *s_lo = s_hi + N1;
+    uint64_t *full = reinterpret_cast<uint64_t *>(s_lo + 256), *empty = full + NST, *done_bar = empty + NST;
+    unsigned *s_item = reinterpret_cast<unsigned *>(done_bar + ND);
+    if (threadIdx.x < 256) {
+        s_hi[threadIdx.x] = tw_hi[threadIdx.x];
+        s_lo[threadIdx.x] = tw_lo[threadIdx.x];
+    }
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NST; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 256);
+        }
+        for (int s = 0; s < ND; s++)
+            mbar_init(&done_bar[s], 256);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    const size_t total = (size_t)REAL_LAG * REAL_CT + n_frames * (REAL_CT + REAL_RT);
+
+    if (threadIdx.x >= 256) { // ---- the data mover (as in fft_fused_tma2_kernel)
+        if (threadIdx.x != 256)
+            return;
+        unsigned *pend[ND];
+        for (int i = 0; i < ND; i++)
+            pend[i] = nullptr;
+        unsigned it = 0, next_pub = 0;
+        auto count_tile = [&](unsigned j) {
+            unsigned *d = pend[j % ND];
+            if (d)
+                asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(d) : "memory");
+        };
+        auto try_publish = [&]() {
+            while (next_pub < it && mbar_test(&done_bar[next_pub % ND], (next_pub / ND) & 1)) {
+                count_tile(next_pub);
+                next_pub++;
+            }
+        };
+        auto wait_dep = [&](const unsigned *ctr, unsigned target) {
+            while (ld_acquire_gpu(ctr) < target) {
+                try_publish();
+                __nanosleep(32);
+            }
+        };
+        for (;; it++) {
+            const int s = it % NST;
+            if (it >= (unsigned)NST) {
+                while (!SDSP_FUSED_POLL(&empty[s], ((it / NST) - 1) & 1))
+                    try_publish();
+                while (next_pub + ND <= it) {
+                    mbar_wait(&done_bar[next_pub % ND], (next_pub / ND) & 1);
+                    count_tile(next_pub);
+                    next_pub++;
+                }
+            }
+            const size_t q = atomicAdd(ticket, 1u);
+            bool cols = false;
+            size_t f = n_frames;
+            int tile = 0;
+            if (q < total)
+                real_decode(q, cols, f, tile);
+            const bool real = q < total && f < n_frames;
+            if (real && !cols)
+                wait_dep(col_done + f, REAL_CT);
+            s_item[s] = q < total ? (unsigned)q : 0xffffffffu;
+            if (q >= total) {
+                mbar_arrive(&full[s]);
+                break;
+            }
+            cplx<T> *dst = stage0 + (size_t)s * SLOT;
+            unsigned *d = nullptr;
+            if (!real) {
+                mbar_arrive(&full[s]);
+            } else if (cols) {
+                mbar_expect_tx_only(&full[s], TILE_BYTES);
+                tma_load_3d(dst, &in_map, 32 * tile, 0, (int)f, &full[s]); // 256 rows x 32 real columns
+                if (f >= (size_t)REAL_RING)
+                    wait_dep(row_done + (f - REAL_RING), REAL_RT);
+                mbar_arrive(&full[s]);
+                d = col_done + f;
+            } else {
+                const uint32_t bytes = tile == REAL_RT - 1 ? (uint32_t)(N2 * sizeof(cplx<T>)) : TILE_BYTES; // the ninth tile is row 128 alone
+                asm volatile("fence.proxy.async.global;" ::: "memory");
+                mbar_expect_tx(&full[s], bytes);
+                bulk_load_1d(dst, scratch + (f % REAL_RING) * RFRAME + (size_t)(16 * tile) * N2, bytes, &full[s]);
+                d = row_done + f;
+            }
+            pend[it % ND] = d;
+        }
+        for (; next_pub < it; next_pub++) {
+            mbar_wait(&done_bar[next_pub % ND], (next_pub / ND) & 1);
+            count_tile(next_pub);
+        }
+        return;
+    }
+
+    // ---- the 256 compute threads
+    const int lo16 = threadIdx.x & 15, hi16 = threadIdx.x >> 4;
+    // column tiles: packed pair p = lo16 (columns 32 c + 2 p, + 1), thread ct = hi16 of its transform.  Launch-long share of the
+    // factors W_N^(b k1), k1 = ct + 16 e, b = 32 c + 2 p:  W^(b k1) = [W^(2p ct) W^(32c ct)] [W^(32 p) W_256^(2c)]^e
+    const unsigned x_a = 2u * (unsigned)lo16 * (unsigned)hi16, x_b = 32u * (unsigned)lo16; // < 512
+    const cplx<T> w_a = cmul(s_hi[x_a >> 8], s_lo[x_a & 255u]), w_b = cmul(s_hi[x_b >> 8], s_lo[x_b & 255u]);
+    for (unsigned it = 0;; it++) {
+        const int s = it % NST;
+        mbar_wait(&full[s], (it / NST) & 1);
+        const unsigned q = s_item[s];
+        if (q == 0xffffffffu)
+            break;
+        bool cols;
+        size_t f;
+        int tile;
+        real_decode(q, cols, f, tile);
+        cplx<T> *st = stage0 + (size_t)s * SLOT, *xbuf = st;
+        cplx<T> *sc = scratch + (f % REAL_RING) * RFRAME;
+        cplx<T> v[Cfg::E];
+        if (f >= n_frames) {
+            mbar_arrive(&empty[s]);
+            mbar_arrive(&done_bar[it % ND]);
+            continue;
+        }
+        if (cols) {
+            const int t = hi16, p = lo16;
+            // the tile is [256 rows][32 floats]: columns 2p, 2p + 1 of row a are one 8-byte element
+            const cplx<T> *rs = st + p;
+#pragma unroll
+            for (int e = 0; e < Cfg::E; e++)
+                v[e] = rs[(t + Cfg::S * e) * 16];
+            cta_sync<1, 256>(); // every thread has its points: the slot becomes the exchange buffer
+            cplx<T> *fs = xbuf + (size_t)p * PITCH;
+            fft_pass<Cfg, 0, T>(v, t, tw);
+#pragma unroll
+            for (int e = 0; e < Cfg::E; e++)
+                fs[fft_out_phys<Cfg, 0>(t, e)] = v[e];
+            cta_sync<1, 256>();
+#pragma unroll
+            for (int e = 0; e < Cfg::E; e++)
+                v[e] = fs[fft_read_phys<Cfg>(t, e)];
+            fft_pass<Cfg, 1, T>(v, t, tw); // v[e] = Z[k1], k1 = t + 16 e
+            // the mirror terms Z[256 - k1] sit in other threads of the transform: one more exchange, natural order
+            cta_sync<1, 256>(); // (everyone has read the previous exchange)
+#pragma unroll
+            for (int e = 0; e < Cfg::E; e++)
+                fs[Cfg::pad(t + 16 * e)] = v[e];
+            cta_sync<1, 256>();
+            // factors: first term and ratio for the even column; the odd column's are those times W_N^(k1) (a table look-up with
+            // two distinct addresses per warp)
+            const unsigned xt = 32u * (unsigned)tile * (unsigned)t;
+            cplx<T> w0 = cmul(w_a, cmul(s_hi[xt >> 8], s_lo[xt & 255u]));
+            w0 = cplx<T>{ w0.x * (T)0.5, w0.y * (T)0.5 }; // the 1/2 of the separation (exact)
+            const cplx<T> r1 = cmul(w_b, s_hi[2 * tile]);
+            const cplx<T> r2 = cmul(r1, r1), r3 = cmul(r2, r1), r4 = cmul(r2, r2);
+            const cplx<T> q1 = cmul(w0, r4);
+            cplx<T> *op = sc + 32 * tile + 2 * p;
+#pragma unroll
+            for (int e = 0; e <= 8; e++) {
+                if (e == 8 && t != 0)
+                    break; // k1 = 128 exists for t = 0 only
+                const int k1 = t + 16 * e;
+                const cplx<T> zm = fs[Cfg::pad((256 - k1) & 255)];
+                const cplx<T> a = v[e], b = cplx<T>{ zm.x, -zm.y };
+                const cplx<T> ye = a + b, d = a - b;
+                const cplx<T> yo = cplx<T>{ d.y, -d.x }; // -i (a - b)
+                const cplx<T> base = e < 4 ? w0 : (e < 8 ? q1 : cmul(q1, r4));
+                const cplx<T> we = (e & 3) == 0 ? base : cmul(base, (e & 3) == 1 ? r1 : (e & 3) == 2 ? r2 : r3);
+                const cplx<T> wo = cmul(we, s_lo[k1]);
+                const cplx<T> o0 = cmul(ye, we), o1 = cmul(yo, wo);
+                if constexpr (sizeof(T) == 4)
+                    *reinterpret_cast<float4 *>(op + (size_t)k1 * N2) = make_float4(o0.x, o0.y, o1.x, o1.y);
+                else {
+                    op[(size_t)k1 * N2] = o0;
+                    op[(size_t)k1 * N2 + 1] = o1;
+                }
+            }
+            fence_proxy_async();
+            mbar_arrive(&empty[s]);
+        } else {
+            const int t = lo16, row = hi16;
+            const bool last_tile = tile == REAL_RT - 1; // row 128 alone: only the first 2 KB of the slot were filled
+            const cplx<T> *gp = st + row * N2 + t;
+#pragma unroll
+            for (int e = 0; e < Cfg::E; e++)
+                v[e] = (last_tile && row != 0) ? cplx<T>{ 0, 0 } : gp[Cfg::S * e];
+            cta_sync<1, 256>();
+            if constexpr (sizeof(cplx<T>) == 8) { // the tile's lines of the ring are dead: drop them from L2
+                if (!last_tile || threadIdx.x < 16)
+                    asm volatile("discard.global.L2 [%0], 128;" ::"l"(sc + (size_t)(16 * tile) * N2 + (size_t)threadIdx.x * 16) : "memory");
+            }
+            fft_pass<Cfg, 0, T>(v, t, tw);
+            cplx<T> *fs = xbuf + (size_t)row * PITCH;
+#pragma unroll
+            for (int e = 0; e < Cfg::E; e++)
+                fs[fft_out_phys<Cfg, 0>(t, e)] = v[e];
+            cta_sync<1, 256>();
+            const int row2 = lo16, t2 = hi16;
+            const cplx<T> *rs = xbuf + (size_t)row2 * PITCH;
+#pragma unroll
+            for (int e = 0; e < Cfg::E; e++)
+                v[e] = rs[fft_read_phys<Cfg>(t2, e)];
+            fence_proxy_async();
+            mbar_arrive(&empty[s]);
+            fft_pass<Cfg, 1, T>(v, t2, tw);
+            const int k1 = 16 * tile + row2;
+            if (!last_tile || row2 == 0) {
+                cplx<T> *op = data + f * FRAME + k1;
+#pragma unroll
+                for (int e = 0; e < Cfg::E; e++)
+                    st_stream(op + (size_t)(t2 + Cfg::S * e) * N1, v[e]);
+                if (k1 != 0 && k1 != 128) { // X[N - k] = conj X[k]
+                    cplx<T> *mp = data + f * FRAME + (256 - k1);
+#pragma unroll
+                    for (int e = 0; e < Cfg::E; e++)
+                        st_stream(mp + (size_t)(255 - t2 - Cfg::S * e) * N1, cplx<T>{ v[e].x, -v[e].y });
+                }
+            }
+        }
+        mbar_arrive(&done_bar[it % ND]);
+    }
+}
+
 template <typename T, int N1>
 struct FusedTmaCfg {
     static constexpr int NST = SDSP_FUSED_TMA_NST, MINB = SDSP_FUSED_TMA_MINB;
 };
+
+// forward real-input frames of 65536 points (fp32): the half-work queue, fft_real64k_kernel
+static int launch_real64k(const FftPlan &p, void *data, const void *real_in, size_t n_frames, cudaStream_t stream)
+{
+    using T = float;
+    const size_t need = (1 + 2 * n_frames) * sizeof(unsigned);
+    FftPlan &mp = const_cast<FftPlan &>(p);
+    if (mp.fused_counter_bytes < need) {
+        if (mp.d_fused_counters)
+            cudaFree(mp.d_fused_counters);
+        mp.d_fused_counters = nullptr;
+        mp.fused_counter_bytes = 0;
+        if (cudaMalloc(&mp.d_fused_counters, need) != cudaSuccess) {
+            cudaGetLastError();
+            return set_error(SDSP_B200_ERR_OOM, "fft: cannot allocate %zu bytes of work-queue counters", need);
+        }
+        mp.fused_counter_bytes = need;
+    }
+    SDSP_CUDA(cudaMemsetAsync(mp.d_fused_counters, 0, need, stream));
+    unsigned *ctr = static_cast<unsigned *>(mp.d_fused_counters);
+    const cuuint64_t gdim[3] = { 256, 256, (cuuint64_t)n_frames };
+    const cuuint64_t gstride[2] = { 256 * sizeof(T), 256 * 256 * sizeof(T) };
+    const cuuint32_t box[3] = { 32, 256, 1 };
+    const cuuint32_t estr[3] = { 1, 1, 1 };
+    CUtensorMap map;
+    CUresult r = get_encode_fn()(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void *>(real_in), gdim, gstride, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return set_error(SDSP_B200_ERR_CUDA, "fft: cuTensorMapEncodeTiled failed with %d (real input, n=%u frames=%zu)", (int)r, p.n, n_frames);
+    const size_t items = (size_t)REAL_LAG * REAL_CT + n_frames * (REAL_CT + REAL_RT);
+    size_t grid = (size_t)p.sm_count * (size_t)p.real64k_ctas;
+    if (grid > items)
+        grid = items;
+    fft_real64k_kernel<T, SDSP_FUSED_TMA_MINB><<<(unsigned)grid, 288, p.real64k_smem, stream>>>(
+        map, reinterpret_cast<cplx<T> *>(data), reinterpret_cast<cplx<T> *>(p.d_scratch), reinterpret_cast<const cplx<T> *>(p.d_tw_rows),
+        reinterpret_cast<const cplx<T> *>(p.d_tw_hi), reinterpret_cast<const cplx<T> *>(p.d_tw_lo), ctr, ctr + 1, ctr + 1 + n_frames, n_frames);
+    SDSP_CUDA(cudaGetLastError());
+    return SDSP_B200_OK;
+}
 
 template <typename T, int N1>
 static int launch_fused_tma(const FftPlan &p, void *data, const void *real_in, size_t n_frames, cudaStream_t stream)
@@ -1800,6 +2106,10 @@ static int launch_fused_tma(const FftPlan &p, void *data, const void *real_in, s
     const void *src = real_in ? real_in : data;
     if (reinterpret_cast<uintptr_t>(src) % 16 != 0 || n_frames > 0x7fffffffu) // the tensor map needs a 16-byte-aligned base
         return launch_fused<T, N1>(p, data, real_in, n_frames, stream);
+    if constexpr (N1 == 256 && sizeof(T) == 4) {
+        if (real_in && p.real64k_ctas > 0 && p.direction == SDSP_B200_FORWARD && reinterpret_cast<uintptr_t>(data) % 16 == 0)
+            return launch_real64k(p, data, real_in, n_frames, stream);
+    }
     const size_t need = (1 + 2 * n_frames) * sizeof(unsigned);
     FftPlan &mp = const_cast<FftPlan &>(p);
     if (mp.fused_counter_bytes < need) {
@@ -1934,6 +2244,22 @@ static int setup_fused(FftPlan &p)
             }
             // two slots that double as exchange buffers: measured +1.5 % (2^16) / +3.6 % (2^15), -1.7 % at 2^17 (profiles/r02_fft_fused_variants.txt):
             // the default up to N1 = 256; SDSP_B200_FFT_FUSED_TMA=1 / 2 pins the one- / two-slot kernel
+            if constexpr (N1 == 256) { // forward real-input frames: the half-work queue (SDSP_B200_FFT_REAL64K=0 keeps the complex kernels)
+                const char *e = getenv("SDSP_B200_FFT_REAL64K");
+                if (!e || atoi(e) != 0) {
+                    auto rk = fft_real64k_kernel<T, MINB>;
+                    const size_t slot = ((size_t)16 * LargeStride<Cfg>::value + 15) / 16 * 16;
+                    const size_t rsmem = (2 * slot + 512) * sizeof(cplx<T>) + 128;
+                    int rocc = 0;
+                    if (cudaFuncSetAttribute(rk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem) == cudaSuccess &&
+                        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&rocc, rk, 288, rsmem) == cudaSuccess && rocc >= 1 &&
+                        (size_t)REAL_RING * REAL_ROWS * 256 <= p.scratch_frames * (size_t)N1 * 256) {
+                        p.real64k_ctas = rocc;
+                        p.real64k_smem = rsmem;
+                    }
+                    cudaGetLastError();
+                }
+            }
             const int mode = fused_tma_mode();
             if (mode == 2 || (mode == SDSP_FUSED_TMA_DEFAULT && !getenv("SDSP_B200_FFT_FUSED_TMA") && N1 <= 256)) {
                 auto tk2 = fft_fused_tma2_kernel<T, N1, MINB>;

@@ -185,6 +185,22 @@ def test_large_frames_many_frames_and_unsupported_sizes(prec):
     assert e.value.status == K.ERR_UNSUPPORTED
 
 
+def _check_conjugate_symmetry(y):
+    """Spectra of real 65536-point frames from fft_real64k_kernel: bins with k mod 256 in 1 .. 127 are computed, their mirrors
+    N - k are stored as the conjugate of the same registers (equal to the bit); the bins of rows 0 and 128 (k mod 256 in
+    {0, 128}) mirror into their own row and are each computed: symmetric to rounding."""
+    import torch
+
+    n = y.shape[1]
+    k = torch.arange(1, n, device=y.device)
+    mirror = torch.conj(y[:, n - k]).resolve_conj()
+    exact = (k % 256 != 0) & (k % 256 != 128)
+    assert torch.equal(y[:, k[exact]], mirror[:, exact])
+    rest = ~exact
+    scale = y.abs().amax(dim=1, keepdim=True)
+    assert float(((y[:, k[rest]] - mirror[:, rest]).abs() / scale).max()) <= 1e-5
+
+
 @pytest.mark.parametrize("prec", ["f32", "f64"])
 @pytest.mark.parametrize("n", [64, 1024, 4096, 16384, 32768, 65536, 131072])
 def test_real_input_frames_match_oracle(n, prec):
@@ -205,18 +221,24 @@ def test_real_input_frames_match_oracle(n, prec):
     # host buffers through the staging path give the same bits as the device call
     yh = plan.real(x.astype(np.float32 if prec == "f32" else np.float64))
     assert np.array_equal(yh, yd.cpu().numpy())
-    # and the same bits as the complex entry point fed (x, 0)
+    # and the same bits as the complex entry point fed (x, 0) -- except forward fp32 frames of 65536 points, which take the
+    # half-work kernel that exploits the conjugate symmetry of a real frame's spectrum (fft_real64k_kernel): same transform,
+    # different rounding, and X[N - k] == conj(X[k]) to the bit
     z = torch.complex(xd, torch.zeros_like(xd)).contiguous()
     plan(z)
     torch.cuda.synchronize()
-    assert torch.equal(z, yd)
+    if n == 65536 and prec == "f32":
+        assert rel_l2(yd.cpu().numpy(), z.cpu().numpy()) <= FFT_TOL[prec]
+        _check_conjugate_symmetry(yd)
+    else:
+        assert torch.equal(z, yd)
 
 
-@pytest.mark.parametrize("frames", [1, 2, 31, 32, 33, 47, 48, 49, 63, 64, 65, 95, 96, 97, 127, 129, 200])
+@pytest.mark.parametrize("frames", [1, 2, 31, 32, 33, 47, 48, 49, 63, 64, 65, 87, 88, 89, 95, 96, 97, 127, 129, 175, 176, 177, 200, 365])
 def test_fused_65536_kernel_at_the_edges_of_its_work_queue(frames):
     """The 65536-point kernel orders column and row tiles through a queue with a 48-frame lag and a 96-frame scratch ring
-    (fp32; 32 / 64 in the variant without the data-mover warp): frame counts below, at and just past those boundaries,
-    forward and reverse, complex and real input."""
+    (fp32; 32 / 64 in the variant without the data-mover warp; 88 / 176 in the real-input kernel): frame counts below, at and
+    just past those boundaries, forward and reverse, complex and real input."""
     torch = pytest.importorskip("torch")
     n = 65536
     g = torch.Generator(device="cuda").manual_seed(frames)
@@ -236,13 +258,21 @@ def test_fused_65536_kernel_at_the_edges_of_its_work_queue(frames):
     torch.cuda.synchronize()
     err = (y - x).abs().pow(2).sum(dim=1).sqrt() / x.abs().pow(2).sum(dim=1).sqrt()
     assert float(err.max()) <= 2 * FFT_TOL["f32"]
-    # real input, out of place: same bits as the complex entry point fed (x, 0)
+    # real input, out of place, forward: the half-work kernel (its own queue: 8 + 9 tiles per frame) against the complex entry point
+    # fed (x, 0), every frame; reverse plans keep the complex kernels: same bits
     xr = x.real.contiguous()
     z = torch.complex(xr, torch.zeros_like(xr)).contiguous()
     fwd(z)
     out = fwd.real(xr)
     torch.cuda.synchronize()
-    assert torch.equal(z, out)
+    err = (z - out).abs().pow(2).sum(dim=1).sqrt() / z.abs().pow(2).sum(dim=1).sqrt()
+    assert float(err.max()) <= FFT_TOL["f32"]
+    _check_conjugate_symmetry(out)
+    zi = torch.complex(xr, torch.zeros_like(xr)).contiguous()
+    inv(zi)
+    outi = inv.real(xr)
+    torch.cuda.synchronize()
+    assert torch.equal(zi, outi)
 
 
 _OTHER_QUEUE_SNIPPET = r"""
@@ -307,9 +337,9 @@ def test_host_buffers_in_slabs_match_the_device_resident_call(n, frames):
         got = x.copy()
         plan(got)
         assert np.array_equal(got, want)
+    # real frames through host buffers against the device-resident real-input call (same kernel: same bits)
     real = np.ascontiguousarray(x.real)
     spec = plan.real(real)
-    d2 = torch.from_numpy(real.astype(np.complex64)).cuda()
-    plan(d2)
+    d2 = plan.real(torch.from_numpy(real).cuda())
     torch.cuda.synchronize()
     assert np.array_equal(spec, d2.cpu().numpy())
