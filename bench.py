@@ -43,6 +43,8 @@ WORKLOADS = {
     "fft256_f32": dict(kind="fft", n=256, frames=1 << 20, precision="f32", bytes_per_sample=16),
     "fft64_f32": dict(kind="fft", n=64, frames=1 << 22, precision="f32", bytes_per_sample=16),
     "fft32768_f32": dict(kind="fft", n=32768, frames=8192, precision="f32", bytes_per_sample=16),
+    # real frames in (4 B/sample), complex spectra out (8 B/sample), out of place: config 5's transform on its own
+    "fftreal65536_f32": dict(kind="fft", n=65536, frames=4096, precision="f32", bytes_per_sample=12, real_input=True),
     "fft131072_f32": dict(kind="fft", n=131072, frames=2048, precision="f32", bytes_per_sample=16),
     "fft262144_f32": dict(kind="fft", n=262144, frames=1024, precision="f32", bytes_per_sample=16),
     "fft16384_f32": dict(kind="fft", n=16384, frames=16384, precision="f32", bytes_per_sample=16),
@@ -233,20 +235,34 @@ class FftWorkload:
         self.samples_per_step = self.frames * self.n
         self.step_no = 0
         self.stream = torch.cuda.current_stream().cuda_stream
+        self.real_input = bool(spec.get("real_input"))
+        if self.real_input:
+            self.real = torch.randn(self.frames, self.n, device="cuda", generator=g, dtype=self.rdtype)
 
     def describe(self):
-        return self.fwd.describe()
+        return ("real frames in, spectra out: " if self.real_input else "") + self.fwd.describe()
 
     def launches_per_step(self):
         return self.fwd.launches(self.frames)
 
     def step(self):
+        if self.real_input:
+            self.fwd.exec_real_ptr(self.real.data_ptr(), self.data.data_ptr(), self.frames, self.K.PTR_DEVICE, self.stream)
+            self.step_no += 1
+            return
         plan = self.fwd if self.step_no % 2 == 0 else self.inv
         plan.exec_ptr(self.data.data_ptr(), self.frames, self.K.PTR_DEVICE, self.stream)
         self.step_no += 1
 
     def self_check(self):
-        """After an even number of steps the batch is the input again (forward then reverse)."""
+        """After an even number of steps the batch is the input again (forward then reverse).  Real input: sampled spectra
+        against torch.fft of the same frames."""
+        if self.real_input:
+            torch = self.torch
+            torch.cuda.synchronize()
+            ref = torch.fft.fft(self.real[self.check_idx].double())
+            got = torch.view_as_complex(self.data[self.check_idx]).to(torch.complex128)
+            return float(((got - ref).abs().pow(2).sum(dim=1).sqrt() / ref.abs().pow(2).sum(dim=1).sqrt()).max())
         if self.step_no % 2:
             self.step()
         self.torch.cuda.synchronize()

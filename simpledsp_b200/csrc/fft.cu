@@ -1803,7 +1803,10 @@ __global__ void __launch_bounds__(288, MINB)
 // 17 items per frame instead of 32, the output is conjugate-symmetric to the bit.  Queue order: column tiles of frame f + LAG, then
 // row tiles of frame f; a row tile waits for its frame's 8 column tiles, a column tile for the 9 row tiles of the ring slot's
 // previous tenant -- both hold smaller tickets.
-constexpr int REAL_CT = 8, REAL_RT = 9, REAL_LAG = 88, REAL_RING = 176, REAL_ROWS = 129;
+#ifndef SDSP_REAL_LAG
+#define SDSP_REAL_LAG 64 // frames between a frame's column tiles and its row tiles (x 17 items; the ring holds twice that, 33 MB; 48 / 88 / 94 measured)
+#endif
+constexpr int REAL_CT = 8, REAL_RT = 9, REAL_LAG = SDSP_REAL_LAG, REAL_RING = 2 * SDSP_REAL_LAG, REAL_ROWS = 129;
 __host__ __device__ __forceinline__ void real_decode(size_t q, bool &cols, size_t &f, int &tile)
 {
     if (q < (size_t)REAL_LAG * REAL_CT) {

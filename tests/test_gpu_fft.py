@@ -234,10 +234,10 @@ def test_real_input_frames_match_oracle(n, prec):
         assert torch.equal(z, yd)
 
 
-@pytest.mark.parametrize("frames", [1, 2, 31, 32, 33, 47, 48, 49, 63, 64, 65, 87, 88, 89, 95, 96, 97, 127, 129, 175, 176, 177, 200, 365])
+@pytest.mark.parametrize("frames", [1, 2, 31, 32, 33, 47, 48, 49, 63, 64, 65, 87, 88, 89, 95, 96, 97, 127, 128, 129, 175, 176, 177, 200, 365])
 def test_fused_65536_kernel_at_the_edges_of_its_work_queue(frames):
     """The 65536-point kernel orders column and row tiles through a queue with a 48-frame lag and a 96-frame scratch ring
-    (fp32; 32 / 64 in the variant without the data-mover warp; 88 / 176 in the real-input kernel): frame counts below, at and
+    (fp32; 32 / 64 in the variant without the data-mover warp; 64 / 128 in the real-input kernel): frame counts below, at and
     just past those boundaries, forward and reverse, complex and real input."""
     torch = pytest.importorskip("torch")
     n = 65536
