@@ -1,10 +1,8 @@
 mkdir -p gpurun_out
-run() { timeout 300 python bench.py --steps $2 --warmup 3 --no-e2e --no-cpu --no-secondary --workload $1 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$3', d['config']['workload'], round(d['ms_per_step'],4), round(d['value']), round(d['roofline']['achieved'],1), round(d['roofline']['frac'],4), d['self_check'], d['clocks']['sm_mhz'], d['clocks']['reasons'])" >> gpurun_out/r02_fft_real64k_lag.log 2>&1; }
-rm -f gpurun_out/r02_fft_real64k_lag.log
+run() { timeout 300 python bench.py --steps $2 --warmup 3 --no-e2e --no-cpu --no-secondary --workload $1 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$3', d['config']['workload'], round(d['ms_per_step'],4), round(d['value']), round(d['roofline']['achieved'],1), round(d['roofline']['frac'],4), d['self_check'], d['clocks']['sm_mhz'], d['clocks']['reasons'])" >> gpurun_out/r02_fft_real64k_tb.log 2>&1; }
+rm -f gpurun_out/r02_fft_real64k_tb.log
 for rep in 1 2; do
-SDSP_B200_FFT_REAL64K=0 run fftreal65536_f32 20 "complex-kernels"
-for lib in lib lib_rl48 lib_rl64 lib_rl94; do
+for lib in lib lib_tb2 lib_tb4; do
 SDSP_B200_LIB=$PWD/simpledsp_b200/$lib/libsdsp_b200.so run fftreal65536_f32 20 "$lib"
 done; done
-cat gpurun_out/r02_fft_real64k_lag.log
-timeout 600 python -m pytest tests/test_gpu_fft.py -m gpu -q --timeout 300 -x -k "host_buffers" 2>&1 | tail -3
+cat gpurun_out/r02_fft_real64k_tb.log
