@@ -301,6 +301,84 @@ __global__ void __launch_bounds__(THREADS, MINB)
     }
 }
 
+
+// =================================================================================================
+// Real frames in, HALF spectra out (sdsp_b200_fft_exec_r2c): a real frame of N = 2M samples is read as M complex numbers
+// z[n] = x[2n] + i x[2n + 1] -- the frame as it lies in memory -- transformed by the M-point kernel code above, and the bins
+// k = 0 .. M of the N-point spectrum come out of one more exchange (every bin needs its mirror Z[M - k]):
+//   X[k] = (Z[k] + conj Z[M - k]) / 2  +  W_N^k (-i) (Z[k] - conj Z[M - k]) / 2,      X[M] = Re Z[0] - Im Z[0].
+// 4 bytes in and 4 bytes out per real sample against 8 + 8 for the reference's calling convention (real part filled, imaginary
+// part zero: test/testFFT.cpp:24, :86) and 4 + 8 for sdsp_b200_fft_exec_real.  W_N^k = W_N^t W_N^(S e) for k = t + S e: the first
+// factor is a per-thread constant (one table look-up per launch), the second is W_(2E)^e, a compile-time index into a 64th-root
+// table in constant memory.  The bins above M are the conjugates of those below (not written).
+__constant__ float2 c_w64_f32[32];
+__constant__ double2 c_w64_f64[32];
+template <typename T>
+__device__ __forceinline__ cplx<T> w64(int j)
+{
+    if constexpr (sizeof(T) == 4)
+        return cplx<T>{ c_w64_f32[j].x, c_w64_f32[j].y };
+    else
+        return cplx<T>{ c_w64_f64[j].x, c_w64_f64[j].y };
+}
+
+template <class Cfg, typename T, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+    fft_r2c_kernel(const cplx<T> *__restrict__ in, cplx<T> *__restrict__ out, const cplx<T> *__restrict__ tw, const cplx<T> *__restrict__ tw_n,
+                   size_t n_frames, int prefetch)
+{
+    constexpr int FPC = THREADS / Cfg::TPF, M = Cfg::N;
+    static_assert(THREADS % Cfg::TPF == 0 && FPC >= 1, "block must hold whole frames");
+    static_assert(32 % Cfg::E == 0, "the 64th-root table covers 2, 4, 8, 16 or 32 points per thread");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx<T> *smem = reinterpret_cast<cplx<T> *>(smem_raw);
+    const int fl = threadIdx.x / Cfg::TPF;
+    const int t = threadIdx.x % Cfg::TPF;
+    cplx<T> *fs = smem + (size_t)fl * Cfg::PADDED_N;
+    const size_t groups = (n_frames + FPC - 1) / FPC;
+    const cplx<T> wt = tw_n[t]; // W_N^t
+
+    for (size_t g = blockIdx.x; g < groups; g += gridDim.x) {
+        const size_t frame = g * FPC + fl;
+        const bool active = frame < n_frames;
+        if (prefetch && threadIdx.x == 0 && g + gridDim.x < groups) {
+            const size_t nf = (g + gridDim.x) * FPC;
+            const size_t cnt = (n_frames - nf) < (size_t)FPC ? (n_frames - nf) : (size_t)FPC;
+            prefetch_l2_bulk(in + nf * (size_t)M, (unsigned)(cnt * M * sizeof(cplx<T>)));
+        }
+        cplx<T> v[Cfg::E];
+        const cplx<T> *gp = in + frame * (size_t)M + t;
+#pragma unroll
+        for (int e = 0; e < Cfg::E; e++)
+            v[e] = active ? ld_stream(gp + Cfg::S * e) : cplx<T>{ 0, 0 };
+        fft_kernel_passes<Cfg, T, THREADS, MINB, 0, false>(v, fs, tw, t, nullptr);
+        // v[e] = Z[t + S e].  The mirror terms through the exchange buffer in natural order (reads run downwards: no padding needed)
+        if constexpr (Cfg::NPASS > 1)
+            __syncthreads(); // everyone has read the last exchange
+#pragma unroll
+        for (int e = 0; e < Cfg::E; e++)
+            fs[t + Cfg::S * e] = v[e];
+        __syncthreads();
+        if (active) {
+            cplx<T> *op = out + frame * (size_t)(M + 1);
+#pragma unroll
+            for (int e = 0; e < Cfg::E; e++) {
+                const int k = t + Cfg::S * e;
+                const cplx<T> zm = fs[(M - k) & (M - 1)]; // k = 0 mirrors into itself
+                const cplx<T> a = v[e], b = cplx<T>{ zm.x, -zm.y };
+                const cplx<T> ye = a + b, d = a - b;
+                const cplx<T> yo = cplx<T>{ d.y, -d.x }; // -i (a - b)
+                const cplx<T> w = e == 0 ? wt : cmul(wt, w64<T>(e * (32 / Cfg::E)));
+                const cplx<T> x = ye + cmul(yo, w);
+                st_stream(op + k, cplx<T>{ (T)0.5 * x.x, (T)0.5 * x.y });
+            }
+            if (t == 0)
+                st_stream(op + M, cplx<T>{ v[0].x - v[0].y, (T)0 });
+        }
+        __syncthreads(); // the mirror terms have been read before the next group's first exchange
+    }
+}
+
 // =================================================================================================
 // digit reversal on the device (reference fft.h:217-236).  Base 2: bit reversal of the log2(n) low
 // bits; base 4: the same with the two bits of every digit kept in order.
@@ -2373,6 +2451,26 @@ SDSP_FFT_CFG(12, 256, 3, 4096, 16, 16, 16, 16)
 SDSP_FFT_CFG(13, 512, 2, 8192, 16, 16, 16, 16, 2)
 SDSP_FFT_CFG(14, 1024, 1, 16384, 16, 16, 16, 16, 4)
 #undef SDSP_FFT_CFG
+// fp32 frames of 8192 / 16384 points: 32 points per thread and a radix-32 first pass make them three passes (two exchanges through
+// shared memory per sample, like the 4096-point frames) instead of four (three exchanges).  These kernels sit at the L1 / shared-memory
+// data path's limit of about 64 B per cycle and SM, so the fourth crossing is what kept them at 0.68 / 0.64.
+struct CfgR32_13 {
+    using type = FftCfg<8192, 32, 32, 16, 16, 1, 5>;
+    static constexpr int THREADS = 256, MINB = 2;
+};
+struct CfgR32_14 {
+    using type = FftCfg<16384, 32, 32, 32, 16, 1, 5>;
+    static constexpr int THREADS = 512, MINB = 1;
+};
+static bool fft_r32_enabled() // SDSP_B200_FFT_R32=0: the four-pass, 16-points-per-thread kernels (comparison aid)
+{
+    static int on = -1;
+    if (on < 0) {
+        const char *e = getenv("SDSP_B200_FFT_R32");
+        on = e ? atoi(e) : 1;
+    }
+    return on != 0;
+}
 
 static constexpr int MAX_LOG2N_F32 = 14;
 static constexpr int MAX_LOG2N_F64 = 13;
@@ -2413,8 +2511,22 @@ static int setup_for(FftPlan &p)
             }
         }
     }
-    if (p.precision == SDSP_B200_F32)
+    if (p.precision == SDSP_B200_F32) {
+        if constexpr (LG == 13) {
+            if (fft_r32_enabled())
+                return setup_cta<CfgR32_13::type, float, CfgR32_13::THREADS, CfgR32_13::MINB>(p);
+        }
+        if constexpr (LG == 14) {
+            if (fft_r32_enabled()) {
+                const int rc = setup_cta<CfgR32_14::type, float, CfgR32_14::THREADS, CfgR32_14::MINB>(p);
+                static const bool alias = getenv("SDSP_B200_FFT_R32_ALIAS") && atoi(getenv("SDSP_B200_FFT_R32_ALIAS")) != 0;
+                if (rc == SDSP_B200_OK && alias)
+                    return enable_alias<CfgR32_14::type, float, CfgR32_14::THREADS, CfgR32_14::MINB>(p);
+                return rc;
+            }
+        }
         return setup_cta<typename C::type, float, C::THREADS, C::MINB>(p);
+    }
     if constexpr (LG <= MAX_LOG2N_F64)
     {
         constexpr int MB = LG == 13 ? 1 : (C::MINB > 2 ? 2 : C::MINB); // (8192 points fp64: 128 registers, one CTA)
@@ -2434,9 +2546,14 @@ template <int LG>
 static int emulate_for(int precision, bool inverse, void *frame)
 {
     using C = CfgFor<LG>;
-    if (precision == SDSP_B200_F32)
-        emulate_cfg<typename C::type, float>(frame, inverse);
-    else
+    if (precision == SDSP_B200_F32) {
+        if (LG == 13 && fft_r32_enabled())
+            emulate_cfg<CfgR32_13::type, float>(frame, inverse);
+        else if (LG == 14 && fft_r32_enabled())
+            emulate_cfg<CfgR32_14::type, float>(frame, inverse);
+        else
+            emulate_cfg<typename C::type, float>(frame, inverse);
+    } else
         emulate_cfg<typename C::type, double>(frame, inverse);
     return SDSP_B200_OK;
 }

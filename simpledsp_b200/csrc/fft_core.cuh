@@ -31,7 +31,9 @@ namespace sdsp_b200
 {
 // ------------------------------------------------------------------------------------------------
 // factorisation of one frame
-template <int N_, int E_, int R0_, int R1_ = 1, int R2_ = 1, int R3_ = 1>
+// PADSH_: the exchange buffer carries one spare element after every 2^PADSH_ (16 for the radix-16 factorisations; 32 where the first
+// pass is a radix-32 one, whose writes stride by 32 elements)
+template <int N_, int E_, int R0_, int R1_ = 1, int R2_ = 1, int R3_ = 1, int PADSH_ = 4>
 struct FftCfg {
     static constexpr int N = N_;  // points per frame
     static constexpr int E = E_;  // points per thread
@@ -63,11 +65,12 @@ struct FftCfg {
     }
     // shared-memory exchange: one spare element after every 16 keeps both the strided writes of a pass
     // and the unit-stride reads of the next one free of bank conflicts (8-byte and 16-byte elements)
+    static constexpr int PADSH = PADSH_, PADW = 1 << PADSH_;
     SDSP_HD static constexpr int pad(int pos)
     {
-        return pos + (pos >> 4);
+        return pos + (pos >> PADSH_);
     }
-    static constexpr int PADDED_N = N_ + (N_ >> 4);
+    static constexpr int PADDED_N = N_ + (N_ >> PADSH_);
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -189,6 +192,52 @@ struct Dft<16, T> {
     }
 };
 
+template <typename T>
+struct Dft<32, T> {
+    // decimation in frequency once, then two 16-point transforms: even outputs from a[j] + a[j + 16], odd outputs from
+    // (a[j] - a[j + 16]) W32^j
+    SDSP_HD static void run(cplx<T> (&a)[32])
+    {
+        constexpr T h = FftConst<T>::SQRT1_2;
+        constexpr T c1 = (T)0.98078528040323044912618223613423903697L, s1 = (T)0.19509032201612826784828486847702224093L;
+        constexpr T c2 = FftConst<T>::COS_PI_8, s2 = FftConst<T>::SIN_PI_8;
+        constexpr T c3 = (T)0.83146961230254523707878837761790575673L, s3 = (T)0.55557023301960222474283081394853287438L;
+        cplx<T> ev[16], od[16];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int j = 0; j < 16; j++) {
+            ev[j] = a[j] + a[j + 16];
+            od[j] = a[j] - a[j + 16];
+        }
+        // W32^j = (cos(pi j / 16), -sin(pi j / 16)), j = 1 .. 7; W32^(8 + j) = -i W32^j
+        od[1] = cmul(od[1], cplx<T>{ c1, -s1 });
+        od[2] = cmul(od[2], cplx<T>{ c2, -s2 });
+        od[3] = cmul(od[3], cplx<T>{ c3, -s3 });
+        od[4] = cplx<T>{ h * (od[4].x + od[4].y), h * (od[4].y - od[4].x) };
+        od[5] = cmul(od[5], cplx<T>{ s3, -c3 });
+        od[6] = cmul(od[6], cplx<T>{ s2, -c2 });
+        od[7] = cmul(od[7], cplx<T>{ s1, -c1 });
+        od[8] = mul_neg_i(od[8]);
+        od[9] = cmul(od[9], cplx<T>{ -s1, -c1 });
+        od[10] = cmul(od[10], cplx<T>{ -s2, -c2 });
+        od[11] = cmul(od[11], cplx<T>{ -s3, -c3 });
+        od[12] = cplx<T>{ h * (od[12].y - od[12].x), -(h * (od[12].x + od[12].y)) };
+        od[13] = cmul(od[13], cplx<T>{ -c3, -s3 });
+        od[14] = cmul(od[14], cplx<T>{ -c2, -s2 });
+        od[15] = cmul(od[15], cplx<T>{ -c1, -s1 });
+        Dft<16, T>::run(ev);
+        Dft<16, T>::run(od);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int j = 0; j < 16; j++) {
+            a[2 * j] = ev[j];
+            a[2 * j + 1] = od[j];
+        }
+    }
+};
+
 // ------------------------------------------------------------------------------------------------
 // one pass over the E points a thread holds.
 //   in : v[e] = element at position t + S*e of the current arrangement
@@ -216,7 +265,27 @@ SDSP_HD void fft_pass(cplx<T> (&v)[Cfg::E], int t, const cplx<T> *__restrict__ t
             const int b = t + Cfg::S * q;
             const int m = b / PP;
             const cplx<T> *row = tw + Cfg::tw_offset(P) + m;
-            if ((sizeof(T) == 8 || SDSP_FFT_TW4_F32) && R == 16 && M >= SDSP_FFT_TW4_MIN_M) {
+            if (R == 32 && M >= SDSP_FFT_TW4_MIN_M) {
+                // radix-32 first pass (fp32 frames of 8192 / 16384 points): the same idea with eight loads (k = 1, 4, 8 .. 28) and
+                // 23 products, three roundings deep at most
+                const cplx<T> w1 = row[0];
+                const cplx<T> w2 = cmul(w1, w1), w3 = cmul(w2, w1);
+                const cplx<T> lo[4] = { w1, w1, w2, w3 };
+                cplx<T> hi[8];
+                hi[0] = w1;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+                for (int j = 1; j < 8; j++)
+                    hi[j] = row[(4 * j - 1) * M];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+                for (int k = 1; k < R; k++) {
+                    const cplx<T> w = k < 4 ? lo[k] : (k % 4 == 0 ? hi[k / 4] : cmul(hi[k / 4], lo[k % 4]));
+                    a[k] = cmul(a[k], w);
+                }
+            } else if ((sizeof(T) == 8 || SDSP_FFT_TW4_F32) && R == 16 && M >= SDSP_FFT_TW4_MIN_M) {
                 // fp64 frames of 4096 points and more, first pass: the 15 factors W^(m k) of a butterfly come from a table of
                 // 15 x M x 16 bytes (61 KB at 4096 points) that does not stay in what the exchange buffers leave of L1, and
                 // loading them all costs as many bytes from L2 as the frame itself.  Four of them are loaded (k = 1, 4, 8, 12),
@@ -267,8 +336,8 @@ SDSP_HD int fft_out_pos(int t, int e)
 template <class Cfg>
 SDSP_HD int fft_read_phys(int t, int e)
 {
-    if (Cfg::S % 16 == 0)
-        return t + (t >> 4) + e * (Cfg::S + Cfg::S / 16);
+    if (Cfg::S % Cfg::PADW == 0)
+        return t + (t >> Cfg::PADSH) + e * (Cfg::S + Cfg::S / Cfg::PADW);
     return Cfg::pad(t + Cfg::S * e);
 }
 template <class Cfg, int P>
@@ -277,12 +346,18 @@ SDSP_HD int fft_out_phys(int t, int e)
     constexpr int R = Cfg::radix(P);
     constexpr int G = Cfg::E / R;
     constexpr int PP = Cfg::pprev(P);
-    if (G == 1 && PP % 16 == 0) { // b = t, K = t % PP, m = t / PP, k = e
+    constexpr int W = Cfg::PADW;
+    if (G == 1 && PP % W == 0) { // b = t, K = t % PP, m = t / PP, k = e
         const int K = t % PP, m = t / PP;
-        return K + (K >> 4) + (PP * R + PP * R / 16) * m + e * (PP + PP / 16);
+        return K + (K >> Cfg::PADSH) + (PP * R + PP * R / W) * m + e * (PP + PP / W);
     }
-    if (G == 1 && PP == 1 && R == 16) // pos = e + 16 t
-        return 17 * t + e;
+    if (G == 1 && PP == 1 && R == W) // pos = e + R t
+        return (R + 1) * t + e;
+    if (G > 1 && PP % W == 0 && Cfg::S % PP == 0) { // b = t + S q: K = t % PP, m = t / PP + (S / PP) q, with q = e % G, k = e / G
+        const int K = t % PP, m = t / PP;
+        const int q = e % G, k = e / G;
+        return K + (K >> Cfg::PADSH) + (PP * R + PP * R / W) * m + (PP * R + PP * R / W) * (Cfg::S / PP) * q + k * (PP + PP / W);
+    }
     return Cfg::pad(fft_out_pos<Cfg, P>(t, e));
 }
 
