@@ -45,6 +45,10 @@ WORKLOADS = {
     "fft32768_f32": dict(kind="fft", n=32768, frames=8192, precision="f32", bytes_per_sample=16),
     # real frames in (4 B/sample), complex spectra out (8 B/sample), out of place: config 5's transform on its own
     "fftreal65536_f32": dict(kind="fft", n=65536, frames=4096, precision="f32", bytes_per_sample=12, real_input=True),
+    # real frames in, half spectra out (sdsp_b200_fft_exec_r2c): 4 + 4 bytes per real sample
+    "fftr2c4096_f32": dict(kind="fft", n=4096, frames=131072, precision="f32", bytes_per_sample=8, real_input=True, half=True),
+    "fftr2c4096_f64": dict(kind="fft", n=4096, frames=65536, precision="f64", bytes_per_sample=16, real_input=True, half=True),
+    "fftr2c65536_f32": dict(kind="fft", n=65536, frames=4096, precision="f32", bytes_per_sample=8, real_input=True, half=True),
     "fft131072_f32": dict(kind="fft", n=131072, frames=2048, precision="f32", bytes_per_sample=16),
     "fft262144_f32": dict(kind="fft", n=262144, frames=1024, precision="f32", bytes_per_sample=16),
     "fft16384_f32": dict(kind="fft", n=16384, frames=16384, precision="f32", bytes_per_sample=16),
@@ -229,7 +233,11 @@ class FftWorkload:
         self.fwd = S.FftPlan(self.n, self.radix, self.prec, K.FORWARD, device)
         self.inv = S.FftPlan(self.n, self.radix, self.prec, K.REVERSE, device)
         g = torch.Generator(device="cuda").manual_seed(1234 + device)
-        self.data = torch.randn(self.frames, self.n, 2, device="cuda", generator=g, dtype=self.rdtype)
+        self.half = bool(spec.get("half"))
+        if self.half:  # half spectra out: frames of n/2 + 1 bins
+            self.data = torch.zeros(self.frames, self.n // 2 + 1, 2, device="cuda", dtype=self.rdtype)
+        else:
+            self.data = torch.randn(self.frames, self.n, 2, device="cuda", generator=g, dtype=self.rdtype)
         self.check_idx = torch.linspace(0, self.frames - 1, 32).long().cuda()
         self.orig = self.data[self.check_idx].clone()
         self.samples_per_step = self.frames * self.n
@@ -240,12 +248,19 @@ class FftWorkload:
             self.real = torch.randn(self.frames, self.n, device="cuda", generator=g, dtype=self.rdtype)
 
     def describe(self):
+        if self.half:
+            return "real frames in, half spectra (n/2 + 1 bins) out: the n/2-point configuration of: " + self.S.FftPlan(
+                self.n // 2, 2, self.prec, self.K.FORWARD, self.fwd.device).describe()
         return ("real frames in, spectra out: " if self.real_input else "") + self.fwd.describe()
 
     def launches_per_step(self):
         return self.fwd.launches(self.frames)
 
     def step(self):
+        if self.half:
+            self.fwd.exec_r2c_ptr(self.real.data_ptr(), self.data.data_ptr(), self.frames, self.K.PTR_DEVICE, self.stream)
+            self.step_no += 1
+            return
         if self.real_input:
             self.fwd.exec_real_ptr(self.real.data_ptr(), self.data.data_ptr(), self.frames, self.K.PTR_DEVICE, self.stream)
             self.step_no += 1
@@ -260,7 +275,7 @@ class FftWorkload:
         if self.real_input:
             torch = self.torch
             torch.cuda.synchronize()
-            ref = torch.fft.fft(self.real[self.check_idx].double())
+            ref = (torch.fft.rfft if self.half else torch.fft.fft)(self.real[self.check_idx].double())
             got = torch.view_as_complex(self.data[self.check_idx]).to(torch.complex128)
             return float(((got - ref).abs().pow(2).sum(dim=1).sqrt() / ref.abs().pow(2).sum(dim=1).sqrt()).max())
         if self.step_no % 2:
@@ -274,6 +289,8 @@ class FftWorkload:
     def e2e_prepare(self):
         import simpledsp_b200._capi as K
 
+        if self.half:
+            return self._e2e_prepare_half()
         nbytes = self.frames * self.n * 2 * (4 if self.prec == K.F32 else 8)
         ptr = C.c_void_p()
         K.check(K.lib().sdsp_b200_host_alloc(C.byref(ptr), nbytes))
@@ -289,12 +306,37 @@ class FftWorkload:
         self.e2e_steps_done = 0
         return nbytes, nbytes
 
+    def _e2e_prepare_half(self):
+        """Real frames in pinned host memory -> half spectra in pinned host memory through FftPlan.half_spectrum."""
+        import simpledsp_b200._capi as K
+
+        es = 4 if self.prec == K.F32 else 8
+        in_bytes, out_bytes = self.frames * self.n * es, self.frames * (self.n // 2 + 1) * 2 * es
+        self._pinned, self._pinned_out = C.c_void_p(), C.c_void_p()
+        K.check(K.lib().sdsp_b200_host_alloc(C.byref(self._pinned), in_bytes))
+        K.check(K.lib().sdsp_b200_host_alloc(C.byref(self._pinned_out), out_bytes))
+        rdt, cdt = (np.float32, np.complex64) if self.prec == K.F32 else (np.float64, np.complex128)
+        self.host = np.frombuffer((C.c_char * in_bytes).from_address(self._pinned.value), dtype=rdt).reshape(self.frames, self.n)
+        self.host_out = np.frombuffer((C.c_char * out_bytes).from_address(self._pinned_out.value), dtype=cdt).reshape(self.frames, self.n // 2 + 1)
+        blk = np.random.default_rng(99).standard_normal((1024, self.n)).astype(rdt)
+        for i in range(0, self.frames, 1024):
+            self.host[i:i + 1024] = blk[: min(1024, self.frames - i)]
+        self.e2e_steps_done = 0
+        return in_bytes, out_bytes
+
     def e2e_step(self):
+        if self.half:
+            self.fwd.half_spectrum(self.host, out=self.host_out)
+            self.e2e_steps_done += 1
+            return
         plan = self.fwd if self.e2e_steps_done % 2 == 0 else self.inv
         plan(self.host)  # public API on a host array: H2D, transform, D2H, synchronous
         self.e2e_steps_done += 1
 
     def e2e_check(self):
+        if self.half:
+            ref = np.fft.rfft(self.host[-4:].astype(np.float64), axis=1)
+            return float(np.linalg.norm(self.host_out[-4:] - ref) / np.linalg.norm(ref))
         if self.e2e_steps_done % 2:
             self.e2e_step()
         err = np.linalg.norm(self.host[:4] - self.host_first) / np.linalg.norm(self.host_first)
@@ -305,6 +347,9 @@ class FftWorkload:
 
         self.host = None
         K.lib().sdsp_b200_host_free(self._pinned)
+        if self.half:
+            self.host_out = None
+            K.lib().sdsp_b200_host_free(self._pinned_out)
 
 
 class IirWorkload:
@@ -572,8 +617,9 @@ def run_reference(args, spec, workload_name):
 
 
 # --------------------------------------------------------------------------------------------------
-SECONDARY = ("fft4096_f64", "iir16384_f32", "iir16384_f32_scan", "iir4096_f32", "iirscan_f64", "fft65536_f32", "pipeline_cfg5_f32")
-E2E_SECONDARY = ("fft4096_f64", "iir16384_f32")
+SECONDARY = ("fft4096_f64", "iir16384_f32", "iir16384_f32_scan", "iir4096_f32", "iirscan_f64", "fft65536_f32", "pipeline_cfg5_f32",
+             "fft8192_f32", "fft16384_f32", "fftr2c4096_f32")
+E2E_SECONDARY = ("fft4096_f64", "iir16384_f32", "fftr2c4096_f32")
 
 
 def main():
@@ -660,7 +706,8 @@ def main():
         err = wl.e2e_check()
         samples = getattr(wl, "e2e_samples_per_step", wl.samples_per_step)
         wl.e2e_release()
-        api = ("simpledsp_b200.FftPlan.__call__(numpy view of pinned host memory) -> sdsp_b200_fft_exec(PTR_HOST)" if spec["kind"] == "fft" else
+        api = ("simpledsp_b200.FftPlan.half_spectrum(numpy views of pinned host memory) -> sdsp_b200_fft_exec_r2c(PTR_HOST)" if spec.get("half") else
+               "simpledsp_b200.FftPlan.__call__(numpy view of pinned host memory) -> sdsp_b200_fft_exec(PTR_HOST)" if spec["kind"] == "fft" else
                "simpledsp_b200.IirBank.process_ptr(pinned host memory) -> sdsp_b200_iir_bank_process(PTR_HOST), staged in chunks of time")
         return {"value": samples * e2e_steps * world / e2e_s / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3, "samples_per_step": samples,

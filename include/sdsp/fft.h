@@ -110,7 +110,7 @@ namespace detail
         check(sdsp_b200_fft_exec(h->plan, frames, n_frames, ptr_kind, stream), "sdsp_b200_fft_exec");
     }
 
-    template <class T, int RADIX, typename S>
+    template <class T, int RADIX, typename S, bool HALF = false>
     void run_real(const S *real_frames, std::complex<S> *spectra, uint32_t n, size_t n_frames, int ptr_kind, void *stream)
     {
         thread_local std::vector<std::pair<uint32_t, std::unique_ptr<plan_holder>>> cache;
@@ -122,7 +122,10 @@ namespace detail
             cache.emplace_back(n, std::make_unique<plan_holder>(n, RADIX, precision_of<S>(), T::Direction()));
             h = cache.back().second.get();
         }
-        check(sdsp_b200_fft_exec_real(h->plan, real_frames, spectra, n_frames, ptr_kind, stream), "sdsp_b200_fft_exec_real");
+        if (HALF)
+            check(sdsp_b200_fft_exec_r2c(h->plan, real_frames, spectra, n_frames, ptr_kind, stream), "sdsp_b200_fft_exec_r2c");
+        else
+            check(sdsp_b200_fft_exec_real(h->plan, real_frames, spectra, n_frames, ptr_kind, stream), "sdsp_b200_fft_exec_real");
     }
 } // namespace detail
 
@@ -351,5 +354,17 @@ template <class T = forward_fft, typename S>
 void fft_radix4_real(const S *real_frames, std::complex<S> *spectra, size_t n, size_t n_frames)
 {
     detail::run_real<T, 4, S>(real_frames, spectra, static_cast<uint32_t>(n), n_frames, SDSP_B200_PTR_HOST, nullptr);
+}
+// real frames in, HALF spectra out: bins 0 .. n/2 of each frame (n/2 + 1 values, frames n/2 + 1 values apart); the rest of the
+// spectrum of a real signal is the conjugate mirror, X[n - k] = conj X[k].  Half the bytes of the calls above in either direction.
+template <typename S>
+void fft_half_spectrum(const S *real_frames, std::complex<S> *half_spectra, size_t n, size_t n_frames)
+{
+    detail::run_real<forward_fft, 2, S, true>(real_frames, half_spectra, static_cast<uint32_t>(n), n_frames, SDSP_B200_PTR_HOST, nullptr);
+}
+template <typename S>
+void fft_half_spectrum_device(const S *real_frames, std::complex<S> *half_spectra, size_t n, size_t n_frames, void *stream = nullptr)
+{
+    detail::run_real<forward_fft, 2, S, true>(real_frames, half_spectra, static_cast<uint32_t>(n), n_frames, SDSP_B200_PTR_DEVICE, stream);
 }
 } // namespace sdsp

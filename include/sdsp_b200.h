@@ -117,6 +117,13 @@ int sdsp_b200_fft_exec(sdsp_b200_fft_plan plan, void *data, size_t n_frames, int
  * zero (test/testFFT.cpp:24, :86).  This does that placement inside the first load of the transform, so the input
  * costs half the bytes. */
 int sdsp_b200_fft_exec_real(sdsp_b200_fft_plan plan, const void *real_in, void *spectrum_out, size_t n_frames, int ptr_kind, void *stream);
+/* Real frames in (n scalars each), HALF spectra out: the bins 0 .. n/2 of each frame (n/2 + 1 complex values, frames n/2 + 1
+ * values apart), out of place, forward plans only.  The bins above n/2 are the conjugates of those below, X[n - k] = conj X[k],
+ * so nothing is lost against the reference's convention (real part filled, imaginary part zero, full spectrum back:
+ * test/testFFT.cpp:24, :86) while the call moves 4 + 4 bytes per sample instead of 8 + 8 (fp32).  On the device the frame
+ * is read as n/2 complex numbers, transformed by the n/2-point kernel and separated in one more exchange.
+ * n = 4 .. 65536 (f32) / 4 .. 16384 (f64); device buffers aligned to one complex element. */
+int sdsp_b200_fft_exec_r2c(sdsp_b200_fft_plan plan, const void *real_in, void *half_spectrum_out, size_t n_frames, int ptr_kind, void *stream);
 /* human-readable description of the factorisation / launch geometry the plan chose */
 int sdsp_b200_fft_plan_describe(sdsp_b200_fft_plan plan, char *buf, size_t buf_len);
 /* number of kernel launches one exec of n_frames device-resident frames issues */

@@ -336,7 +336,6 @@ __global__ void __launch_bounds__(THREADS, MINB)
     const int t = threadIdx.x % Cfg::TPF;
     cplx<T> *fs = smem + (size_t)fl * Cfg::PADDED_N;
     const size_t groups = (n_frames + FPC - 1) / FPC;
-    const cplx<T> wt = tw_n[t]; // W_N^t
 
     for (size_t g = blockIdx.x; g < groups; g += gridDim.x) {
         const size_t frame = g * FPC + fl;
@@ -361,6 +360,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
         __syncthreads();
         if (active) {
             cplx<T> *op = out + frame * (size_t)(M + 1);
+            const cplx<T> wt = tw_n[t]; // W_N^t (re-read per frame: two or four registers less across the passes)
 #pragma unroll
             for (int e = 0; e < Cfg::E; e++) {
                 const int k = t + Cfg::S * e;
@@ -427,6 +427,7 @@ __global__ void digit_reverse_permute_kernel(cplx<T> *data, uint32_t n, int log2
 struct FftPlan;
 typedef int (*fft_launch_fn)(const FftPlan &, void *data, const void *real_in, size_t n_frames, cudaStream_t stream);
 typedef void (*fft_emulate_fn)(void *frame, const void *tw, bool inverse);
+typedef int (*fft_r2c_launch_fn)(const FftPlan &, const void *real_in, void *half_out, size_t n_frames, cudaStream_t stream);
 
 struct FftPlan {
     uint32_t n = 0;
@@ -439,6 +440,12 @@ struct FftPlan {
     bool two_slot = false; // data-mover kernel with two tile slots that double as exchange buffers (fft_fused_tma2_kernel)
     int real64k_ctas = 0;  // > 0: forward real-input frames of 65536 points take fft_real64k_kernel (resident CTAs per SM)
     size_t real64k_smem = 0;
+    // half-spectrum path (sdsp_b200_fft_exec_r2c): an n/2-point complex transform plus a separation step; set up at the first call
+    bool r2c_ready = false;
+    fft_r2c_launch_fn r2c_launch = nullptr;
+    void *d_r2c_tw = nullptr, *d_r2c_twn = nullptr;
+    size_t r2c_smem = 0;
+    int r2c_ctas = 0, r2c_threads = 0, r2c_fpc = 0, r2c_e = 0, r2c_npass = 0;
     void *d_tw = nullptr;
     size_t tw_bytes = 0;
     fft_launch_fn launch = nullptr;
@@ -1904,8 +1911,10 @@ template <typename T, int MINB>
 __global__ void __launch_bounds__(288, MINB)
     fft_real64k_kernel(const __grid_constant__ CUtensorMap in_map, cplx<T> *__restrict__ data, cplx<T> *__restrict__ scratch,
                        const cplx<T> *__restrict__ tw, const cplx<T> *__restrict__ tw_hi, const cplx<T> *__restrict__ tw_lo,
-                       unsigned *__restrict__ ticket, unsigned *__restrict__ col_done, unsigned *__restrict__ row_done, size_t n_frames)
+                       unsigned *__restrict__ ticket, unsigned *__restrict__ col_done, unsigned *__restrict__ row_done, size_t n_frames, int half)
 {
+    // half != 0 (sdsp_b200_fft_exec_r2c): only the bins 0 .. 32768 are written, frames 32769 bins apart -- of every row the lower
+    // half of k2 directly and the upper half through its mirror bin, which lies in the lower half of the spectrum
     using Cfg = FftCfg<256, 16, 16, 16>; // rows and (packed) columns alike
     constexpr int N1 = 256, N2 = 256, PITCH = LargeStride<Cfg>::value;
     constexpr int XBUF = 16 * PITCH;
@@ -2118,15 +2127,18 @@ __global__ void __launch_bounds__(288, MINB)
             fft_pass<Cfg, 1, T>(v, t2, tw);
             const int k1 = 16 * tile + row2;
             if (!last_tile || row2 == 0) {
-                cplx<T> *op = data + f * FRAME + k1;
+                const size_t pitch = half ? FRAME / 2 + 1 : FRAME;
+                cplx<T> *op = data + f * pitch + k1;
 #pragma unroll
                 for (int e = 0; e < Cfg::E; e++)
-                    st_stream(op + (size_t)(t2 + Cfg::S * e) * N1, v[e]);
+                    if (!half || e < 8 || (e == 8 && t2 == 0 && k1 == 0)) // k2 = t2 + 16 e < 128, and the bin N / 2
+                        st_stream(op + (size_t)(t2 + Cfg::S * e) * N1, v[e]);
                 if (k1 != 0 && k1 != 128) { // X[N - k] = conj X[k]
-                    cplx<T> *mp = data + f * FRAME + (256 - k1);
+                    cplx<T> *mp = data + f * pitch + (256 - k1);
 #pragma unroll
                     for (int e = 0; e < Cfg::E; e++)
-                        st_stream(mp + (size_t)(255 - t2 - Cfg::S * e) * N1, cplx<T>{ v[e].x, -v[e].y });
+                        if (!half || e >= 8)
+                            st_stream(mp + (size_t)(255 - t2 - Cfg::S * e) * N1, cplx<T>{ v[e].x, -v[e].y });
                 }
             }
         }
@@ -2140,7 +2152,7 @@ struct FusedTmaCfg {
 };
 
 // forward real-input frames of 65536 points (fp32): the half-work queue, fft_real64k_kernel
-static int launch_real64k(const FftPlan &p, void *data, const void *real_in, size_t n_frames, cudaStream_t stream)
+static int launch_real64k(const FftPlan &p, void *data, const void *real_in, size_t n_frames, cudaStream_t stream, bool half = false)
 {
     using T = float;
     const size_t need = (1 + 2 * n_frames) * sizeof(unsigned);
@@ -2174,7 +2186,7 @@ static int launch_real64k(const FftPlan &p, void *data, const void *real_in, siz
         grid = items;
     fft_real64k_kernel<T, SDSP_FUSED_TMA_MINB><<<(unsigned)grid, 288, p.real64k_smem, stream>>>(
         map, reinterpret_cast<cplx<T> *>(data), reinterpret_cast<cplx<T> *>(p.d_scratch), reinterpret_cast<const cplx<T> *>(p.d_tw_rows),
-        reinterpret_cast<const cplx<T> *>(p.d_tw_hi), reinterpret_cast<const cplx<T> *>(p.d_tw_lo), ctr, ctr + 1, ctr + 1 + n_frames, n_frames);
+        reinterpret_cast<const cplx<T> *>(p.d_tw_hi), reinterpret_cast<const cplx<T> *>(p.d_tw_lo), ctr, ctr + 1, ctr + 1 + n_frames, n_frames, half ? 1 : 0);
     SDSP_CUDA(cudaGetLastError());
     return SDSP_B200_OK;
 }
@@ -2517,13 +2529,8 @@ static int setup_for(FftPlan &p)
                 return setup_cta<CfgR32_13::type, float, CfgR32_13::THREADS, CfgR32_13::MINB>(p);
         }
         if constexpr (LG == 14) {
-            if (fft_r32_enabled()) {
-                const int rc = setup_cta<CfgR32_14::type, float, CfgR32_14::THREADS, CfgR32_14::MINB>(p);
-                static const bool alias = getenv("SDSP_B200_FFT_R32_ALIAS") && atoi(getenv("SDSP_B200_FFT_R32_ALIAS")) != 0;
-                if (rc == SDSP_B200_OK && alias)
-                    return enable_alias<CfgR32_14::type, float, CfgR32_14::THREADS, CfgR32_14::MINB>(p);
-                return rc;
-            }
+            if (fft_r32_enabled()) // (staging the next frame into the idle exchange buffer, fft_cta_alias_kernel: 0.65 against 0.69)
+                return setup_cta<CfgR32_14::type, float, CfgR32_14::THREADS, CfgR32_14::MINB>(p);
         }
         return setup_cta<typename C::type, float, C::THREADS, C::MINB>(p);
     }
@@ -2558,6 +2565,104 @@ static int emulate_for(int precision, bool inverse, void *frame)
     return SDSP_B200_OK;
 }
 
+
+// ---- half-spectrum plans (sdsp_b200_fft_exec_r2c): the M = n / 2 point configuration of the table above behind fft_r2c_kernel
+template <class Cfg, typename T, int THREADS, int MINB>
+static int launch_r2c(const FftPlan &p, const void *real_in, void *half_out, size_t n_frames, cudaStream_t stream)
+{
+    constexpr int FPC = THREADS / Cfg::TPF;
+    const size_t groups = (n_frames + FPC - 1) / FPC;
+    if (groups == 0)
+        return SDSP_B200_OK;
+    const size_t resident = (size_t)p.sm_count * (size_t)p.r2c_ctas;
+    const size_t grid = groups < resident * 4 ? groups : resident * 4;
+    const int prefetch = fft_prefetch_enabled() && (Cfg::N * sizeof(cplx<T>)) % 16 == 0 && reinterpret_cast<uintptr_t>(real_in) % 16 == 0 ? 1 : 0;
+    fft_r2c_kernel<Cfg, T, THREADS, MINB><<<(unsigned)grid, THREADS, p.r2c_smem, stream>>>(
+        static_cast<const cplx<T> *>(real_in), static_cast<cplx<T> *>(half_out), static_cast<const cplx<T> *>(p.d_r2c_tw),
+        static_cast<const cplx<T> *>(p.d_r2c_twn), n_frames, prefetch);
+    SDSP_CUDA(cudaGetLastError());
+    return SDSP_B200_OK;
+}
+
+static int upload_w64()
+{
+    float2 f[32];
+    double2 d[32];
+    for (int j = 0; j < 32; j++) {
+        long double re, im;
+        unit_root((uint64_t)j, 64, re, im);
+        f[j] = make_float2((float)re, (float)im);
+        d[j] = make_double2((double)re, (double)im);
+    }
+    SDSP_CUDA(cudaMemcpyToSymbol(c_w64_f32, f, sizeof(f)));
+    SDSP_CUDA(cudaMemcpyToSymbol(c_w64_f64, d, sizeof(d)));
+    return SDSP_B200_OK;
+}
+
+template <class Cfg, typename T, int THREADS, int MINB>
+static int setup_r2c_cfg(FftPlan &p)
+{
+    constexpr int FPC = THREADS / Cfg::TPF;
+    auto kern = fft_r2c_kernel<Cfg, T, THREADS, MINB>;
+    p.r2c_smem = (size_t)FPC * Cfg::PADDED_N * sizeof(cplx<T>);
+    if (p.r2c_smem > 48 * 1024)
+        SDSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.r2c_smem));
+    int occ = 0;
+    SDSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, p.r2c_smem));
+    if (occ < 1)
+        return set_error(SDSP_B200_ERR_UNSUPPORTED, "fft r2c kernel for n=%u does not fit on an SM", p.n);
+    p.r2c_ctas = occ;
+    p.r2c_threads = THREADS;
+    p.r2c_fpc = FPC;
+    p.r2c_e = Cfg::E;
+    p.r2c_npass = Cfg::NPASS;
+    int rc = upload_w64();
+    if (rc)
+        return rc;
+    int radices[4] = { Cfg::R0, Cfg::R1, Cfg::R2, Cfg::R3 };
+    std::vector<cplx<T>> tw;
+    build_twiddles<T>(Cfg::N, radices, Cfg::NPASS, tw);
+    tw.push_back(cplx<T>{ 1, 0 }); // (single-pass frames have no table; keep the pointer valid)
+    SDSP_CUDA(cudaMalloc(&p.d_r2c_tw, tw.size() * sizeof(cplx<T>)));
+    SDSP_CUDA(cudaMemcpy(p.d_r2c_tw, tw.data(), tw.size() * sizeof(cplx<T>), cudaMemcpyHostToDevice));
+    std::vector<cplx<T>> wn(Cfg::TPF); // W_n^t, n = 2 M, for the threads' first bins
+    for (int t = 0; t < Cfg::TPF; t++) {
+        long double re, im;
+        unit_root((uint64_t)t, (uint64_t)2 * Cfg::N, re, im);
+        wn[t] = cplx<T>{ (T)re, (T)im };
+    }
+    SDSP_CUDA(cudaMalloc(&p.d_r2c_twn, wn.size() * sizeof(cplx<T>)));
+    SDSP_CUDA(cudaMemcpy(p.d_r2c_twn, wn.data(), wn.size() * sizeof(cplx<T>), cudaMemcpyHostToDevice));
+    p.r2c_launch = &launch_r2c<Cfg, T, THREADS, MINB>;
+    return SDSP_B200_OK;
+}
+
+static int launch_r2c_real64k(const FftPlan &p, const void *real_in, void *half_out, size_t n_frames, cudaStream_t stream)
+{
+    if (reinterpret_cast<uintptr_t>(real_in) % 16 != 0 || n_frames > 0x7fffffffu)
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "fft_exec_r2c: frames of 65536 points need a 16-byte-aligned input");
+    return launch_real64k(p, half_out, real_in, n_frames, stream, true);
+}
+
+template <int LG>
+static int setup_r2c_for(FftPlan &p) // LG = log2(n / 2)
+{
+    using C = CfgFor<LG>;
+    if (p.precision == SDSP_B200_F32) {
+        if constexpr (LG == 13)
+            return setup_r2c_cfg<CfgR32_13::type, float, CfgR32_13::THREADS, CfgR32_13::MINB>(p);
+        else if constexpr (LG == 14)
+            return setup_r2c_cfg<CfgR32_14::type, float, CfgR32_14::THREADS, CfgR32_14::MINB>(p);
+        else
+            return setup_r2c_cfg<typename C::type, float, C::THREADS, C::MINB>(p);
+    }
+    if constexpr (LG <= MAX_LOG2N_F64) {
+        constexpr int MB = LG == 13 ? 1 : (C::MINB > 2 ? 2 : C::MINB);
+        return setup_r2c_cfg<typename C::type, double, C::THREADS, MB>(p);
+    } else
+        return set_error(SDSP_B200_ERR_UNSUPPORTED, "fft_exec_r2c: n=%u in f64 is not built (up to 16384)", p.n);
+}
+
 #define SDSP_FOR_EACH_LG(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14)
 
 static int setup_plan(FftPlan &p)
@@ -2590,6 +2695,34 @@ static int emulate_dispatch(uint32_t n, int precision, bool inverse, void *frame
 #undef X
     default: return set_error(SDSP_B200_ERR_UNSUPPORTED, "emulate_fft: n=%u not built", n);
     }
+}
+
+
+static int setup_r2c(FftPlan &p)
+{
+    if (p.r2c_ready)
+        return SDSP_B200_OK;
+    if (p.direction != SDSP_B200_FORWARD)
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "fft_exec_r2c: the plan must be a forward one");
+    if (p.n < 4)
+        return set_error(SDSP_B200_ERR_UNSUPPORTED, "fft_exec_r2c: n=%u (needs at least 4 points)", p.n);
+    const int lg = ilog2(p.n) - 1;
+    int rc;
+    if (lg == 15 && p.precision == SDSP_B200_F32 && p.real64k_ctas > 0) {
+        p.r2c_launch = &launch_r2c_real64k;
+        rc = SDSP_B200_OK;
+    } else
+        switch (lg) {
+#define X(LG) \
+    case LG: rc = setup_r2c_for<LG>(p); break;
+            SDSP_FOR_EACH_LG(X)
+#undef X
+        default:
+            rc = set_error(SDSP_B200_ERR_UNSUPPORTED, "fft_exec_r2c: n=%u is not built (f32 up to 65536, f64 up to 16384 points)", p.n);
+        }
+    if (rc == SDSP_B200_OK)
+        p.r2c_ready = true;
+    return rc;
 }
 
 static int check_fft_args(uint32_t n, int radix, int precision, int direction)
@@ -2674,7 +2807,8 @@ int sdsp_b200_fft_plan_destroy(sdsp_b200_fft_plan plan)
     if (plan->p.d_stage)
         cudaFree(plan->p.d_stage);
     plan->p.host.release();
-    for (void *q : { plan->p.d_tw_cols, plan->p.d_tw_rows, plan->p.d_tw_hi, plan->p.d_tw_lo, plan->p.d_scratch, plan->p.d_fused_counters })
+    for (void *q : { plan->p.d_tw_cols, plan->p.d_tw_rows, plan->p.d_tw_hi, plan->p.d_tw_lo, plan->p.d_scratch, plan->p.d_fused_counters, plan->p.d_r2c_tw,
+                     plan->p.d_r2c_twn })
         if (q)
             cudaFree(q);
     delete plan;
@@ -2810,6 +2944,70 @@ int sdsp_b200_fft_exec_real(sdsp_b200_fft_plan plan, const void *real_in, void *
             rc = cuda_fail((int)cudaGetLastError(), "cudaEventRecord", __FILE__, __LINE__);
         if (rc == SDSP_B200_OK &&
             cudaMemcpyAsync(static_cast<char *>(spectrum_out) + done * out_bytes, d_out, cnt * out_bytes, cudaMemcpyDeviceToHost, cs) != cudaSuccess)
+            rc = cuda_fail((int)cudaGetLastError(), "D2H", __FILE__, __LINE__);
+        which = (which + 1) % nbuf;
+        first = false;
+    }
+    return p.host.drain(rc);
+}
+
+
+// real frames in (n scalars), half spectra out (n / 2 + 1 bins per frame, frames n / 2 + 1 bins apart), out of place, forward
+int sdsp_b200_fft_exec_r2c(sdsp_b200_fft_plan plan, const void *real_in, void *half_spectrum_out, size_t n_frames, int ptr_kind, void *stream)
+{
+    if (!plan)
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "fft_exec_r2c: null plan");
+    if (n_frames == 0)
+        return SDSP_B200_OK;
+    if (!real_in || !half_spectrum_out)
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "fft_exec_r2c: null data");
+    FftPlan &p = plan->p;
+    SDSP_CUDA(cudaSetDevice(p.device));
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const size_t es = p.precision == SDSP_B200_F32 ? sizeof(float) : sizeof(double);
+    if (ptr_kind != SDSP_B200_PTR_DEVICE && ptr_kind != SDSP_B200_PTR_HOST)
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "fft_exec_r2c: bad ptr_kind %d", ptr_kind);
+    if ((reinterpret_cast<uintptr_t>(half_spectrum_out) % (2 * es)) != 0 ||
+        (reinterpret_cast<uintptr_t>(real_in) % (ptr_kind == SDSP_B200_PTR_DEVICE ? 2 * es : es)) != 0)
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "fft_exec_r2c: device buffers must be aligned to one complex element (the real frame is read in pairs)");
+    std::lock_guard<std::mutex> lock(p.mu);
+    int rc = setup_r2c(p);
+    if (rc)
+        return rc;
+    if (ptr_kind == SDSP_B200_PTR_DEVICE)
+        return p.r2c_launch(p, real_in, half_spectrum_out, n_frames, s);
+    // host buffers: slabs through the plan's staging memory, each buffer = half-spectrum slab + real slab behind it
+    if (s)
+        SDSP_CUDA(cudaStreamSynchronize(s));
+    rc = p.host.ensure();
+    if (rc)
+        return rc;
+    const size_t in_bytes = (size_t)p.n * es, out_bytes = ((size_t)p.n / 2 + 1) * 2 * es;
+    const size_t out_slot = (out_bytes + 15) / 16 * 16; // (per frame, only to size the slab; frames stay n / 2 + 1 bins apart)
+    size_t slab = (64u << 20) / (in_bytes + out_slot);
+    slab = slab < 1 ? 1 : slab > n_frames ? n_frames : slab;
+    const int nbuf = n_frames > slab ? 2 : 1;
+    const size_t out_slab = (slab * out_bytes + 255) / 256 * 256;
+    const size_t buf_bytes = out_slab + slab * in_bytes;
+    rc = ensure_device_stage(p.d_stage, p.stage_bytes, buf_bytes * nbuf, "fft_exec_r2c");
+    if (rc)
+        return rc;
+    int which = 0;
+    bool first = true;
+    for (size_t done = 0; done < n_frames && rc == SDSP_B200_OK; done += slab) {
+        const size_t cnt = (n_frames - done) < slab ? (n_frames - done) : slab;
+        char *d_out = static_cast<char *>(p.d_stage) + (size_t)which * buf_bytes, *d_in = d_out + out_slab;
+        cudaStream_t cs = p.host.stream[which];
+        if (cudaMemcpyAsync(d_in, static_cast<const char *>(real_in) + done * in_bytes, cnt * in_bytes, cudaMemcpyHostToDevice, cs) != cudaSuccess)
+            rc = cuda_fail((int)cudaGetLastError(), "H2D", __FILE__, __LINE__);
+        if (rc == SDSP_B200_OK && !first && cudaStreamWaitEvent(cs, p.host.kernel_done[which ^ 1], 0) != cudaSuccess)
+            rc = cuda_fail((int)cudaGetLastError(), "cudaStreamWaitEvent", __FILE__, __LINE__);
+        if (rc == SDSP_B200_OK)
+            rc = p.r2c_launch(p, d_in, d_out, cnt, cs);
+        if (rc == SDSP_B200_OK && cudaEventRecord(p.host.kernel_done[which], cs) != cudaSuccess)
+            rc = cuda_fail((int)cudaGetLastError(), "cudaEventRecord", __FILE__, __LINE__);
+        if (rc == SDSP_B200_OK &&
+            cudaMemcpyAsync(static_cast<char *>(half_spectrum_out) + done * out_bytes, d_out, cnt * out_bytes, cudaMemcpyDeviceToHost, cs) != cudaSuccess)
             rc = cuda_fail((int)cudaGetLastError(), "D2H", __FILE__, __LINE__);
         which = (which + 1) % nbuf;
         first = false;

@@ -65,6 +65,33 @@ class FftPlan:
         self.exec_real_ptr(real_in.data_ptr(), out.data_ptr(), real_in.numel() // n, K.PTR_DEVICE, torch.cuda.current_stream().cuda_stream)
         return out
 
+    def exec_r2c_ptr(self, real_ptr: int, out_ptr: int, n_frames: int, ptr_kind: int, stream=None) -> None:
+        """n_frames real frames of n scalars at real_ptr -> n_frames half spectra of n/2 + 1 complex at out_ptr (out of place)."""
+        K.check(K.lib().sdsp_b200_fft_exec_r2c(self._h, real_ptr, out_ptr, n_frames, ptr_kind, stream))
+
+    def half_spectrum(self, real_in, out=None):
+        """Bins 0 .. n/2 of the transform of real frames (the rest is the conjugate mirror): shape (..., n) -> (..., n/2 + 1).
+        numpy in -> numpy out (staged through the device), torch CUDA tensor in -> torch CUDA tensor out."""
+        n = self.n
+        shape = tuple(real_in.shape[:-1]) + (n // 2 + 1,)
+        if real_in.shape[-1] != n:
+            raise ValueError(f"last dimension must be {n}")
+        if isinstance(real_in, np.ndarray):
+            want = np.float32 if self.precision == K.F32 else np.float64
+            x = np.ascontiguousarray(real_in, dtype=want)
+            if out is None:
+                out = np.empty(shape, dtype=np.complex64 if self.precision == K.F32 else np.complex128)
+            self.exec_r2c_ptr(x.ctypes.data, out.ctypes.data, x.size // n, K.PTR_HOST, None)
+            return out
+        import torch
+
+        if real_in.device.index != self.device:
+            raise ValueError("tensor lives on another device than the plan")
+        if out is None:
+            out = torch.empty(shape, device=real_in.device, dtype=torch.complex64 if self.precision == K.F32 else torch.complex128)
+        self.exec_r2c_ptr(real_in.data_ptr(), out.data_ptr(), real_in.numel() // n, K.PTR_DEVICE, torch.cuda.current_stream().cuda_stream)
+        return out
+
     def __call__(self, data):
         """Transform every length-n row of ``data`` in place (numpy: staged through the device;
         torch CUDA tensor: in place on the current stream, asynchronously).  Returns ``data``."""

@@ -234,6 +234,61 @@ def test_real_input_frames_match_oracle(n, prec):
         assert torch.equal(z, yd)
 
 
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+@pytest.mark.parametrize("n", [4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 65536])
+def test_half_spectrum_of_real_frames_matches_oracle(n, prec):
+    """sdsp_b200_fft_exec_r2c: bins 0 .. n/2 of the spectrum of real frames.  Checked against the oracle's transform of (x, 0) --
+    the reference's calling convention, test/testFFT.cpp:24, :86 -- at the FFT tolerance, device and host buffers (same bits),
+    odd frame counts (partial groups), input untouched."""
+    torch = pytest.importorskip("torch")
+    code, dt = PREC[prec]
+    if prec == "f64" and n > 16384:
+        with pytest.raises(RuntimeError):
+            S.FftPlan(n, 2, code, K.FORWARD).half_spectrum(np.zeros((1, n)))
+        return
+    rdt = np.float32 if prec == "f32" else np.float64
+    frames = 261 if n <= 256 else 37 if n <= 4096 else 9
+    rng = np.random.default_rng(n + 1)
+    x = rng.standard_normal((frames, n)).astype(np.float32).astype(rdt)
+    ref = oracle_fft(x.astype(np.complex128))[:, : n // 2 + 1]
+    plan = S.FftPlan(n, 2, code, K.FORWARD)
+    xd = torch.from_numpy(x).cuda()
+    yd = plan.half_spectrum(xd)
+    torch.cuda.synchronize()
+    assert tuple(yd.shape) == (frames, n // 2 + 1)
+    got = yd.cpu().numpy()
+    assert rel_l2(got, ref) <= FFT_TOL[prec]
+    assert torch.equal(xd.cpu(), torch.from_numpy(x))
+    # the purely real bins of a real signal
+    scale = np.abs(ref).max(axis=1)
+    assert np.all(np.abs(got[:, 0].imag) <= 1e-6 * scale) and np.all(got[:, n // 2].imag == 0)
+    yh = plan.half_spectrum(x)
+    assert np.array_equal(yh, got)
+    # one frame, and a frame count that leaves the last group of a CTA partly empty
+    y1 = plan.half_spectrum(xd[:1].contiguous())
+    torch.cuda.synchronize()
+    assert np.array_equal(y1.cpu().numpy(), got[:1])
+
+
+def test_half_spectrum_full_size_and_errors():
+    """Config-2-sized batch of real frames (65536 x 4096, fp32) against torch.fft.rfft, and the argument checks."""
+    torch = pytest.importorskip("torch")
+    n, frames = 4096, 65536
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = torch.randn(frames, n, device="cuda", generator=g, dtype=torch.float32)
+    plan = S.FftPlan(n, 4, K.F32, K.FORWARD)
+    y = plan.half_spectrum(x)
+    ref = torch.fft.rfft(x.double(), dim=1)
+    err = (y.to(torch.complex128) - ref).abs().pow(2).sum(dim=1).sqrt() / ref.abs().pow(2).sum(dim=1).sqrt()
+    assert float(err.max()) <= FFT_TOL["f32"]
+    idx = [0, 1, 32767, 65535]
+    assert rel_l2(y[idx].cpu().numpy(), oracle_fft(x[idx].cpu().numpy().astype(np.complex128))[:, : n // 2 + 1]) <= FFT_TOL["f32"]
+    with pytest.raises(RuntimeError):
+        S.FftPlan(n, 4, K.F32, K.REVERSE).half_spectrum(x[:2].contiguous())
+    with pytest.raises(RuntimeError):
+        S.FftPlan(2, 2, K.F32, K.FORWARD).half_spectrum(np.zeros((3, 2), dtype=np.float32))
+
+
 @pytest.mark.parametrize("frames", [1, 2, 31, 32, 33, 47, 48, 49, 63, 64, 65, 87, 88, 89, 95, 96, 97, 127, 128, 129, 175, 176, 177, 200, 365])
 def test_fused_65536_kernel_at_the_edges_of_its_work_queue(frames):
     """The 65536-point kernel orders column and row tiles through a queue with a 48-frame lag and a 96-frame scratch ring
