@@ -70,6 +70,9 @@ WORKLOADS = {
     # them in waves of 32768 frames (one 16 GiB spectrum buffer)
     "pipeline_cfg5_f32": dict(kind="pipeline", channels=4096, frames_per_channel=64, n=65536, precision="f32", sections=4,
                               bytes_per_sample=20, strong=True, wave_frames=32768),
+    # the same job with half spectra out (bins 0 .. 32768 of every frame; the rest is the conjugate mirror): 8 + 4 + 4 bytes per sample
+    "pipeline_cfg5_r2c_f32": dict(kind="pipeline", channels=4096, frames_per_channel=64, n=65536, precision="f32", sections=4,
+                                  bytes_per_sample=16, strong=True, wave_frames=65536, half=True),
     "iir16384_f32_scan": dict(kind="iir", channels=16384, samples=1 << 20, precision="f32", sections=4, bytes_per_sample=8, path="scan"),
     # same bank, channel pitch not a power of two (2^20 + 8256 samples): separates DRAM channel effects from kernel effects
     "iir16384_f32_pitch": dict(kind="iir", channels=16384, samples=1 << 20, pitch=(1 << 20) + 8256, precision="f32", sections=4,
@@ -463,13 +466,15 @@ class PipelineWorkload:
             self.signal[lo:lo + rows].normal_(generator=g)
         self.frames = self.ch * self.fpc
         self.wave = min(self.frames, spec.get("wave_frames", self.frames))
-        self.spectra = torch.empty(self.wave, self.n, device="cuda", dtype=torch.complex64)
+        self.half = bool(spec.get("half"))
+        self.bins = self.n // 2 + 1 if self.half else self.n
+        self.spectra = torch.empty(self.wave, self.bins, device="cuda", dtype=torch.complex64)
         self.samples_per_step = self.ch * self.len
         self.stream = torch.cuda.current_stream().cuda_stream
 
     def describe(self):
-        return (self.bank.describe(self.len, self.len, self.K.IIR_SCAN) + f" | then real-input, {self.frames} frames in waves of {self.wave}: "
-                + self.plan.describe())
+        return (self.bank.describe(self.len, self.len, self.K.IIR_SCAN) + f" | then real-input, {self.frames} frames in waves of {self.wave}"
+                + (", half spectra out: " if self.half else ": ") + self.plan.describe())
 
     def launches_per_step(self):
         return 1
@@ -483,7 +488,8 @@ class PipelineWorkload:
         self.bank.process_ptr(self.signal.data_ptr(), self.len, self.len, K.PTR_DEVICE, K.IIR_SCAN, self.stream)
         for lo in range(0, self.frames, self.wave):
             cnt = min(self.wave, self.frames - lo)
-            self.plan.exec_real_ptr(self.signal.data_ptr() + lo * self.n * 4, self.spectra.data_ptr(), cnt, K.PTR_DEVICE, self.stream)
+            (self.plan.exec_r2c_ptr if self.half else self.plan.exec_real_ptr)(
+                self.signal.data_ptr() + lo * self.n * 4, self.spectra.data_ptr(), cnt, K.PTR_DEVICE, self.stream)
 
     def self_check(self):
         """A sampled frame of the spectrum buffer equals the transform of the filtered signal it was made from."""
@@ -493,7 +499,7 @@ class PipelineWorkload:
         last_wave = (self.frames - 1) // self.wave * self.wave  # the spectrum buffer holds the last wave
         for fr in (last_wave, last_wave + (self.frames - last_wave) // 2, self.frames - 1):
             x = self.signal.view(-1)[fr * self.n:(fr + 1) * self.n].double()
-            ref = torch.fft.fft(x)
+            ref = (torch.fft.rfft if self.half else torch.fft.fft)(x)
             got = self.spectra[fr - last_wave].to(torch.complex128)
             worst = max(worst, float((got - ref).abs().pow(2).sum().sqrt() / ref.abs().pow(2).sum().sqrt().clamp_min(1e-300)))
         return worst
