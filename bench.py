@@ -92,6 +92,11 @@ NCU_TRAFFIC = {
     "iir16384_f32": (1.37387e11, "profiles/r02_ncu_iir16384_f32_delta_v1.txt"),
     "iir4096_f32_scan": (1.37408e11, "profiles/r01_ncu_iir4096_f32_split_v1.txt (main pass)"),
     "iirscan_f64": (1.7126e10, "profiles/r01_launches_iir_split_v1.txt (main pass)"),
+    # captures taken on a quarter / an eighth of the bench's frames (ncu replays every launch), scaled to the bench's frame count
+    "fft8192_f32": (4 * 1.03341e9, "profiles/r02_ncu_fft8192_f32_radix32_v1.txt (8192 frames: 1.033 GB for 1.074 GB algorithmic; x 4)"),
+    "fft16384_f32": (4 * 1.02115e9, "profiles/r02_ncu_fft16384_f32_radix32_v1.txt (4096 frames: 1.021 GB for 1.074 GB algorithmic; x 4)"),
+    "fftr2c4096_f32": (8 * 4.92013e8, "profiles/r02_ncu_fftr2c4096_f32_v1.txt (16384 frames: 0.492 GB for 0.537 GB algorithmic; x 8)"),
+    "fftreal65536_f32": (4 * 7.68692e8, "profiles/r02_ncu_fftreal65536_f32_v1.txt (1024 frames: 0.769 GB for 0.805 GB algorithmic; x 4)"),
 }
 
 

@@ -81,6 +81,20 @@ int main()
         }
         sdsp::fft_radix4(zd.data(), N, frames);
         CHECK(rel_l2(sd.data(), zd.data(), N * frames) < 1e-5, "fp32 real-input transform off by more than 1e-5 rel-L2");
+        // half spectra: bins 0 .. N/2, frames N/2 + 1 bins apart, against the fp64 spectra of the same frames
+        std::vector<std::complex<float>> half((N / 2 + 1) * frames);
+        sdsp::fft_half_spectrum(real.data(), half.data(), N, frames);
+        std::vector<std::complex<double>> hd((N / 2 + 1) * frames), hr((N / 2 + 1) * frames);
+        for (size_t f = 0; f < frames; f++)
+            for (size_t k = 0; k <= N / 2; k++) {
+                hd[f * (N / 2 + 1) + k] = half[f * (N / 2 + 1) + k];
+                hr[f * (N / 2 + 1) + k] = zd[f * N + k];
+            }
+        CHECK(rel_l2(hd.data(), hr.data(), hd.size()) < 1e-5, "fp32 half spectrum off by more than 1e-5 rel-L2");
+        std::vector<double> reald(real.begin(), real.end());
+        std::vector<std::complex<double>> halfd((N / 2 + 1) * frames);
+        sdsp::fft_half_spectrum(reald.data(), halfd.data(), N, frames);
+        CHECK(rel_l2(halfd.data(), hr.data(), hr.size()) < 1e-12, "fp64 half spectrum off by more than 1e-12 rel-L2");
     }
     // ---- a bank of channels against one filter object per channel (reference signature, casc_2o_iir.h:36-80)
     {

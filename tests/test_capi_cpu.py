@@ -44,6 +44,8 @@ def test_no_device_is_a_loud_error_not_a_fallback():
         S.IirBank(4, 8)
     with pytest.raises(S.SdspError):
         S.digit_reverse_table(64, 2)
+    with pytest.raises(S.SdspError):
+        S.FftPlan(64, 2, K.F32, K.FORWARD).half_spectrum(np.zeros((2, 64), dtype=np.float32))
 
 
 def test_argument_validation():
