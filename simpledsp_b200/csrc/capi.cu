@@ -115,6 +115,7 @@ int sdsp_b200_shutdown(void)
     // plans and banks own their allocations and die with their handles; the one library-owned cache is the set of
     // one-channel banks behind sdsp_b200_iir_process_once
     iir_release_process_once_cache();
+    fft_release_l2_persist(); // the persisting-L2 carve-out of the large-frame FFT kernels (device-wide state)
     return SDSP_B200_OK;
 }
 

@@ -1083,6 +1083,12 @@ static int setup_cluster64k(FftPlan &p)
 #ifndef SDSP_FUSED_TMA_DEFAULT
 #define SDSP_FUSED_TMA_DEFAULT 1
 #endif
+#ifndef SDSP_FFT_L2_PERSIST_DEFAULT
+#define SDSP_FFT_L2_PERSIST_DEFAULT 1
+#endif
+#ifndef SDSP_FFT_L2_PERSIST_MB_DEFAULT
+#define SDSP_FFT_L2_PERSIST_MB_DEFAULT 16 // persisting carve-out of L2 in MB (sweep: profiles/r02_fft_l2_persist_sweep.txt)
+#endif
 #ifndef SDSP_FUSED_TMA_MINB
 #define SDSP_FUSED_TMA_MINB 3
 #endif
@@ -1889,7 +1895,7 @@ __global__ void __launch_bounds__(288, MINB)
 // row tiles of frame f; a row tile waits for its frame's 8 column tiles, a column tile for the 9 row tiles of the ring slot's
 // previous tenant -- both hold smaller tickets.
 #ifndef SDSP_REAL_LAG
-#define SDSP_REAL_LAG 64 // frames between a frame's column tiles and its row tiles (x 17 items; the ring holds twice that, 33 MB; 48 / 88 / 94 measured)
+#define SDSP_REAL_LAG 96 // frames between a frame's column tiles and its row tiles (x 17 items; the ring holds twice that, 51 MB, a third of it pinned in L2: profiles/r02_fft_l2_persist_sweep.txt; 64 was best without the pinning)
 #endif
 constexpr int REAL_CT = 8, REAL_RT = 9, REAL_LAG = SDSP_REAL_LAG, REAL_RING = 2 * SDSP_REAL_LAG, REAL_ROWS = 129;
 __host__ __device__ __forceinline__ void real_decode(size_t q, bool &cols, size_t &f, int &tile)
@@ -2151,6 +2157,75 @@ struct FusedTmaCfg {
     static constexpr int NST = SDSP_FUSED_TMA_NST, MINB = SDSP_FUSED_TMA_MINB;
 };
 
+
+// The scratch ring of the queue kernels as a PERSISTING window of L2 (per launch, cudaLaunchAttributeAccessPolicyWindow): part of the
+// ring's lines are pinned, so the streaming input and output of the same kernel do not push them out, which is what limited the lead of the
+// column phase over the row phase.  The carve-out (cudaLimitPersistingL2CacheSize, device-wide state, set at the first such launch and
+// given back by sdsp_b200_shutdown) is 16 MB: the gain peaks there and a carve-out of the ring's size is a LOSS -- what is left of L2
+// must still buffer the streams (profiles/r02_fft_l2_persist_sweep.txt).  SDSP_B200_FFT_L2_PERSIST=0 switches the window off,
+// SDSP_B200_FFT_L2_PERSIST_MB sizes the carve-out (tuning aids).
+static std::mutex g_persist_mu;
+static int g_persist_bytes[64], g_persist_window[64];
+static bool g_persist_seen[64];
+
+static bool ring_persist_window(int device, void *base, size_t bytes, cudaLaunchAttribute &attr)
+{
+    static int mode = -1;
+    if (mode < 0) {
+        const char *e = getenv("SDSP_B200_FFT_L2_PERSIST");
+        mode = e ? atoi(e) : SDSP_FFT_L2_PERSIST_DEFAULT;
+    }
+    if (mode == 0 || device < 0 || device >= 64)
+        return false;
+    std::lock_guard<std::mutex> lock(g_persist_mu);
+    if (!g_persist_seen[device]) {
+        g_persist_seen[device] = true;
+        int max_persist = 0;
+        g_persist_window[device] = 0;
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device);
+        cudaDeviceGetAttribute(&g_persist_window[device], cudaDevAttrMaxAccessPolicyWindowSize, device);
+        size_t want = (size_t)SDSP_FFT_L2_PERSIST_MB_DEFAULT << 20;
+        if (getenv("SDSP_B200_FFT_L2_PERSIST_MB"))
+            want = (size_t)atoi(getenv("SDSP_B200_FFT_L2_PERSIST_MB")) << 20;
+        if (want < (size_t)max_persist)
+            max_persist = (int)want;
+        if (max_persist > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist) != cudaSuccess) {
+            cudaGetLastError();
+            max_persist = 0;
+        }
+        g_persist_bytes[device] = max_persist;
+    }
+    if (g_persist_bytes[device] <= 0 || g_persist_window[device] <= 0)
+        return false;
+    const size_t win = bytes < (size_t)g_persist_window[device] ? bytes : (size_t)g_persist_window[device];
+    attr.id = cudaLaunchAttributeAccessPolicyWindow;
+    attr.val.accessPolicyWindow.base_ptr = base;
+    attr.val.accessPolicyWindow.num_bytes = win;
+    attr.val.accessPolicyWindow.hitRatio = win <= (size_t)g_persist_bytes[device] ? 1.0f : (float)g_persist_bytes[device] / (float)win;
+    attr.val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.val.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+    return true;
+}
+
+// sdsp_b200_shutdown: give the persisting carve-out back on every device that got one
+void fft_release_l2_persist()
+{
+    std::lock_guard<std::mutex> lock(g_persist_mu);
+    int cur = 0;
+    const bool have_cur = cudaGetDevice(&cur) == cudaSuccess;
+    for (int d = 0; d < 64; d++) {
+        if (g_persist_seen[d] && g_persist_bytes[d] > 0 && cudaSetDevice(d) == cudaSuccess) {
+            cudaCtxResetPersistingL2Cache();
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
+        }
+        g_persist_seen[d] = false;
+        g_persist_bytes[d] = 0;
+    }
+    if (have_cur)
+        cudaSetDevice(cur);
+    cudaGetLastError();
+}
+
 // forward real-input frames of 65536 points (fp32): the half-work queue, fft_real64k_kernel
 static int launch_real64k(const FftPlan &p, void *data, const void *real_in, size_t n_frames, cudaStream_t stream, bool half = false)
 {
@@ -2184,10 +2259,21 @@ static int launch_real64k(const FftPlan &p, void *data, const void *real_in, siz
     size_t grid = (size_t)p.sm_count * (size_t)p.real64k_ctas;
     if (grid > items)
         grid = items;
-    fft_real64k_kernel<T, SDSP_FUSED_TMA_MINB><<<(unsigned)grid, 288, p.real64k_smem, stream>>>(
-        map, reinterpret_cast<cplx<T> *>(data), reinterpret_cast<cplx<T> *>(p.d_scratch), reinterpret_cast<const cplx<T> *>(p.d_tw_rows),
-        reinterpret_cast<const cplx<T> *>(p.d_tw_hi), reinterpret_cast<const cplx<T> *>(p.d_tw_lo), ctr, ctr + 1, ctr + 1 + n_frames, n_frames, half ? 1 : 0);
-    SDSP_CUDA(cudaGetLastError());
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid, 1, 1);
+    cfg.blockDim = dim3(288, 1, 1);
+    cfg.dynamicSmemBytes = p.real64k_smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    const size_t ring_bytes = (size_t)REAL_RING * REAL_ROWS * 256 * sizeof(cplx<T>);
+    if (ring_persist_window(p.device, p.d_scratch, ring_bytes, attr[0])) {
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+    }
+    SDSP_CUDA(cudaLaunchKernelEx(&cfg, fft_real64k_kernel<T, SDSP_FUSED_TMA_MINB>, map, reinterpret_cast<cplx<T> *>(data),
+                                 reinterpret_cast<cplx<T> *>(p.d_scratch), reinterpret_cast<const cplx<T> *>(p.d_tw_rows),
+                                 reinterpret_cast<const cplx<T> *>(p.d_tw_hi), reinterpret_cast<const cplx<T> *>(p.d_tw_lo), ctr, ctr + 1,
+                                 ctr + 1 + n_frames, n_frames, half ? 1 : 0));
     return SDSP_B200_OK;
 }
 
@@ -2241,13 +2327,22 @@ static int launch_fused_tma(const FftPlan &p, void *data, const void *real_in, s
     unsigned *a_col = ctr + 1, *a_row = ctr + 1 + n_frames;
     const int a_real = real_in ? 1 : 0, a_inv = p.direction == SDSP_B200_REVERSE ? 1 : 0;
     const T a_scale = (T)(1.0 / ((double)N1 * 256.0));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid, 1, 1);
+    cfg.blockDim = dim3(288, 1, 1);
+    cfg.dynamicSmemBytes = p.smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    if (ring_persist_window(p.device, p.d_scratch, (size_t)FusedRing<T, N1>::RING * N1 * 256 * sizeof(cplx<T>), attr[0])) {
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+    }
     if (p.two_slot)
-        fft_fused_tma2_kernel<T, N1, MINB><<<(unsigned)grid, 288, p.smem_bytes, stream>>>(map, a_data, a_real, a_scratch, a_twc, a_twr, a_hi, a_lo, ctr,
-                                                                                         a_col, a_row, n_frames, a_inv, a_scale);
+        SDSP_CUDA(cudaLaunchKernelEx(&cfg, fft_fused_tma2_kernel<T, N1, MINB>, map, a_data, a_real, a_scratch, a_twc, a_twr, a_hi, a_lo, ctr, a_col, a_row,
+                                     n_frames, a_inv, a_scale));
     else
-        fft_fused_tma_kernel<T, N1, NST, MINB><<<(unsigned)grid, 288, p.smem_bytes, stream>>>(map, a_data, a_real, a_scratch, a_twc, a_twr, a_hi, a_lo,
-                                                                                             ctr, a_col, a_row, n_frames, a_inv, a_scale);
-    SDSP_CUDA(cudaGetLastError());
+        SDSP_CUDA(cudaLaunchKernelEx(&cfg, fft_fused_tma_kernel<T, N1, NST, MINB>, map, a_data, a_real, a_scratch, a_twc, a_twr, a_hi, a_lo, ctr, a_col,
+                                     a_row, n_frames, a_inv, a_scale));
     return SDSP_B200_OK;
 }
 
@@ -2287,6 +2382,11 @@ static int setup_fused(FftPlan &p)
     p.e = 16;
     p.threads = 256;
     p.scratch_frames = FusedRing<T, N1>::RING;
+    if (N1 == 256 && sizeof(T) == 4) { // the real-input kernel's ring (REAL_RING frames of 129 rows) may be the larger one
+        const size_t need = ((size_t)REAL_RING * REAL_ROWS * 256 + 65535) / 65536;
+        if (need > p.scratch_frames)
+            p.scratch_frames = need;
+    }
     const size_t frame_bytes = (size_t)N1 * 256 * sizeof(cplx<T>);
     if (cudaMalloc(&p.d_scratch, p.scratch_frames * frame_bytes) != cudaSuccess) {
         cudaGetLastError();

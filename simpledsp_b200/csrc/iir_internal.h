@@ -53,6 +53,8 @@ inline int iir_bank_state_rows(const IirBank &b)
     return 2 * (b.sections + 1) + (b.precision == SDSP_B200_F32 ? b.sections : 0);
 }
 
+// fft.cu
+void fft_release_l2_persist(); // sdsp_b200_shutdown()
 // iir.cu
 void iir_release_process_once_cache(); // sdsp_b200_shutdown()
 int iir_launch_sequential(const IirBank &b, void *data, size_t n_samples, size_t stride, cudaStream_t stream);

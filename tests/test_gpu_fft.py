@@ -289,10 +289,10 @@ def test_half_spectrum_full_size_and_errors():
         S.FftPlan(2, 2, K.F32, K.FORWARD).half_spectrum(np.zeros((3, 2), dtype=np.float32))
 
 
-@pytest.mark.parametrize("frames", [1, 2, 31, 32, 33, 47, 48, 49, 63, 64, 65, 87, 88, 89, 95, 96, 97, 127, 128, 129, 175, 176, 177, 200, 365])
+@pytest.mark.parametrize("frames", [1, 2, 31, 32, 33, 47, 48, 49, 63, 64, 65, 87, 88, 89, 95, 96, 97, 127, 128, 129, 175, 176, 177, 191, 192, 193, 200, 365, 401])
 def test_fused_65536_kernel_at_the_edges_of_its_work_queue(frames):
     """The 65536-point kernel orders column and row tiles through a queue with a 48-frame lag and a 96-frame scratch ring
-    (fp32; 32 / 64 in the variant without the data-mover warp; 64 / 128 in the real-input kernel): frame counts below, at and
+    (fp32; 32 / 64 in the variant without the data-mover warp; 96 / 192 in the real-input kernel): frame counts below, at and
     just past those boundaries, forward and reverse, complex and real input."""
     torch = pytest.importorskip("torch")
     n = 65536
@@ -372,6 +372,24 @@ def test_fused_queue_with_and_without_the_data_mover_warp_agree(n, tmp_path):
     gen = torch.Generator(device="cuda").manual_seed(7)
     x = torch.view_as_complex(torch.randn(97, n, 2, device="cuda", generator=gen, dtype=torch.float32)).cpu().numpy()
     assert rel_l2(outs["1"][g], oracle_fft(x[g])) <= FFT_TOL["f32"]
+
+
+def test_shutdown_gives_the_l2_carve_out_back_and_the_library_stays_usable():
+    """The large-frame kernels pin part of their scratch ring in L2 (a persisting access-policy window; the carve-out is
+    device-wide state set at the first such launch).  sdsp_b200_shutdown resets it; the next launch sets it up again and
+    gives the same bits."""
+    torch = pytest.importorskip("torch")
+    n, frames = 65536, 130
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.randn(frames, n, device="cuda", generator=g, dtype=torch.float32)
+    plan = S.FftPlan(n, 4, K.F32, K.FORWARD)
+    a = plan.real(x)
+    torch.cuda.synchronize()
+    K.check(K.lib().sdsp_b200_shutdown())
+    b = plan.real(x)
+    torch.cuda.synchronize()
+    assert torch.equal(a, b)
+    assert rel_l2(a[:2].cpu().numpy(), oracle_fft(x[:2].cpu().numpy().astype(np.complex128))) <= FFT_TOL["f32"]
 
 
 @pytest.mark.parametrize("n,frames", [(65536, 300), (4096, 6000), (1024, 3)])
