@@ -1072,7 +1072,7 @@ static int setup_cluster64k(FftPlan &p)
 #define SDSP_FUSED_LEAD_F32 512 // tiles of lead between a frame's column tiles and its row tiles (fp32)
 #endif
 #ifndef SDSP_FUSED_LEAD_F32_TMA
-#define SDSP_FUSED_LEAD_F32_TMA 768
+#define SDSP_FUSED_LEAD_F32_TMA 1024 // (768 before a sixth of the ring was pinned in L2: profiles/r02_fft_l2_persist_sweep.txt)
 #endif
 #ifndef SDSP_FUSED_POLL
 #define SDSP_FUSED_POLL mbar_test // or mbar_try: one try_wait (suspends up to the hardware time limit) per round
@@ -1123,10 +1123,10 @@ struct FusedRing {
     static constexpr int TILES = N1 / 16;                     // tiles per frame, either phase
     static constexpr int COLS = 256 / (N1 / 16);              // columns per column tile
     // frames between a frame's column tiles and its row tiles: 512 (fp32) / 256 (fp64) tiles of lead, more than the CTAs in flight
-    // (fp32 runs the data-mover kernel, which discards consumed ring lines: 768 tiles of lead, 48 MB, measured best up to
+    // (fp32 runs the data-mover kernel, which discards consumed ring lines: 1024 tiles of lead, 64 MB with 16 MB of it pinned in L2, measured best up to
     // N1 = 512; 512 tiles for N1 = 1024)
     static constexpr int LAG = (sizeof(T) == 4 ? (N1 <= 512 ? SDSP_FUSED_LEAD_F32_TMA : SDSP_FUSED_LEAD_F32) : 256) / TILES;
-    static constexpr int RING = 2 * LAG;                      // scratch frames: 32 MB (48 MB) whatever the frame size
+    static constexpr int RING = 2 * LAG;                      // scratch frames: 32 MB (64 MB) whatever the frame size
 };
 
 __device__ __forceinline__ cplx<float> ld_l2(const cplx<float> *p)
@@ -1596,7 +1596,7 @@ __global__ void __launch_bounds__(288, MINB)
                 v[e] = gp[Cfg::S * e];
             mbar_arrive(&empty[s]);
             // the tile's 32 KB of the ring are dead now (256 lines of 128 bytes, one per thread): drop them from L2 instead of
-            // letting them be written back to HBM when they are evicted -- that is what makes a 48 MB ring affordable
+            // letting them be written back to HBM when they are evicted -- that is what makes a 64 MB ring affordable
             // (profiles/r01_fft65536_variants.txt)
             if constexpr (sizeof(cplx<T>) == 8)
                 asm volatile("discard.global.L2 [%0], 128;" ::"l"(sc + (size_t)(16 * tile) * N2 + (size_t)threadIdx.x * 16) : "memory");
@@ -1846,7 +1846,7 @@ __global__ void __launch_bounds__(288, MINB)
                 v[e] = gp[Cfg::S * e];
             cta_sync<1, 256>(); // every thread has its points: the slot becomes the exchange buffer
             // the tile's 32 KB of the ring are dead now (256 lines of 128 bytes, one per thread): drop them from L2 instead of
-            // letting them be written back to HBM when they are evicted -- that is what makes a 48 MB ring affordable
+            // letting them be written back to HBM when they are evicted -- that is what makes a 64 MB ring affordable
             // (profiles/r01_fft65536_variants.txt)
             if constexpr (sizeof(cplx<T>) == 8)
                 asm volatile("discard.global.L2 [%0], 128;" ::"l"(sc + (size_t)(16 * tile) * N2 + (size_t)threadIdx.x * 16) : "memory");

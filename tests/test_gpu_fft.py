@@ -291,7 +291,7 @@ def test_half_spectrum_full_size_and_errors():
 
 @pytest.mark.parametrize("frames", [1, 2, 31, 32, 33, 47, 48, 49, 63, 64, 65, 87, 88, 89, 95, 96, 97, 127, 128, 129, 175, 176, 177, 191, 192, 193, 200, 365, 401])
 def test_fused_65536_kernel_at_the_edges_of_its_work_queue(frames):
-    """The 65536-point kernel orders column and row tiles through a queue with a 48-frame lag and a 96-frame scratch ring
+    """The 65536-point kernel orders column and row tiles through a queue with a 64-frame lag and a 128-frame scratch ring
     (fp32; 32 / 64 in the variant without the data-mover warp; 96 / 192 in the real-input kernel): frame counts below, at and
     just past those boundaries, forward and reverse, complex and real input."""
     torch = pytest.importorskip("torch")

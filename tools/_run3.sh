@@ -1,13 +1,15 @@
 mkdir -p gpurun_out
-L=gpurun_out/r02_fft_final_real.log
+L=gpurun_out/r02_fft_persist5.log
 run() { timeout 300 python bench.py --steps $2 --warmup 3 --no-e2e --no-cpu --no-secondary --workload $1 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$3', d['config']['workload'], round(d['ms_per_step'],4), round(d['value']), round(d['roofline']['achieved'],1), round(d['roofline']['frac'],4), d['self_check'], d['clocks']['sm_mhz'], d['clocks']['reasons'])" >> $L 2>&1; }
 rm -f $L
-timeout 900 python -m pytest tests/test_gpu_fft.py -m gpu -q --timeout 300 -x 2>&1 | tail -4
 for rep in 1 2; do
-run pipeline_cfg5_f32 5 "lib"
-run pipeline_cfg5_r2c_f32 5 "lib"
-SDSP_B200_FFT_L2_PERSIST=0 run pipeline_cfg5_f32 5 "persist-off"
-run fft4096_f32 20 "lib"
-run iir16384_f32 5 "lib"
+for lib in lib lib_lead1024; do
+for w in fft32768_f32 fft65536_f32 fft131072_f32; do
+SDSP_B200_LIB=$PWD/simpledsp_b200/$lib/libsdsp_b200.so run $w 20 "$lib"
+done; done
+for lib in lib_lag80 lib lib_lag112; do
+for w in fftreal65536_f32 fftr2c65536_f32; do
+SDSP_B200_LIB=$PWD/simpledsp_b200/$lib/libsdsp_b200.so run $w 20 "$lib"
+done; done
 done
 cat $L
