@@ -86,7 +86,7 @@ WORKLOADS = {
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, one launch at the workload's full size, from the
 # committed `ncu --set full` summaries (profiles/); None where no capture at that size exists
 NCU_TRAFFIC = {
-    "fft4096_f32": (4.2705e9, "profiles/r01_ncu_fft4096_f32_v2.txt"),
+    "fft4096_f32": (4.26326e9, "profiles/r02_ncu_fft4096_f32_v1.txt"),
     "fft4096_f64": (8.683e9, "profiles/r01_ncu_fft4096_f64_v2.txt"),
     "fft65536_f32": (4.3077e9, "profiles/r01_ncu_fft65536_f32_fused_tma_v2.txt"),
     "iir16384_f32": (1.37387e11, "profiles/r02_ncu_iir16384_f32_delta_v1.txt"),
