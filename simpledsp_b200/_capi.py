@@ -41,6 +41,7 @@ SIGNATURES = {
     "sdsp_b200_fft_exec": (C.c_int, [_vp, _vp, _sz, C.c_int, _vp]),
     "sdsp_b200_fft_exec_real": (C.c_int, [_vp, _vp, _vp, _sz, C.c_int, _vp]),
     "sdsp_b200_fft_exec_r2c": (C.c_int, [_vp, _vp, _vp, _sz, C.c_int, _vp]),
+    "sdsp_b200_fft_exec_c2r": (C.c_int, [_vp, _vp, _vp, _sz, C.c_int, _vp]),
     "sdsp_b200_fft_plan_describe": (C.c_int, [_vp, C.c_char_p, _sz]),
     "sdsp_b200_fft_plan_launches": (C.c_int, [_vp, _sz, C.POINTER(C.c_int)]),
     "sdsp_b200_twiddle_table": (C.c_int, [C.c_uint32, C.c_int, _dp]),

@@ -379,6 +379,63 @@ __global__ void __launch_bounds__(THREADS, MINB)
     }
 }
 
+
+// The way back (sdsp_b200_fft_exec_c2r, reverse plans): bins 0 .. M of a real frame's spectrum in, the n = 2M real samples out, 1/n
+// included (reverse_fft::ScaleValues, reference fft.h:128-132).  The separation runs backwards at the first load -- both terms come
+// from global memory, so it needs no exchange:
+//   Z[k] = 1/2 [ (X[k] + conj X[M - k]) + i conj(W_n^k) (X[k] - conj X[M - k]) ],   z = IDFT_M(Z),   x[2j] + i x[2j + 1] = z[j]
+// with the inverse transform done by the forward passes on swapped components (IDFT(x) = swap(DFT(swap x)) / M, exact).
+template <class Cfg, typename T, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+    fft_c2r_kernel(const cplx<T> *__restrict__ in, cplx<T> *__restrict__ out, const cplx<T> *__restrict__ tw, const cplx<T> *__restrict__ tw_n,
+                   size_t n_frames)
+{
+    constexpr int FPC = THREADS / Cfg::TPF, M = Cfg::N;
+    static_assert(THREADS % Cfg::TPF == 0 && FPC >= 1, "block must hold whole frames");
+    static_assert(32 % Cfg::E == 0, "the 64th-root table covers 2, 4, 8, 16 or 32 points per thread");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx<T> *smem = reinterpret_cast<cplx<T> *>(smem_raw);
+    const int fl = threadIdx.x / Cfg::TPF;
+    const int t = threadIdx.x % Cfg::TPF;
+    cplx<T> *fs = smem + (size_t)fl * Cfg::PADDED_N;
+    const size_t groups = (n_frames + FPC - 1) / FPC;
+    const T half_over_m = (T)(0.5 / (double)M);
+
+    for (size_t g = blockIdx.x; g < groups; g += gridDim.x) {
+        const size_t frame = g * FPC + fl;
+        const bool active = frame < n_frames;
+        cplx<T> v[Cfg::E];
+        if (active) {
+            const cplx<T> *ip = in + frame * (size_t)(M + 1);
+            const cplx<T> wt = tw_n[t];
+#pragma unroll
+            for (int e = 0; e < Cfg::E; e++) {
+                const int k = t + Cfg::S * e;
+                const cplx<T> a = ld_stream(ip + k), xm = ld_stream(ip + (M - k));
+                const cplx<T> b = cplx<T>{ xm.x, -xm.y };
+                const cplx<T> s = a + b, d = a - b;
+                const cplx<T> w = e == 0 ? wt : cmul(wt, w64<T>(e * (32 / Cfg::E)));
+                const cplx<T> r = cmul(d, cplx<T>{ w.x, -w.y }); // conj(W_n^k) (X[k] - conj X[M - k])
+                const cplx<T> z = cplx<T>{ s.x - r.y, s.y + r.x }; // + i r
+                v[e] = cplx<T>{ z.y, z.x };                         // swapped for the inverse
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < Cfg::E; e++)
+                v[e] = cplx<T>{ 0, 0 };
+        }
+        fft_kernel_passes<Cfg, T, THREADS, MINB, 0, false>(v, fs, tw, t, nullptr);
+        if (active) {
+            cplx<T> *op = out + frame * (size_t)M + t;
+#pragma unroll
+            for (int e = 0; e < Cfg::E; e++)
+                st_stream(op + Cfg::S * e, cplx<T>{ v[e].y * half_over_m, v[e].x * half_over_m });
+        }
+        if constexpr (Cfg::NPASS > 1)
+            __syncthreads(); // the last pass has read the exchange buffer before the next group writes it
+    }
+}
+
 // =================================================================================================
 // digit reversal on the device (reference fft.h:217-236).  Base 2: bit reversal of the log2(n) low
 // bits; base 4: the same with the two bits of every digit kept in order.
@@ -2700,10 +2757,28 @@ static int upload_w64()
 }
 
 template <class Cfg, typename T, int THREADS, int MINB>
+static int launch_c2r(const FftPlan &p, const void *half_in, void *real_out, size_t n_frames, cudaStream_t stream)
+{
+    constexpr int FPC = THREADS / Cfg::TPF;
+    const size_t groups = (n_frames + FPC - 1) / FPC;
+    if (groups == 0)
+        return SDSP_B200_OK;
+    const size_t resident = (size_t)p.sm_count * (size_t)p.r2c_ctas;
+    const size_t grid = groups < resident * 4 ? groups : resident * 4;
+    fft_c2r_kernel<Cfg, T, THREADS, MINB><<<(unsigned)grid, THREADS, p.r2c_smem, stream>>>(
+        static_cast<const cplx<T> *>(half_in), static_cast<cplx<T> *>(real_out), static_cast<const cplx<T> *>(p.d_r2c_tw),
+        static_cast<const cplx<T> *>(p.d_r2c_twn), n_frames);
+    SDSP_CUDA(cudaGetLastError());
+    return SDSP_B200_OK;
+}
+
+template <class Cfg, typename T, int THREADS, int MINB>
 static int setup_r2c_cfg(FftPlan &p)
 {
     constexpr int FPC = THREADS / Cfg::TPF;
-    auto kern = fft_r2c_kernel<Cfg, T, THREADS, MINB>;
+    const bool back = p.direction == SDSP_B200_REVERSE; // reverse plans: half spectrum -> real frame
+    const void *kern = back ? reinterpret_cast<const void *>(fft_c2r_kernel<Cfg, T, THREADS, MINB>) :
+                              reinterpret_cast<const void *>(fft_r2c_kernel<Cfg, T, THREADS, MINB>);
     p.r2c_smem = (size_t)FPC * Cfg::PADDED_N * sizeof(cplx<T>);
     if (p.r2c_smem > 48 * 1024)
         SDSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.r2c_smem));
@@ -2733,7 +2808,7 @@ static int setup_r2c_cfg(FftPlan &p)
     }
     SDSP_CUDA(cudaMalloc(&p.d_r2c_twn, wn.size() * sizeof(cplx<T>)));
     SDSP_CUDA(cudaMemcpy(p.d_r2c_twn, wn.data(), wn.size() * sizeof(cplx<T>), cudaMemcpyHostToDevice));
-    p.r2c_launch = &launch_r2c<Cfg, T, THREADS, MINB>;
+    p.r2c_launch = back ? &launch_c2r<Cfg, T, THREADS, MINB> : &launch_r2c<Cfg, T, THREADS, MINB>;
     return SDSP_B200_OK;
 }
 
@@ -2802,13 +2877,11 @@ static int setup_r2c(FftPlan &p)
 {
     if (p.r2c_ready)
         return SDSP_B200_OK;
-    if (p.direction != SDSP_B200_FORWARD)
-        return set_error(SDSP_B200_ERR_INVALID_ARG, "fft_exec_r2c: the plan must be a forward one");
     if (p.n < 4)
         return set_error(SDSP_B200_ERR_UNSUPPORTED, "fft_exec_r2c: n=%u (needs at least 4 points)", p.n);
     const int lg = ilog2(p.n) - 1;
     int rc;
-    if (lg == 15 && p.precision == SDSP_B200_F32 && p.real64k_ctas > 0) {
+    if (lg == 15 && p.precision == SDSP_B200_F32 && p.real64k_ctas > 0 && p.direction == SDSP_B200_FORWARD) {
         p.r2c_launch = &launch_r2c_real64k;
         rc = SDSP_B200_OK;
     } else
@@ -2818,7 +2891,7 @@ static int setup_r2c(FftPlan &p)
             SDSP_FOR_EACH_LG(X)
 #undef X
         default:
-            rc = set_error(SDSP_B200_ERR_UNSUPPORTED, "fft_exec_r2c: n=%u is not built (f32 up to 65536, f64 up to 16384 points)", p.n);
+            rc = set_error(SDSP_B200_ERR_UNSUPPORTED, "fft_exec_r2c / _c2r: n=%u is not built (f32 up to 65536 forward / 32768 reverse, f64 up to 16384 points)", p.n);
         }
     if (rc == SDSP_B200_OK)
         p.r2c_ready = true;
@@ -3052,44 +3125,49 @@ int sdsp_b200_fft_exec_real(sdsp_b200_fft_plan plan, const void *real_in, void *
 }
 
 
-// real frames in (n scalars), half spectra out (n / 2 + 1 bins per frame, frames n / 2 + 1 bins apart), out of place, forward
-int sdsp_b200_fft_exec_r2c(sdsp_b200_fft_plan plan, const void *real_in, void *half_spectrum_out, size_t n_frames, int ptr_kind, void *stream)
+// real frames <-> half spectra (n / 2 + 1 bins per frame, frames n / 2 + 1 bins apart), out of place.  back = false: real in, half
+// spectra out (forward plans); back = true: half spectra in, real frames out (reverse plans, 1/n included)
+static int exec_half(sdsp_b200_fft_plan plan, const void *in, void *out, size_t n_frames, int ptr_kind, void *stream, bool back)
 {
+    const char *who = back ? "fft_exec_c2r" : "fft_exec_r2c";
     if (!plan)
-        return set_error(SDSP_B200_ERR_INVALID_ARG, "fft_exec_r2c: null plan");
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "%s: null plan", who);
     if (n_frames == 0)
         return SDSP_B200_OK;
-    if (!real_in || !half_spectrum_out)
-        return set_error(SDSP_B200_ERR_INVALID_ARG, "fft_exec_r2c: null data");
+    if (!in || !out)
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "%s: null data", who);
     FftPlan &p = plan->p;
+    if ((p.direction == SDSP_B200_REVERSE) != back)
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "%s: the plan must be a %s one", who, back ? "reverse" : "forward");
     SDSP_CUDA(cudaSetDevice(p.device));
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     const size_t es = p.precision == SDSP_B200_F32 ? sizeof(float) : sizeof(double);
     if (ptr_kind != SDSP_B200_PTR_DEVICE && ptr_kind != SDSP_B200_PTR_HOST)
-        return set_error(SDSP_B200_ERR_INVALID_ARG, "fft_exec_r2c: bad ptr_kind %d", ptr_kind);
-    if ((reinterpret_cast<uintptr_t>(half_spectrum_out) % (2 * es)) != 0 ||
-        (reinterpret_cast<uintptr_t>(real_in) % (ptr_kind == SDSP_B200_PTR_DEVICE ? 2 * es : es)) != 0)
-        return set_error(SDSP_B200_ERR_INVALID_ARG, "fft_exec_r2c: device buffers must be aligned to one complex element (the real frame is read in pairs)");
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "%s: bad ptr_kind %d", who, ptr_kind);
+    const void *real_side = back ? out : in, *cplx_side = back ? in : out;
+    if ((reinterpret_cast<uintptr_t>(cplx_side) % (2 * es)) != 0 ||
+        (reinterpret_cast<uintptr_t>(real_side) % (ptr_kind == SDSP_B200_PTR_DEVICE ? 2 * es : es)) != 0)
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "%s: device buffers must be aligned to one complex element (the real frame is accessed in pairs)", who);
     std::lock_guard<std::mutex> lock(p.mu);
     int rc = setup_r2c(p);
     if (rc)
         return rc;
     if (ptr_kind == SDSP_B200_PTR_DEVICE)
-        return p.r2c_launch(p, real_in, half_spectrum_out, n_frames, s);
-    // host buffers: slabs through the plan's staging memory, each buffer = half-spectrum slab + real slab behind it
+        return p.r2c_launch(p, in, out, n_frames, s);
+    // host buffers: slabs through the plan's staging memory, each buffer = output slab + input slab behind it
     if (s)
         SDSP_CUDA(cudaStreamSynchronize(s));
     rc = p.host.ensure();
     if (rc)
         return rc;
-    const size_t in_bytes = (size_t)p.n * es, out_bytes = ((size_t)p.n / 2 + 1) * 2 * es;
-    const size_t out_slot = (out_bytes + 15) / 16 * 16; // (per frame, only to size the slab; frames stay n / 2 + 1 bins apart)
-    size_t slab = (64u << 20) / (in_bytes + out_slot);
+    const size_t real_bytes = (size_t)p.n * es, half_bytes = ((size_t)p.n / 2 + 1) * 2 * es;
+    const size_t in_bytes = back ? half_bytes : real_bytes, out_bytes = back ? real_bytes : half_bytes;
+    size_t slab = (64u << 20) / (in_bytes + out_bytes);
     slab = slab < 1 ? 1 : slab > n_frames ? n_frames : slab;
     const int nbuf = n_frames > slab ? 2 : 1;
-    const size_t out_slab = (slab * out_bytes + 255) / 256 * 256;
-    const size_t buf_bytes = out_slab + slab * in_bytes;
-    rc = ensure_device_stage(p.d_stage, p.stage_bytes, buf_bytes * nbuf, "fft_exec_r2c");
+    const size_t out_slab = (slab * out_bytes + 255) / 256 * 256, in_slab = (slab * in_bytes + 255) / 256 * 256;
+    const size_t buf_bytes = out_slab + in_slab;
+    rc = ensure_device_stage(p.d_stage, p.stage_bytes, buf_bytes * nbuf, who);
     if (rc)
         return rc;
     int which = 0;
@@ -3098,7 +3176,7 @@ int sdsp_b200_fft_exec_r2c(sdsp_b200_fft_plan plan, const void *real_in, void *h
         const size_t cnt = (n_frames - done) < slab ? (n_frames - done) : slab;
         char *d_out = static_cast<char *>(p.d_stage) + (size_t)which * buf_bytes, *d_in = d_out + out_slab;
         cudaStream_t cs = p.host.stream[which];
-        if (cudaMemcpyAsync(d_in, static_cast<const char *>(real_in) + done * in_bytes, cnt * in_bytes, cudaMemcpyHostToDevice, cs) != cudaSuccess)
+        if (cudaMemcpyAsync(d_in, static_cast<const char *>(in) + done * in_bytes, cnt * in_bytes, cudaMemcpyHostToDevice, cs) != cudaSuccess)
             rc = cuda_fail((int)cudaGetLastError(), "H2D", __FILE__, __LINE__);
         if (rc == SDSP_B200_OK && !first && cudaStreamWaitEvent(cs, p.host.kernel_done[which ^ 1], 0) != cudaSuccess)
             rc = cuda_fail((int)cudaGetLastError(), "cudaStreamWaitEvent", __FILE__, __LINE__);
@@ -3106,13 +3184,22 @@ int sdsp_b200_fft_exec_r2c(sdsp_b200_fft_plan plan, const void *real_in, void *h
             rc = p.r2c_launch(p, d_in, d_out, cnt, cs);
         if (rc == SDSP_B200_OK && cudaEventRecord(p.host.kernel_done[which], cs) != cudaSuccess)
             rc = cuda_fail((int)cudaGetLastError(), "cudaEventRecord", __FILE__, __LINE__);
-        if (rc == SDSP_B200_OK &&
-            cudaMemcpyAsync(static_cast<char *>(half_spectrum_out) + done * out_bytes, d_out, cnt * out_bytes, cudaMemcpyDeviceToHost, cs) != cudaSuccess)
+        if (rc == SDSP_B200_OK && cudaMemcpyAsync(static_cast<char *>(out) + done * out_bytes, d_out, cnt * out_bytes, cudaMemcpyDeviceToHost, cs) != cudaSuccess)
             rc = cuda_fail((int)cudaGetLastError(), "D2H", __FILE__, __LINE__);
         which = (which + 1) % nbuf;
         first = false;
     }
     return p.host.drain(rc);
+}
+
+int sdsp_b200_fft_exec_r2c(sdsp_b200_fft_plan plan, const void *real_in, void *half_spectrum_out, size_t n_frames, int ptr_kind, void *stream)
+{
+    return exec_half(plan, real_in, half_spectrum_out, n_frames, ptr_kind, stream, false);
+}
+
+int sdsp_b200_fft_exec_c2r(sdsp_b200_fft_plan plan, const void *half_spectrum_in, void *real_out, size_t n_frames, int ptr_kind, void *stream)
+{
+    return exec_half(plan, half_spectrum_in, real_out, n_frames, ptr_kind, stream, true);
 }
 
 int sdsp_b200_fft_plan_describe(sdsp_b200_fft_plan plan, char *buf, size_t buf_len)
