@@ -49,6 +49,8 @@ WORKLOADS = {
     "fftr2c4096_f32": dict(kind="fft", n=4096, frames=131072, precision="f32", bytes_per_sample=8, real_input=True, half=True),
     "fftr2c4096_f64": dict(kind="fft", n=4096, frames=65536, precision="f64", bytes_per_sample=16, real_input=True, half=True),
     "fftr2c65536_f32": dict(kind="fft", n=65536, frames=4096, precision="f32", bytes_per_sample=8, real_input=True, half=True),
+    # half spectra in, real frames out (sdsp_b200_fft_exec_c2r, 1/n included)
+    "fftc2r4096_f32": dict(kind="fft", n=4096, frames=131072, precision="f32", bytes_per_sample=8, real_input=True, half=True, back=True),
     "fft131072_f32": dict(kind="fft", n=131072, frames=2048, precision="f32", bytes_per_sample=16),
     "fft262144_f32": dict(kind="fft", n=262144, frames=1024, precision="f32", bytes_per_sample=16),
     "fft16384_f32": dict(kind="fft", n=16384, frames=16384, precision="f32", bytes_per_sample=16),
@@ -242,7 +244,12 @@ class FftWorkload:
         self.inv = S.FftPlan(self.n, self.radix, self.prec, K.REVERSE, device)
         g = torch.Generator(device="cuda").manual_seed(1234 + device)
         self.half = bool(spec.get("half"))
-        if self.half:  # half spectra out: frames of n/2 + 1 bins
+        self.back = bool(spec.get("back"))
+        if self.back:  # half spectra in (of real signals: bins 0 and n/2 real)
+            self.data = torch.randn(self.frames, self.n // 2 + 1, 2, device="cuda", generator=g, dtype=self.rdtype)
+            self.data[:, 0, 1] = 0
+            self.data[:, -1, 1] = 0
+        elif self.half:  # half spectra out: frames of n/2 + 1 bins
             self.data = torch.zeros(self.frames, self.n // 2 + 1, 2, device="cuda", dtype=self.rdtype)
         else:
             self.data = torch.randn(self.frames, self.n, 2, device="cuda", generator=g, dtype=self.rdtype)
@@ -257,7 +264,7 @@ class FftWorkload:
 
     def describe(self):
         if self.half:
-            return "real frames in, half spectra (n/2 + 1 bins) out: the n/2-point configuration of: " + self.S.FftPlan(
+            return ("half spectra in, real frames out" if self.back else "real frames in, half spectra (n/2 + 1 bins) out") + ": the n/2-point configuration of: " + self.S.FftPlan(
                 self.n // 2, 2, self.prec, self.K.FORWARD, self.fwd.device).describe()
         return ("real frames in, spectra out: " if self.real_input else "") + self.fwd.describe()
 
@@ -265,6 +272,10 @@ class FftWorkload:
         return self.fwd.launches(self.frames)
 
     def step(self):
+        if self.back:
+            self.inv.exec_c2r_ptr(self.data.data_ptr(), self.real.data_ptr(), self.frames, self.K.PTR_DEVICE, self.stream)
+            self.step_no += 1
+            return
         if self.half:
             self.fwd.exec_r2c_ptr(self.real.data_ptr(), self.data.data_ptr(), self.frames, self.K.PTR_DEVICE, self.stream)
             self.step_no += 1
@@ -280,6 +291,12 @@ class FftWorkload:
     def self_check(self):
         """After an even number of steps the batch is the input again (forward then reverse).  Real input: sampled spectra
         against torch.fft of the same frames."""
+        if self.back:
+            torch = self.torch
+            torch.cuda.synchronize()
+            ref = torch.fft.irfft(torch.view_as_complex(self.data[self.check_idx]).to(torch.complex128), n=self.n)
+            got = self.real[self.check_idx].double()
+            return float(((got - ref).pow(2).sum(dim=1).sqrt() / ref.pow(2).sum(dim=1).sqrt()).max())
         if self.real_input:
             torch = self.torch
             torch.cuda.synchronize()

@@ -110,6 +110,21 @@ namespace detail
         check(sdsp_b200_fft_exec(h->plan, frames, n_frames, ptr_kind, stream), "sdsp_b200_fft_exec");
     }
 
+    template <typename S>
+    void run_c2r(const std::complex<S> *half_spectra, S *real_frames, uint32_t n, size_t n_frames, int ptr_kind, void *stream)
+    {
+        thread_local std::vector<std::pair<uint32_t, std::unique_ptr<plan_holder>>> cache;
+        plan_holder *h = nullptr;
+        for (auto &e : cache)
+            if (e.first == n)
+                h = e.second.get();
+        if (!h) {
+            cache.emplace_back(n, std::make_unique<plan_holder>(n, 2, precision_of<S>(), SDSP_B200_REVERSE));
+            h = cache.back().second.get();
+        }
+        check(sdsp_b200_fft_exec_c2r(h->plan, half_spectra, real_frames, n_frames, ptr_kind, stream), "sdsp_b200_fft_exec_c2r");
+    }
+
     template <class T, int RADIX, typename S, bool HALF = false>
     void run_real(const S *real_frames, std::complex<S> *spectra, uint32_t n, size_t n_frames, int ptr_kind, void *stream)
     {
@@ -366,5 +381,16 @@ template <typename S>
 void fft_half_spectrum_device(const S *real_frames, std::complex<S> *half_spectra, size_t n, size_t n_frames, void *stream = nullptr)
 {
     detail::run_real<forward_fft, 2, S, true>(real_frames, half_spectra, static_cast<uint32_t>(n), n_frames, SDSP_B200_PTR_DEVICE, stream);
+}
+// and back: half spectra in, real frames out, 1/n included (reverse_fft's scaling, reference fft.h:128-132)
+template <typename S>
+void fft_real_from_half_spectrum(const std::complex<S> *half_spectra, S *real_frames, size_t n, size_t n_frames)
+{
+    detail::run_c2r<S>(half_spectra, real_frames, static_cast<uint32_t>(n), n_frames, SDSP_B200_PTR_HOST, nullptr);
+}
+template <typename S>
+void fft_real_from_half_spectrum_device(const std::complex<S> *half_spectra, S *real_frames, size_t n, size_t n_frames, void *stream = nullptr)
+{
+    detail::run_c2r<S>(half_spectra, real_frames, static_cast<uint32_t>(n), n_frames, SDSP_B200_PTR_DEVICE, stream);
 }
 } // namespace sdsp

@@ -92,6 +92,34 @@ class FftPlan:
         self.exec_r2c_ptr(real_in.data_ptr(), out.data_ptr(), real_in.numel() // n, K.PTR_DEVICE, torch.cuda.current_stream().cuda_stream)
         return out
 
+    def exec_c2r_ptr(self, half_ptr: int, real_ptr: int, n_frames: int, ptr_kind: int, stream=None) -> None:
+        """n_frames half spectra of n/2 + 1 complex at half_ptr -> n_frames real frames of n scalars at real_ptr (reverse plans)."""
+        K.check(K.lib().sdsp_b200_fft_exec_c2r(self._h, half_ptr, real_ptr, n_frames, ptr_kind, stream))
+
+    def real_from_half_spectrum(self, half_in, out=None):
+        """The way back from half_spectrum (reverse plans, 1/n included): shape (..., n/2 + 1) complex -> (..., n) real."""
+        n = self.n
+        if half_in.shape[-1] != n // 2 + 1:
+            raise ValueError(f"last dimension must be {n // 2 + 1}")
+        shape = tuple(half_in.shape[:-1]) + (n,)
+        frames = 1
+        for d in shape[:-1]:
+            frames *= int(d)
+        if isinstance(half_in, np.ndarray):
+            x = np.ascontiguousarray(half_in, dtype=np.complex64 if self.precision == K.F32 else np.complex128)
+            if out is None:
+                out = np.empty(shape, dtype=np.float32 if self.precision == K.F32 else np.float64)
+            self.exec_c2r_ptr(x.ctypes.data, out.ctypes.data, frames, K.PTR_HOST, None)
+            return out
+        import torch
+
+        if half_in.device.index != self.device:
+            raise ValueError("tensor lives on another device than the plan")
+        if out is None:
+            out = torch.empty(shape, device=half_in.device, dtype=torch.float32 if self.precision == K.F32 else torch.float64)
+        self.exec_c2r_ptr(half_in.data_ptr(), out.data_ptr(), frames, K.PTR_DEVICE, torch.cuda.current_stream().cuda_stream)
+        return out
+
     def __call__(self, data):
         """Transform every length-n row of ``data`` in place (numpy: staged through the device;
         torch CUDA tensor: in place on the current stream, asynchronously).  Returns ``data``."""

@@ -95,6 +95,15 @@ int main()
         std::vector<std::complex<double>> halfd((N / 2 + 1) * frames);
         sdsp::fft_half_spectrum(reald.data(), halfd.data(), N, frames);
         CHECK(rel_l2(halfd.data(), hr.data(), hr.size()) < 1e-12, "fp64 half spectrum off by more than 1e-12 rel-L2");
+        // and back: the real frames again, 1/N included
+        std::vector<double> backd(N * frames);
+        sdsp::fft_real_from_half_spectrum(halfd.data(), backd.data(), N, frames);
+        double num = 0, den = 0;
+        for (size_t i = 0; i < N * frames; i++) {
+            num += (backd[i] - reald[i]) * (backd[i] - reald[i]);
+            den += reald[i] * reald[i];
+        }
+        CHECK(std::sqrt(num / den) < 1e-12, "fp64 real_from_half_spectrum(half_spectrum(x)) != x");
     }
     // ---- a bank of channels against one filter object per channel (reference signature, casc_2o_iir.h:36-80)
     {

@@ -270,6 +270,44 @@ def test_half_spectrum_of_real_frames_matches_oracle(n, prec):
     assert np.array_equal(y1.cpu().numpy(), got[:1])
 
 
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+@pytest.mark.parametrize("n", [4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768])
+def test_real_frames_back_from_half_spectra(n, prec):
+    """sdsp_b200_fft_exec_c2r (reverse plans): bins 0 .. n/2 in, real frames out with reverse_fft's 1/n (fft.h:128-132).  Against the
+    oracle's REVERSE transform of the full, mirror-completed spectrum; the round trip through exec_r2c; host buffers = same bits."""
+    torch = pytest.importorskip("torch")
+    code, dt = PREC[prec]
+    if prec == "f64" and n > 16384:
+        with pytest.raises(RuntimeError):
+            S.FftPlan(n, 2, code, K.REVERSE).real_from_half_spectrum(np.zeros((1, n // 2 + 1), dtype=np.complex128))
+        return
+    frames = 261 if n <= 256 else 37 if n <= 4096 else 9
+    rng = np.random.default_rng(n + 2)
+    m = n // 2
+    half = (rng.standard_normal((frames, m + 1)) + 1j * rng.standard_normal((frames, m + 1))).astype(np.complex64).astype(dt)
+    half[:, 0] = half[:, 0].real  # what a real signal's spectrum looks like
+    half[:, m] = half[:, m].real
+    full = np.concatenate([half, np.conj(half[:, m - 1:0:-1])], axis=1).astype(np.complex128)
+    ref = oracle_fft(full, inverse=True)
+    assert np.abs(ref.imag).max() <= 1e-9 * np.abs(ref.real).max()
+    inv = S.FftPlan(n, 2, code, K.REVERSE)
+    hd = torch.from_numpy(half).cuda()
+    xd = inv.real_from_half_spectrum(hd)
+    torch.cuda.synchronize()
+    got = xd.cpu().numpy()
+    assert got.shape == (frames, n)
+    assert rel_l2(got, ref.real) <= FFT_TOL[prec]
+    assert torch.equal(hd.cpu(), torch.from_numpy(half))
+    assert np.array_equal(inv.real_from_half_spectrum(half), got)
+    # round trip
+    fwd = S.FftPlan(n, 2, code, K.FORWARD)
+    again = fwd.half_spectrum(xd)
+    torch.cuda.synchronize()
+    assert rel_l2(again.cpu().numpy(), half.astype(np.complex128)) <= 2 * FFT_TOL[prec]
+    with pytest.raises(RuntimeError):
+        fwd.real_from_half_spectrum(hd)  # needs a reverse plan
+
+
 def test_half_spectrum_full_size_and_errors():
     """Config-2-sized batch of real frames (65536 x 4096, fp32) against torch.fft.rfft, and the argument checks."""
     torch = pytest.importorskip("torch")
