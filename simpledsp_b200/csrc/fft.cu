@@ -1951,6 +1951,12 @@ __global__ void __launch_bounds__(288, MINB)
 // 17 items per frame instead of 32, the output is conjugate-symmetric to the bit.  Queue order: column tiles of frame f + LAG, then
 // row tiles of frame f; a row tile waits for its frame's 8 column tiles, a column tile for the 9 row tiles of the ring slot's
 // previous tenant -- both hold smaller tickets.
+#ifndef SDSP_REAL_NST
+#define SDSP_REAL_NST 2 // tile slots per CTA
+#endif
+#ifndef SDSP_REAL_MINB
+#define SDSP_REAL_MINB SDSP_FUSED_TMA_MINB
+#endif
 #ifndef SDSP_REAL_LAG
 #define SDSP_REAL_LAG 96 // frames between a frame's column tiles and its row tiles (x 17 items; the ring holds twice that, 51 MB, a third of it pinned in L2: profiles/r02_fft_l2_persist_sweep.txt; 64 was best without the pinning)
 #endif
@@ -1983,7 +1989,7 @@ __global__ void __launch_bounds__(288, MINB)
     constexpr int XBUF = 16 * PITCH;
     constexpr size_t FRAME = (size_t)N1 * N2, RFRAME = (size_t)REAL_ROWS * N2; // output frame; ring frame (rows 0 .. 128)
     constexpr uint32_t TILE_BYTES = 4096 * sizeof(cplx<T>);
-    constexpr int NST = 2, ND = NST + 1;
+    constexpr int NST = SDSP_REAL_NST, ND = NST + 1;
     constexpr int SLOT = (XBUF + 15) / 16 * 16;
     extern __shared__ __align__(128) unsigned char smem_raw128[];
     cplx<T> *stage0 = reinterpret_cast<cplx<T> *>(smem_raw128);
@@ -2327,7 +2333,7 @@ static int launch_real64k(const FftPlan &p, void *data, const void *real_in, siz
         cfg.attrs = attr;
         cfg.numAttrs = 1;
     }
-    SDSP_CUDA(cudaLaunchKernelEx(&cfg, fft_real64k_kernel<T, SDSP_FUSED_TMA_MINB>, map, reinterpret_cast<cplx<T> *>(data),
+    SDSP_CUDA(cudaLaunchKernelEx(&cfg, fft_real64k_kernel<T, SDSP_REAL_MINB>, map, reinterpret_cast<cplx<T> *>(data),
                                  reinterpret_cast<cplx<T> *>(p.d_scratch), reinterpret_cast<const cplx<T> *>(p.d_tw_rows),
                                  reinterpret_cast<const cplx<T> *>(p.d_tw_hi), reinterpret_cast<const cplx<T> *>(p.d_tw_lo), ctr, ctr + 1,
                                  ctr + 1 + n_frames, n_frames, half ? 1 : 0));
@@ -2498,9 +2504,9 @@ static int setup_fused(FftPlan &p)
             if constexpr (N1 == 256) { // forward real-input frames: the half-work queue (SDSP_B200_FFT_REAL64K=0 keeps the complex kernels)
                 const char *e = getenv("SDSP_B200_FFT_REAL64K");
                 if (!e || atoi(e) != 0) {
-                    auto rk = fft_real64k_kernel<T, MINB>;
+                    auto rk = fft_real64k_kernel<T, SDSP_REAL_MINB>;
                     const size_t slot = ((size_t)16 * LargeStride<Cfg>::value + 15) / 16 * 16;
-                    const size_t rsmem = (2 * slot + 512) * sizeof(cplx<T>) + 128;
+                    const size_t rsmem = (SDSP_REAL_NST * slot + 512) * sizeof(cplx<T>) + 128;
                     int rocc = 0;
                     if (cudaFuncSetAttribute(rk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem) == cudaSuccess &&
                         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&rocc, rk, 288, rsmem) == cudaSuccess && rocc >= 1 &&

@@ -1,9 +1,10 @@
 mkdir -p gpurun_out
-L=gpurun_out/r02_fft_c2r.log
-run() { timeout 300 python bench.py --steps $2 --warmup 3 --no-e2e --no-cpu --no-secondary --workload $1 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$3', d['config']['workload'], round(d['ms_per_step'],4), round(d['value']), round(d['roofline']['achieved'],1), round(d['roofline']['frac'],4), d['self_check'], d['clocks']['sm_mhz'], d['clocks']['reasons'])" >> $L 2>&1; }
+L=gpurun_out/r02_fft_nst3.log
+run() { timeout 120 python bench.py --steps $2 --warmup 3 --no-e2e --no-cpu --no-secondary --workload $1 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$3', d['config']['workload'], round(d['ms_per_step'],4), round(d['value']), round(d['roofline']['achieved'],1), round(d['roofline']['frac'],4), d['self_check'], d['clocks']['sm_mhz'], d['clocks']['reasons'])" >> $L 2>&1; }
 rm -f $L
 for rep in 1 2; do
-run fftc2r4096_f32 20 "c2r"
-run fftr2c4096_f32 20 "r2c"
-done
+for lib in lib lib_nst3; do
+for w in fftreal65536_f32 fftr2c65536_f32; do
+SDSP_B200_LIB=$PWD/simpledsp_b200/$lib/libsdsp_b200.so run $w 20 "$lib"
+done; done; done
 cat $L
