@@ -1,10 +1,2 @@
 mkdir -p gpurun_out
-L=gpurun_out/r02_fft_nst3.log
-run() { timeout 120 python bench.py --steps $2 --warmup 3 --no-e2e --no-cpu --no-secondary --workload $1 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$3', d['config']['workload'], round(d['ms_per_step'],4), round(d['value']), round(d['roofline']['achieved'],1), round(d['roofline']['frac'],4), d['self_check'], d['clocks']['sm_mhz'], d['clocks']['reasons'])" >> $L 2>&1; }
-rm -f $L
-for rep in 1 2; do
-for lib in lib lib_nst3; do
-for w in fftreal65536_f32 fftr2c65536_f32; do
-SDSP_B200_LIB=$PWD/simpledsp_b200/$lib/libsdsp_b200.so run $w 20 "$lib"
-done; done; done
-cat $L
+PYTHONPATH=$PWD timeout 600 python tools/experiments/r2c_sweep.py > gpurun_out/r02_r2c_sweep.log 2>&1; cat gpurun_out/r02_r2c_sweep.log
