@@ -45,8 +45,10 @@ class IirBank:
 
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
-            K.lib().sdsp_b200_iir_bank_destroy(self._h)
-            self._h = C.c_void_p()
+            lib = getattr(K, "lib", None)  # (module globals are already gone when this runs at interpreter exit)
+            if lib is not None:
+                lib().sdsp_b200_iir_bank_destroy(self._h)
+                self._h = C.c_void_p()
 
     __del__ = close
 
