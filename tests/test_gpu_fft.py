@@ -325,6 +325,13 @@ def test_half_spectrum_full_size_and_errors():
         S.FftPlan(n, 4, K.F32, K.REVERSE).half_spectrum(x[:2].contiguous())
     with pytest.raises(RuntimeError):
         S.FftPlan(2, 2, K.F32, K.FORWARD).half_spectrum(np.zeros((3, 2), dtype=np.float32))
+    # an empty batch is a no-op; a real frame that does not start on a pair boundary is refused (the kernel reads it in pairs)
+    plan.exec_r2c_ptr(x.data_ptr(), y.data_ptr(), 0, K.PTR_DEVICE, None)
+    with pytest.raises(RuntimeError):
+        plan.exec_r2c_ptr(x.data_ptr() + 4, y.data_ptr(), 1, K.PTR_DEVICE, torch.cuda.current_stream().cuda_stream)
+    with pytest.raises(RuntimeError):
+        plan.exec_r2c_ptr(x.data_ptr(), y.data_ptr(), 1, 7, None)
+    torch.cuda.synchronize()
 
 
 @pytest.mark.parametrize("frames", [1, 2, 31, 32, 33, 47, 48, 49, 63, 64, 65, 87, 88, 89, 95, 96, 97, 127, 128, 129, 175, 176, 177, 191, 192, 193, 200, 365, 401])
