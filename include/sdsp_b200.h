@@ -121,12 +121,14 @@ int sdsp_b200_fft_exec_real(sdsp_b200_fft_plan plan, const void *real_in, void *
  * values apart), out of place, forward plans only.  The bins above n/2 are the conjugates of those below, X[n - k] = conj X[k],
  * so nothing is lost against the reference's convention (real part filled, imaginary part zero, full spectrum back:
  * test/testFFT.cpp:24, :86) while the call moves 4 + 4 bytes per sample instead of 8 + 8 (fp32).  On the device the frame
- * is read as n/2 complex numbers, transformed by the n/2-point kernel and separated in one more exchange.
- * n = 4 .. 65536 (f32) / 4 .. 16384 (f64); device buffers aligned to one complex element. */
+ * is read as n/2 complex numbers, transformed by the n/2-point kernel and separated in one more exchange
+ * (n = 4 .. 65536 in f32, 4 .. 16384 in f64; larger frames go through the plan's full-length transform and a temporary of full
+ * spectra: complete, not fast).  Device buffers aligned to one complex element. */
 int sdsp_b200_fft_exec_r2c(sdsp_b200_fft_plan plan, const void *real_in, void *half_spectrum_out, size_t n_frames, int ptr_kind, void *stream);
 /* The way back, for REVERSE plans: half spectra in (n/2 + 1 bins per frame), real frames out (n scalars each), 1/n included as in
  * reverse_fft::ScaleValues (fft.h:128-132); the imaginary parts of bins 0 and n/2 are ignored, as the mirror symmetry demands.
- * exec_c2r(exec_r2c(x)) == x to rounding.  n = 4 .. 32768 (f32) / 4 .. 16384 (f64). */
+ * exec_c2r(exec_r2c(x)) == x to rounding.  Direct kernel for n = 4 .. 32768 (f32) / 4 .. 16384 (f64); larger frames through the
+ * plan's full-length transform and a temporary. */
 int sdsp_b200_fft_exec_c2r(sdsp_b200_fft_plan plan, const void *half_spectrum_in, void *real_out, size_t n_frames, int ptr_kind, void *stream);
 /* human-readable description of the factorisation / launch geometry the plan chose */
 int sdsp_b200_fft_plan_describe(sdsp_b200_fft_plan plan, char *buf, size_t buf_len);

@@ -498,7 +498,9 @@ struct FftPlan {
     int real64k_ctas = 0;  // > 0: forward real-input frames of 65536 points take fft_real64k_kernel (resident CTAs per SM)
     size_t real64k_smem = 0;
     // half-spectrum path (sdsp_b200_fft_exec_r2c): an n/2-point complex transform plus a separation step; set up at the first call
-    bool r2c_ready = false;
+    bool r2c_ready = false, r2c_through_full = false;
+    void *d_half_tmp = nullptr; // full-spectrum temporary of the sizes without a direct half-spectrum kernel
+    size_t half_tmp_bytes = 0;
     fft_r2c_launch_fn r2c_launch = nullptr;
     void *d_r2c_tw = nullptr, *d_r2c_twn = nullptr;
     size_t r2c_smem = 0;
@@ -2730,6 +2732,7 @@ static int emulate_for(int precision, bool inverse, void *frame)
 
 
 // ---- half-spectrum plans (sdsp_b200_fft_exec_r2c): the M = n / 2 point configuration of the table above behind fft_r2c_kernel
+constexpr int R2C_NO_DIRECT_KERNEL = -12345; // (internal) the size has no M-point one-CTA configuration: take the path through the full spectrum
 template <class Cfg, typename T, int THREADS, int MINB>
 static int launch_r2c(const FftPlan &p, const void *real_in, void *half_out, size_t n_frames, cudaStream_t stream)
 {
@@ -2841,7 +2844,7 @@ static int setup_r2c_for(FftPlan &p) // LG = log2(n / 2)
         constexpr int MB = LG == 13 ? 1 : (C::MINB > 2 ? 2 : C::MINB);
         return setup_r2c_cfg<typename C::type, double, C::THREADS, MB>(p);
     } else
-        return set_error(SDSP_B200_ERR_UNSUPPORTED, "fft_exec_r2c: n=%u in f64 is not built (up to 16384)", p.n);
+        return R2C_NO_DIRECT_KERNEL;
 }
 
 #define SDSP_FOR_EACH_LG(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14)
@@ -2879,6 +2882,85 @@ static int emulate_dispatch(uint32_t n, int precision, bool inverse, void *frame
 }
 
 
+
+// Sizes without a direct half-spectrum kernel (fp32 frames of 2^17 / 2^18 points, fp32 reverse of 2^16, fp64 from 2^15): through
+// the plan's own full-length transform and a temporary of full spectra, a slab of frames at a time -- complete rather than fast
+// (two extra passes over a slab that stays in L2 when it is small).
+template <typename T>
+__global__ void half_compact_kernel(const cplx<T> *__restrict__ full, cplx<T> *__restrict__ half, uint32_t n, size_t frames)
+{
+    const size_t bins = (size_t)n / 2 + 1, total = frames * bins;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t f = i / bins, k = i % bins;
+        half[i] = full[f * n + k];
+    }
+}
+template <typename T>
+__global__ void half_expand_kernel(const cplx<T> *__restrict__ half, cplx<T> *__restrict__ full, uint32_t n, size_t frames)
+{
+    const size_t bins = (size_t)n / 2 + 1, total = frames * (size_t)n;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t f = i / n, k = i % n;
+        cplx<T> v;
+        if (k < bins) {
+            v = half[f * bins + k];
+            if (k == 0 || k == n / 2)
+                v.y = 0; // a real signal's spectrum is real there; whatever the caller left in the imaginary part is ignored
+        } else {
+            const cplx<T> m = half[f * bins + (n - k)];
+            v = cplx<T>{ m.x, -m.y };
+        }
+        full[i] = v;
+    }
+}
+template <typename T>
+__global__ void real_part_kernel(const cplx<T> *__restrict__ full, T *__restrict__ out, size_t total)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = full[i].x;
+}
+
+template <typename T>
+static int launch_half_through_full(const FftPlan &p, const void *in, void *out, size_t n_frames, cudaStream_t stream)
+{
+    FftPlan &mp = const_cast<FftPlan &>(p);
+    const bool back = p.direction == SDSP_B200_REVERSE;
+    const size_t frame_bytes = (size_t)p.n * sizeof(cplx<T>), bins = (size_t)p.n / 2 + 1;
+    size_t slab = (256u << 20) / frame_bytes;
+    slab = slab < 1 ? 1 : slab > n_frames ? n_frames : slab;
+    if (mp.half_tmp_bytes < slab * frame_bytes) {
+        if (mp.d_half_tmp)
+            cudaFree(mp.d_half_tmp);
+        mp.d_half_tmp = nullptr;
+        mp.half_tmp_bytes = 0;
+        if (cudaMalloc(&mp.d_half_tmp, slab * frame_bytes) != cudaSuccess) {
+            cudaGetLastError();
+            return set_error(SDSP_B200_ERR_OOM, "fft: cannot allocate %zu bytes for the full-spectrum temporary", slab * frame_bytes);
+        }
+        mp.half_tmp_bytes = slab * frame_bytes;
+    }
+    cplx<T> *tmp = static_cast<cplx<T> *>(mp.d_half_tmp);
+    const unsigned grid = (unsigned)p.sm_count * 8;
+    for (size_t done = 0; done < n_frames; done += slab) {
+        const size_t cnt = (n_frames - done) < slab ? (n_frames - done) : slab;
+        int rc;
+        if (!back) {
+            rc = p.launch(p, tmp, static_cast<const T *>(in) + done * p.n, cnt, stream);
+            if (rc)
+                return rc;
+            half_compact_kernel<T><<<grid, 256, 0, stream>>>(tmp, static_cast<cplx<T> *>(out) + done * bins, p.n, cnt);
+        } else {
+            half_expand_kernel<T><<<grid, 256, 0, stream>>>(static_cast<const cplx<T> *>(in) + done * bins, tmp, p.n, cnt);
+            rc = p.launch(p, tmp, nullptr, cnt, stream);
+            if (rc)
+                return rc;
+            real_part_kernel<T><<<grid, 256, 0, stream>>>(tmp, static_cast<T *>(out) + done * p.n, cnt * (size_t)p.n);
+        }
+        SDSP_CUDA(cudaGetLastError());
+    }
+    return SDSP_B200_OK;
+}
+
 static int setup_r2c(FftPlan &p)
 {
     if (p.r2c_ready)
@@ -2897,8 +2979,13 @@ static int setup_r2c(FftPlan &p)
             SDSP_FOR_EACH_LG(X)
 #undef X
         default:
-            rc = set_error(SDSP_B200_ERR_UNSUPPORTED, "fft_exec_r2c / _c2r: n=%u is not built (f32 up to 65536 forward / 32768 reverse, f64 up to 16384 points)", p.n);
+            rc = R2C_NO_DIRECT_KERNEL;
         }
+    if (rc == R2C_NO_DIRECT_KERNEL) { // any size the plan itself transforms: through the full spectrum
+        p.r2c_launch = p.precision == SDSP_B200_F32 ? &launch_half_through_full<float> : &launch_half_through_full<double>;
+        p.r2c_through_full = true;
+        rc = SDSP_B200_OK;
+    }
     if (rc == SDSP_B200_OK)
         p.r2c_ready = true;
     return rc;
@@ -2987,7 +3074,7 @@ int sdsp_b200_fft_plan_destroy(sdsp_b200_fft_plan plan)
         cudaFree(plan->p.d_stage);
     plan->p.host.release();
     for (void *q : { plan->p.d_tw_cols, plan->p.d_tw_rows, plan->p.d_tw_hi, plan->p.d_tw_lo, plan->p.d_scratch, plan->p.d_fused_counters, plan->p.d_r2c_tw,
-                     plan->p.d_r2c_twn })
+                     plan->p.d_r2c_twn, plan->p.d_half_tmp })
         if (q)
             cudaFree(q);
     delete plan;

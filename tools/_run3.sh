@@ -1,2 +1,2 @@
 mkdir -p gpurun_out
-PYTHONPATH=$PWD timeout 600 python tools/experiments/r2c_sweep.py > gpurun_out/r02_r2c_sweep.log 2>&1; cat gpurun_out/r02_r2c_sweep.log
+timeout 1200 python -m pytest tests/test_gpu_fft.py tests/test_gpu_reference_tests.py -m gpu -q --timeout 300 -x -k "half_spectr or additions" 2>&1 | tail -8
