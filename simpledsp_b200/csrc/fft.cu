@@ -388,7 +388,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
 template <class Cfg, typename T, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
     fft_c2r_kernel(const cplx<T> *__restrict__ in, cplx<T> *__restrict__ out, const cplx<T> *__restrict__ tw, const cplx<T> *__restrict__ tw_n,
-                   size_t n_frames)
+                   size_t n_frames, int prefetch)
 {
     constexpr int FPC = THREADS / Cfg::TPF, M = Cfg::N;
     static_assert(THREADS % Cfg::TPF == 0 && FPC >= 1, "block must hold whole frames");
@@ -404,6 +404,16 @@ __global__ void __launch_bounds__(THREADS, MINB)
     for (size_t g = blockIdx.x; g < groups; g += gridDim.x) {
         const size_t frame = g * FPC + fl;
         const bool active = frame < n_frames;
+        // the half spectra this CTA takes next, pulled into L2 meanwhile (frames M + 1 bins apart: the 16-byte-aligned inside of the range)
+        if (prefetch && threadIdx.x == 0 && g + gridDim.x < groups) {
+            const size_t nf = (g + gridDim.x) * FPC;
+            const size_t cnt = (n_frames - nf) < (size_t)FPC ? (n_frames - nf) : (size_t)FPC;
+            size_t lo = nf * (size_t)(M + 1) * sizeof(cplx<T>), hi = (nf + cnt) * (size_t)(M + 1) * sizeof(cplx<T>);
+            lo = (lo + 15) & ~(size_t)15;
+            hi &= ~(size_t)15;
+            if (hi > lo)
+                prefetch_l2_bulk(reinterpret_cast<const char *>(in) + lo, (unsigned)(hi - lo));
+        }
         cplx<T> v[Cfg::E];
         if (active) {
             const cplx<T> *ip = in + frame * (size_t)(M + 1);
@@ -2776,7 +2786,7 @@ static int launch_c2r(const FftPlan &p, const void *half_in, void *real_out, siz
     const size_t grid = groups < resident * 4 ? groups : resident * 4;
     fft_c2r_kernel<Cfg, T, THREADS, MINB><<<(unsigned)grid, THREADS, p.r2c_smem, stream>>>(
         static_cast<const cplx<T> *>(half_in), static_cast<cplx<T> *>(real_out), static_cast<const cplx<T> *>(p.d_r2c_tw),
-        static_cast<const cplx<T> *>(p.d_r2c_twn), n_frames);
+        static_cast<const cplx<T> *>(p.d_r2c_twn), n_frames, fft_prefetch_enabled() && reinterpret_cast<uintptr_t>(half_in) % 16 == 0 ? 1 : 0);
     SDSP_CUDA(cudaGetLastError());
     return SDSP_B200_OK;
 }

@@ -1,2 +1,10 @@
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests/test_gpu_fft.py tests/test_gpu_reference_tests.py -m gpu -q --timeout 300 -x -k "half_spectr or additions" 2>&1 | tail -8
+L=gpurun_out/r02_fft_c2r2.log
+run() { timeout 300 python bench.py --steps $2 --warmup 3 --no-e2e --no-cpu --no-secondary --workload $1 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$3', d['config']['workload'], round(d['ms_per_step'],4), round(d['value']), round(d['roofline']['achieved'],1), round(d['roofline']['frac'],4), d['self_check'], d['clocks']['sm_mhz'], d['clocks']['reasons'])" >> $L 2>&1; }
+rm -f $L
+timeout 900 python -m pytest tests/test_gpu_fft.py -m gpu -q --timeout 300 -x -k "back_from_half" 2>&1 | tail -3
+for rep in 1 2; do
+run fftc2r4096_f32 20 "c2r-prefetch"
+SDSP_B200_FFT_PREFETCH=0 run fftc2r4096_f32 20 "c2r-noprefetch"
+done
+cat $L
