@@ -1141,7 +1141,7 @@ static int setup_cluster64k(FftPlan &p)
 #define SDSP_FUSED_LEAD_F32 512 // tiles of lead between a frame's column tiles and its row tiles (fp32)
 #endif
 #ifndef SDSP_FUSED_LEAD_F32_TMA
-#define SDSP_FUSED_LEAD_F32_TMA 1024 // (768 before a sixth of the ring was pinned in L2: profiles/r02_fft_l2_persist_sweep.txt)
+#define SDSP_FUSED_LEAD_F32_TMA 768 // (1024 with part of the ring pinned in L2 is 2 % faster but lets a quarter of the ring spill to HBM: profiles/r02_fft_lag_traffic.txt)
 #endif
 #ifndef SDSP_FUSED_POLL
 #define SDSP_FUSED_POLL mbar_test // or mbar_try: one try_wait (suspends up to the hardware time limit) per round
@@ -1192,10 +1192,10 @@ struct FusedRing {
     static constexpr int TILES = N1 / 16;                     // tiles per frame, either phase
     static constexpr int COLS = 256 / (N1 / 16);              // columns per column tile
     // frames between a frame's column tiles and its row tiles: 512 (fp32) / 256 (fp64) tiles of lead, more than the CTAs in flight
-    // (fp32 runs the data-mover kernel, which discards consumed ring lines: 1024 tiles of lead, 64 MB with 16 MB of it pinned in L2, measured best up to
+    // (fp32 runs the data-mover kernel, which discards consumed ring lines: 768 tiles of lead, 48 MB with 16 MB of it pinned in L2, measured best up to
     // N1 = 512; 512 tiles for N1 = 1024)
     static constexpr int LAG = (sizeof(T) == 4 ? (N1 <= 512 ? SDSP_FUSED_LEAD_F32_TMA : SDSP_FUSED_LEAD_F32) : 256) / TILES;
-    static constexpr int RING = 2 * LAG;                      // scratch frames: 32 MB (64 MB) whatever the frame size
+    static constexpr int RING = 2 * LAG;                      // scratch frames: 32 MB (48 MB) whatever the frame size
 };
 
 __device__ __forceinline__ cplx<float> ld_l2(const cplx<float> *p)
@@ -1665,7 +1665,7 @@ __global__ void __launch_bounds__(288, MINB)
                 v[e] = gp[Cfg::S * e];
             mbar_arrive(&empty[s]);
             // the tile's 32 KB of the ring are dead now (256 lines of 128 bytes, one per thread): drop them from L2 instead of
-            // letting them be written back to HBM when they are evicted -- that is what makes a 64 MB ring affordable
+            // letting them be written back to HBM when they are evicted -- that is what makes a 48 MB ring affordable
             // (profiles/r01_fft65536_variants.txt)
             if constexpr (sizeof(cplx<T>) == 8)
                 asm volatile("discard.global.L2 [%0], 128;" ::"l"(sc + (size_t)(16 * tile) * N2 + (size_t)threadIdx.x * 16) : "memory");
@@ -1915,7 +1915,7 @@ __global__ void __launch_bounds__(288, MINB)
                 v[e] = gp[Cfg::S * e];
             cta_sync<1, 256>(); // every thread has its points: the slot becomes the exchange buffer
             // the tile's 32 KB of the ring are dead now (256 lines of 128 bytes, one per thread): drop them from L2 instead of
-            // letting them be written back to HBM when they are evicted -- that is what makes a 64 MB ring affordable
+            // letting them be written back to HBM when they are evicted -- that is what makes a 48 MB ring affordable
             // (profiles/r01_fft65536_variants.txt)
             if constexpr (sizeof(cplx<T>) == 8)
                 asm volatile("discard.global.L2 [%0], 128;" ::"l"(sc + (size_t)(16 * tile) * N2 + (size_t)threadIdx.x * 16) : "memory");
@@ -1969,10 +1969,20 @@ __global__ void __launch_bounds__(288, MINB)
 #ifndef SDSP_REAL_MINB
 #define SDSP_REAL_MINB SDSP_FUSED_TMA_MINB
 #endif
+// Frames between a frame's column tiles and its row tiles (x 17 items; the ring holds twice that, 51 MB), with 16 MB of the ring pinned
+// in L2 (profiles/r02_fft_l2_persist_sweep.txt, r02_fft_lag_traffic.txt).  96 frames for both output forms.  With full spectra out
+// a fifth of the ring spills to HBM at that lag (DRAM traffic 1.19 x the algorithmic bytes against 1.01 x at 64 frames) -- HBM is not
+// what bounds this kernel, and config 5 runs 4 % faster for it (78.8 against 82.0 ms), so the spill is accepted; with half spectra out
+// (half the output, more room in L2) the traffic stays at 1.0 x and 96 frames are 6 % faster than 64.
 #ifndef SDSP_REAL_LAG
-#define SDSP_REAL_LAG 96 // frames between a frame's column tiles and its row tiles (x 17 items; the ring holds twice that, 51 MB, a third of it pinned in L2: profiles/r02_fft_l2_persist_sweep.txt; 64 was best without the pinning)
+#define SDSP_REAL_LAG 96
 #endif
-constexpr int REAL_CT = 8, REAL_RT = 9, REAL_LAG = SDSP_REAL_LAG, REAL_RING = 2 * SDSP_REAL_LAG, REAL_ROWS = 129;
+#ifndef SDSP_REAL_LAG_HALF
+#define SDSP_REAL_LAG_HALF 96
+#endif
+constexpr int REAL_CT = 8, REAL_RT = 9, REAL_ROWS = 129;
+constexpr int REAL_RING_MAX = 2 * (SDSP_REAL_LAG > SDSP_REAL_LAG_HALF ? SDSP_REAL_LAG : SDSP_REAL_LAG_HALF); // what the scratch is sized for
+template <int REAL_LAG>
 __host__ __device__ __forceinline__ void real_decode(size_t q, bool &cols, size_t &f, int &tile)
 {
     if (q < (size_t)REAL_LAG * REAL_CT) {
@@ -1988,7 +1998,7 @@ __host__ __device__ __forceinline__ void real_decode(size_t q, bool &cols, size_
     tile = cols ? w : w - REAL_CT;
 }
 
-template <typename T, int MINB>
+template <typename T, int MINB, int REAL_LAG>
 __global__ void __launch_bounds__(288, MINB)
     fft_real64k_kernel(const __grid_constant__ CUtensorMap in_map, cplx<T> *__restrict__ data, cplx<T> *__restrict__ scratch,
                        const cplx<T> *__restrict__ tw, const cplx<T> *__restrict__ tw_hi, const cplx<T> *__restrict__ tw_lo,
@@ -1997,7 +2007,7 @@ __global__ void __launch_bounds__(288, MINB)
     // half != 0 (sdsp_b200_fft_exec_r2c): only the bins 0 .. 32768 are written, frames 32769 bins apart -- of every row the lower
     // half of k2 directly and the upper half through its mirror bin, which lies in the lower half of the spectrum
     using Cfg = FftCfg<256, 16, 16, 16>; // rows and (packed) columns alike
-    constexpr int N1 = 256, N2 = 256, PITCH = LargeStride<Cfg>::value;
+    constexpr int N1 = 256, N2 = 256, PITCH = LargeStride<Cfg>::value, REAL_RING = 2 * REAL_LAG;
     constexpr int XBUF = 16 * PITCH;
     constexpr size_t FRAME = (size_t)N1 * N2, RFRAME = (size_t)REAL_ROWS * N2; // output frame; ring frame (rows 0 .. 128)
     constexpr uint32_t TILE_BYTES = 4096 * sizeof(cplx<T>);
@@ -2064,7 +2074,7 @@ __global__ void __launch_bounds__(288, MINB)
             size_t f = n_frames;
             int tile = 0;
             if (q < total)
-                real_decode(q, cols, f, tile);
+                real_decode<REAL_LAG>(q, cols, f, tile);
             const bool real = q < total && f < n_frames;
             if (real && !cols)
                 wait_dep(col_done + f, REAL_CT);
@@ -2115,7 +2125,7 @@ __global__ void __launch_bounds__(288, MINB)
         bool cols;
         size_t f;
         int tile;
-        real_decode(q, cols, f, tile);
+        real_decode<REAL_LAG>(q, cols, f, tile);
         cplx<T> *st = stage0 + (size_t)s * SLOT, *xbuf = st;
         cplx<T> *sc = scratch + (f % REAL_RING) * RFRAME;
         cplx<T> v[Cfg::E];
@@ -2330,7 +2340,8 @@ static int launch_real64k(const FftPlan &p, void *data, const void *real_in, siz
                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
         return set_error(SDSP_B200_ERR_CUDA, "fft: cuTensorMapEncodeTiled failed with %d (real input, n=%u frames=%zu)", (int)r, p.n, n_frames);
-    const size_t items = (size_t)REAL_LAG * REAL_CT + n_frames * (REAL_CT + REAL_RT);
+    const int lag = half ? SDSP_REAL_LAG_HALF : SDSP_REAL_LAG;
+    const size_t items = (size_t)lag * REAL_CT + n_frames * (REAL_CT + REAL_RT);
     size_t grid = (size_t)p.sm_count * (size_t)p.real64k_ctas;
     if (grid > items)
         grid = items;
@@ -2340,15 +2351,15 @@ static int launch_real64k(const FftPlan &p, void *data, const void *real_in, siz
     cfg.dynamicSmemBytes = p.real64k_smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
-    const size_t ring_bytes = (size_t)REAL_RING * REAL_ROWS * 256 * sizeof(cplx<T>);
+    const size_t ring_bytes = (size_t)2 * lag * REAL_ROWS * 256 * sizeof(cplx<T>);
     if (ring_persist_window(p.device, p.d_scratch, ring_bytes, attr[0])) {
         cfg.attrs = attr;
         cfg.numAttrs = 1;
     }
-    SDSP_CUDA(cudaLaunchKernelEx(&cfg, fft_real64k_kernel<T, SDSP_REAL_MINB>, map, reinterpret_cast<cplx<T> *>(data),
-                                 reinterpret_cast<cplx<T> *>(p.d_scratch), reinterpret_cast<const cplx<T> *>(p.d_tw_rows),
-                                 reinterpret_cast<const cplx<T> *>(p.d_tw_hi), reinterpret_cast<const cplx<T> *>(p.d_tw_lo), ctr, ctr + 1,
-                                 ctr + 1 + n_frames, n_frames, half ? 1 : 0));
+    auto kern = half ? fft_real64k_kernel<T, SDSP_REAL_MINB, SDSP_REAL_LAG_HALF> : fft_real64k_kernel<T, SDSP_REAL_MINB, SDSP_REAL_LAG>;
+    SDSP_CUDA(cudaLaunchKernelEx(&cfg, kern, map, reinterpret_cast<cplx<T> *>(data), reinterpret_cast<cplx<T> *>(p.d_scratch),
+                                 reinterpret_cast<const cplx<T> *>(p.d_tw_rows), reinterpret_cast<const cplx<T> *>(p.d_tw_hi),
+                                 reinterpret_cast<const cplx<T> *>(p.d_tw_lo), ctr, ctr + 1, ctr + 1 + n_frames, n_frames, half ? 1 : 0));
     return SDSP_B200_OK;
 }
 
@@ -2457,8 +2468,8 @@ static int setup_fused(FftPlan &p)
     p.e = 16;
     p.threads = 256;
     p.scratch_frames = FusedRing<T, N1>::RING;
-    if (N1 == 256 && sizeof(T) == 4) { // the real-input kernel's ring (REAL_RING frames of 129 rows) may be the larger one
-        const size_t need = ((size_t)REAL_RING * REAL_ROWS * 256 + 65535) / 65536;
+    if (N1 == 256 && sizeof(T) == 4) { // the real-input kernel's ring (frames of 129 rows) may be the larger one
+        const size_t need = ((size_t)REAL_RING_MAX * REAL_ROWS * 256 + 65535) / 65536;
         if (need > p.scratch_frames)
             p.scratch_frames = need;
     }
@@ -2516,13 +2527,15 @@ static int setup_fused(FftPlan &p)
             if constexpr (N1 == 256) { // forward real-input frames: the half-work queue (SDSP_B200_FFT_REAL64K=0 keeps the complex kernels)
                 const char *e = getenv("SDSP_B200_FFT_REAL64K");
                 if (!e || atoi(e) != 0) {
-                    auto rk = fft_real64k_kernel<T, SDSP_REAL_MINB>;
+                    auto rk = fft_real64k_kernel<T, SDSP_REAL_MINB, SDSP_REAL_LAG>;
+                    auto rkh = fft_real64k_kernel<T, SDSP_REAL_MINB, SDSP_REAL_LAG_HALF>;
                     const size_t slot = ((size_t)16 * LargeStride<Cfg>::value + 15) / 16 * 16;
                     const size_t rsmem = (SDSP_REAL_NST * slot + 512) * sizeof(cplx<T>) + 128;
                     int rocc = 0;
                     if (cudaFuncSetAttribute(rk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem) == cudaSuccess &&
+                        cudaFuncSetAttribute(rkh, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem) == cudaSuccess &&
                         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&rocc, rk, 288, rsmem) == cudaSuccess && rocc >= 1 &&
-                        (size_t)REAL_RING * REAL_ROWS * 256 <= p.scratch_frames * (size_t)N1 * 256) {
+                        (size_t)REAL_RING_MAX * REAL_ROWS * 256 <= p.scratch_frames * (size_t)N1 * 256) {
                         p.real64k_ctas = rocc;
                         p.real64k_smem = rsmem;
                     }
