@@ -233,6 +233,8 @@ int sdsp_b200_debug_iir_decay_length(int sections, int numerator, int precision,
  * 0 = row tile, tile index, frame } for ticket q (frames past the batch are empty slots).  A row tile waits for the column tiles
  * of its frame, a column tile for the row tiles of frame - ring: both must hold smaller tickets. */
 int sdsp_b200_debug_fft_queue_item(unsigned n, int precision, unsigned long long q, int *geom, int *item);
+/* the queue of the real-input 65536-point kernel: geom = {column tiles per frame (8), row tiles per frame (9), lag, ring} */
+int sdsp_b200_debug_fft_real_queue_item(int half_spectrum, unsigned long long q, int *geom, int *item);
 
 #ifdef __cplusplus
 }

@@ -68,6 +68,7 @@ SIGNATURES = {
     "sdsp_b200_debug_emulate_iir_diff": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_double, _dp, _dp, _dp, _dp, _vp, _sz]),
     "sdsp_b200_debug_iir_decay_length": (C.c_int, [C.c_int, C.c_int, C.c_int, _dp, _dp, C.POINTER(C.c_ulonglong)]),
     "sdsp_b200_debug_fft_queue_item": (C.c_int, [C.c_uint, C.c_int, C.c_ulonglong, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "sdsp_b200_debug_fft_real_queue_item": (C.c_int, [C.c_int, C.c_ulonglong, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "sdsp_b200_debug_emulate_iir_scan": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_double, _dp, _dp, _dp, _vp, _sz,
                                                    C.c_int, C.c_int]),
 }

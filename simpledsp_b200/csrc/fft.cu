@@ -3382,6 +3382,29 @@ int sdsp_b200_debug_fft_queue_item(unsigned n, int precision, unsigned long long
     }
 }
 
+// the same view of the real-input 65536-point kernel's queue (8 column + 9 row tiles per frame): geom = {column tiles, row tiles, lag, ring}
+int sdsp_b200_debug_fft_real_queue_item(int half_spectrum, unsigned long long q, int *geom, int *item)
+{
+    if (!geom || !item)
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "debug_fft_real_queue_item: bad arguments");
+    const int lag = half_spectrum ? SDSP_REAL_LAG_HALF : SDSP_REAL_LAG;
+    geom[0] = REAL_CT;
+    geom[1] = REAL_RT;
+    geom[2] = lag;
+    geom[3] = 2 * lag;
+    bool cols = false;
+    size_t f = 0;
+    int tile = 0;
+    if (half_spectrum)
+        real_decode<SDSP_REAL_LAG_HALF>((size_t)q, cols, f, tile);
+    else
+        real_decode<SDSP_REAL_LAG>((size_t)q, cols, f, tile);
+    item[0] = cols ? 1 : 0;
+    item[1] = tile;
+    item[2] = (int)f;
+    return SDSP_B200_OK;
+}
+
 int sdsp_b200_fft_plan_launches(sdsp_b200_fft_plan plan, size_t n_frames, int *launches)
 {
     if (!plan || !launches)

@@ -237,6 +237,36 @@ def test_time_split_algorithm_on_the_host(case):
         assert np.abs(y - whole).max() / peak <= tol, (case, pname)
 
 
+@pytest.mark.parametrize("half", [0, 1])
+def test_real_input_queue_order_makes_every_wait_point_at_a_smaller_ticket(half):
+    """The real-input 65536-point kernel (fft_real64k_kernel: 8 packed column tiles + 9 row tiles per frame) hands its items out in one
+    static order too.  The same argument on its own decode function: every tile exactly once, a frame's row tiles after all of its
+    column tiles, a ring slot's new column tiles after all row tiles of its previous tenant -- for batches below, at and past the
+    lag and the ring."""
+    L = K.lib()
+    geom, item = (C.c_int * 4)(), (C.c_int * 3)()
+    K.check(L.sdsp_b200_debug_fft_real_queue_item(half, 0, geom, item))
+    ct, rt, lag, ring = list(geom)
+    assert (ct, rt) == (8, 9) and ring == 2 * lag and lag >= 1
+    assert ring * 129 * 256 * 8 <= 52 << 20  # the ring of half-frames (rows 0 .. 128) stays near the L2 budget the design states
+    for frames in sorted({1, 2, lag - 1, lag, lag + 1, ring - 1, ring, ring + 1, 2 * ring + 3}):
+        total = lag * ct + frames * (ct + rt)
+        col_ticket, row_ticket = {}, {}
+        for q in range(total):
+            K.check(L.sdsp_b200_debug_fft_real_queue_item(half, q, geom, item))
+            is_col, tile, f = list(item)
+            if f >= frames:
+                assert is_col  # empty slots are column slots past the last frame
+                continue
+            (col_ticket if is_col else row_ticket).setdefault(f, []).append((q, tile))
+        for f in range(frames):
+            assert sorted(t for _, t in col_ticket[f]) == list(range(ct))
+            assert sorted(t for _, t in row_ticket[f]) == list(range(rt))
+            assert max(q for q, _ in col_ticket[f]) < min(q for q, _ in row_ticket[f])
+            if f >= ring:
+                assert max(q for q, _ in row_ticket[f - ring]) < min(q for q, _ in col_ticket[f])
+
+
 @pytest.mark.parametrize("prec", ["f32", "f64"])
 @pytest.mark.parametrize("n1", [32, 64, 128, 256, 512, 1024])
 def test_fft_work_queue_order_makes_every_wait_point_at_a_smaller_ticket(n1, prec):
