@@ -212,6 +212,9 @@ int sdsp_b200_iir_process_once(int sections, int numerator, int precision, doubl
  * host), so index arithmetic and rounding behaviour can be checked where no GPU exists.  NOT a
  * fallback: nothing in the library calls these. */
 int sdsp_b200_debug_emulate_fft(uint32_t n, int precision, int direction, void *data, size_t n_frames);
+/* the same for the half-spectrum kernels: back = 0 emulates fft_exec_r2c (real frames in, n/2 + 1 bins out), back = 1 fft_exec_c2r;
+ * n = 4 .. 32768 (the sizes with a direct kernel), host buffers */
+int sdsp_b200_debug_emulate_r2c(uint32_t n, int precision, int back, const void *in, void *out, size_t n_frames);
 int sdsp_b200_debug_emulate_iir(int sections, int numerator, int precision, double gain, const double *b,
                                 const double *a, double *mem, void *data, size_t n_samples);
 /* the same with the fp32 running differences in / out (diff[sections], may be NULL = as sdsp_b200_iir_bank_set_state) */

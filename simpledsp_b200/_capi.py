@@ -64,6 +64,7 @@ SIGNATURES = {
     "sdsp_b200_iir_preload_state": (C.c_int, [C.c_int, C.c_int, C.c_double, _dp, _dp, C.c_double, _dp]),
     "sdsp_b200_iir_process_once": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_double, _dp, _dp, _dp, _vp, _sz, C.c_int]),
     "sdsp_b200_debug_emulate_fft": (C.c_int, [C.c_uint32, C.c_int, C.c_int, _vp, _sz]),
+    "sdsp_b200_debug_emulate_r2c": (C.c_int, [C.c_uint32, C.c_int, C.c_int, _vp, _vp, _sz]),
     "sdsp_b200_debug_emulate_iir": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_double, _dp, _dp, _dp, _vp, _sz]),
     "sdsp_b200_debug_emulate_iir_diff": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_double, _dp, _dp, _dp, _dp, _vp, _sz]),
     "sdsp_b200_debug_iir_decay_length": (C.c_int, [C.c_int, C.c_int, C.c_int, _dp, _dp, C.POINTER(C.c_ulonglong)]),

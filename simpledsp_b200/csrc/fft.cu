@@ -365,12 +365,8 @@ __global__ void __launch_bounds__(THREADS, MINB)
             for (int e = 0; e < Cfg::E; e++) {
                 const int k = t + Cfg::S * e;
                 const cplx<T> zm = fs[(M - k) & (M - 1)]; // k = 0 mirrors into itself
-                const cplx<T> a = v[e], b = cplx<T>{ zm.x, -zm.y };
-                const cplx<T> ye = a + b, d = a - b;
-                const cplx<T> yo = cplx<T>{ d.y, -d.x }; // -i (a - b)
                 const cplx<T> w = e == 0 ? wt : cmul(wt, w64<T>(e * (32 / Cfg::E)));
-                const cplx<T> x = ye + cmul(yo, w);
-                st_stream(op + k, cplx<T>{ (T)0.5 * x.x, (T)0.5 * x.y });
+                st_stream(op + k, r2c_bin(v[e], zm, w));
             }
             if (t == 0)
                 st_stream(op + M, cplx<T>{ v[0].x - v[0].y, (T)0 });
@@ -422,12 +418,9 @@ __global__ void __launch_bounds__(THREADS, MINB)
             for (int e = 0; e < Cfg::E; e++) {
                 const int k = t + Cfg::S * e;
                 const cplx<T> a = ld_stream(ip + k), xm = ld_stream(ip + (M - k));
-                const cplx<T> b = cplx<T>{ xm.x, -xm.y };
-                const cplx<T> s = a + b, d = a - b;
                 const cplx<T> w = e == 0 ? wt : cmul(wt, w64<T>(e * (32 / Cfg::E)));
-                const cplx<T> r = cmul(d, cplx<T>{ w.x, -w.y }); // conj(W_n^k) (X[k] - conj X[M - k])
-                const cplx<T> z = cplx<T>{ s.x - r.y, s.y + r.x }; // + i r
-                v[e] = cplx<T>{ z.y, z.x };                         // swapped for the inverse
+                const cplx<T> z = c2r_bin(a, xm, w);
+                v[e] = cplx<T>{ z.y, z.x }; // swapped for the inverse
             }
         } else {
 #pragma unroll
@@ -2870,6 +2863,71 @@ static int setup_r2c_for(FftPlan &p) // LG = log2(n / 2)
         return R2C_NO_DIRECT_KERNEL;
 }
 
+
+// host emulation of the half-spectrum kernels (sdsp_b200_debug_emulate_r2c): the M-point frame code of fft_emulate_frame plus the
+// separation step with the factors formed the way the kernels form them (W_n^t from the table, times a 64th root)
+template <class Cfg, typename T>
+static void emulate_half_cfg(const void *in, void *out, bool back)
+{
+    constexpr int M = Cfg::N;
+    int radices[4] = { Cfg::R0, Cfg::R1, Cfg::R2, Cfg::R3 };
+    std::vector<cplx<T>> tw;
+    build_twiddles<T>(M, radices, Cfg::NPASS, tw);
+    tw.push_back(cplx<T>{ 1, 0 });
+    auto factor = [&](int t, int e) {
+        long double re, im;
+        unit_root((uint64_t)t, (uint64_t)2 * M, re, im);
+        const cplx<T> wt{ (T)re, (T)im };
+        if (e == 0)
+            return wt;
+        unit_root((uint64_t)(e * (32 / Cfg::E)), 64, re, im);
+        return cmul(wt, cplx<T>{ (T)re, (T)im });
+    };
+    std::vector<cplx<T>> z(M);
+    if (!back) {
+        const T *x = static_cast<const T *>(in);
+        cplx<T> *half = static_cast<cplx<T> *>(out);
+        for (int j = 0; j < M; j++)
+            z[j] = cplx<T>{ x[2 * j], x[2 * j + 1] };
+        fft_emulate_frame<Cfg, T>(z.data(), tw.data(), false, (T)1);
+        for (int t = 0; t < Cfg::TPF; t++)
+            for (int e = 0; e < Cfg::E; e++) {
+                const int k = t + Cfg::S * e;
+                half[k] = r2c_bin(z[k], z[(M - k) & (M - 1)], factor(t, e));
+            }
+        half[M] = cplx<T>{ z[0].x - z[0].y, (T)0 };
+    } else {
+        const cplx<T> *half = static_cast<const cplx<T> *>(in);
+        T *x = static_cast<T *>(out);
+        for (int t = 0; t < Cfg::TPF; t++)
+            for (int e = 0; e < Cfg::E; e++) {
+                const int k = t + Cfg::S * e;
+                z[k] = c2r_bin(half[k], half[M - k], factor(t, e));
+            }
+        fft_emulate_frame<Cfg, T>(z.data(), tw.data(), true, (T)(0.5 / (double)M));
+        for (int j = 0; j < M; j++) {
+            x[2 * j] = z[j].x;
+            x[2 * j + 1] = z[j].y;
+        }
+    }
+}
+
+template <int LG>
+static int emulate_half_for(int precision, bool back, const void *in, void *out) // LG = log2(n / 2)
+{
+    using C = CfgFor<LG>;
+    if (precision == SDSP_B200_F32) {
+        if (LG == 13)
+            emulate_half_cfg<CfgR32_13::type, float>(in, out, back);
+        else if (LG == 14)
+            emulate_half_cfg<CfgR32_14::type, float>(in, out, back);
+        else
+            emulate_half_cfg<typename C::type, float>(in, out, back);
+    } else
+        emulate_half_cfg<typename C::type, double>(in, out, back);
+    return SDSP_B200_OK;
+}
+
 #define SDSP_FOR_EACH_LG(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14)
 
 static int setup_plan(FftPlan &p)
@@ -3499,6 +3557,27 @@ int sdsp_b200_twiddle_table(uint32_t n, int direction, double *out)
             unit_root(j, den, re, im);
             out[2 * ((size_t)i * n + j)] = (double)re;
             out[2 * ((size_t)i * n + j) + 1] = direction == SDSP_B200_REVERSE ? (double)-im : (double)im;
+        }
+    }
+    return SDSP_B200_OK;
+}
+
+// host emulation of sdsp_b200_fft_exec_r2c (back = 0) / _c2r (back = 1) for the sizes with a direct kernel: n = 4 .. 32768
+int sdsp_b200_debug_emulate_r2c(uint32_t n, int precision, int back, const void *in, void *out, size_t n_frames)
+{
+    if (!in || !out || (precision != SDSP_B200_F32 && precision != SDSP_B200_F64) || !is_pow2(n) || n < 4 || n > 32768)
+        return set_error(SDSP_B200_ERR_INVALID_ARG, "debug_emulate_r2c: bad arguments (n = 4 .. 32768, a power of two)");
+    const size_t es = precision == SDSP_B200_F32 ? sizeof(float) : sizeof(double);
+    const size_t real_bytes = (size_t)n * es, half_bytes = ((size_t)n / 2 + 1) * 2 * es;
+    for (size_t f = 0; f < n_frames; f++) {
+        const char *ip = static_cast<const char *>(in) + f * (back ? half_bytes : real_bytes);
+        char *op = static_cast<char *>(out) + f * (back ? real_bytes : half_bytes);
+        switch (ilog2(n) - 1) {
+#define X(LG) \
+    case LG: emulate_half_for<LG>(precision, back != 0, ip, op); break;
+            SDSP_FOR_EACH_LG(X)
+#undef X
+        default: return set_error(SDSP_B200_ERR_UNSUPPORTED, "debug_emulate_r2c: n=%u not built", n);
         }
     }
     return SDSP_B200_OK;

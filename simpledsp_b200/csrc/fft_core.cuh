@@ -362,6 +362,28 @@ SDSP_HD int fft_out_phys(int t, int e)
 }
 
 // ------------------------------------------------------------------------------------------------
+// half spectra of real frames (fft_r2c_kernel / fft_c2r_kernel): a frame of n = 2M reals read as M complex numbers z[j] = x[2j] + i x[2j+1].
+//   forward: X[k] = 1/2 [ (Z[k] + conj Z[M-k]) - i W_n^k (Z[k] - conj Z[M-k]) ]                      (zk = Z[k], zm = Z[M-k], w = W_n^k)
+//   back:    Z[k] = 1/2 [ (X[k] + conj X[M-k]) + i conj(W_n^k) (X[k] - conj X[M-k]) ]                 (the 1/2 is left to the caller's scale)
+template <typename T>
+SDSP_HD cplx<T> r2c_bin(cplx<T> zk, cplx<T> zm, cplx<T> w)
+{
+    const cplx<T> b = cplx<T>{ zm.x, -zm.y };
+    const cplx<T> ye = zk + b, d = zk - b;
+    const cplx<T> yo = cplx<T>{ d.y, -d.x }; // -i (zk - conj zm)
+    const cplx<T> x = ye + cmul(yo, w);
+    return cplx<T>{ (T)0.5 * x.x, (T)0.5 * x.y };
+}
+template <typename T>
+SDSP_HD cplx<T> c2r_bin(cplx<T> xk, cplx<T> xm, cplx<T> w)
+{
+    const cplx<T> b = cplx<T>{ xm.x, -xm.y };
+    const cplx<T> s = xk + b, d = xk - b;
+    const cplx<T> r = cmul(d, cplx<T>{ w.x, -w.y }); // conj(W_n^k) (xk - conj xm)
+    return cplx<T>{ s.x - r.y, s.y + r.x };        // + i r
+}
+
+// ------------------------------------------------------------------------------------------------
 // host emulation of one frame: every "thread" runs the very pass code the kernel runs, the shared
 // memory exchange is an array indexed through the same pad() function.
 template <class Cfg, typename T, int P>

@@ -102,6 +102,35 @@ def test_emulated_fft_kernel_code_matches_oracle(lg):
             assert rel_l2(a, ref) < FFT_TOL[name] * (1e-3 if name == "f64" else 0.1), (n, name, inv)
 
 
+@pytest.mark.parametrize("lg", range(2, 16))
+def test_emulated_half_spectrum_kernel_code_matches_numpy(lg):
+    """sdsp_b200_debug_emulate_r2c runs the per-thread code of fft_r2c_kernel / fft_c2r_kernel on the host (the M = n/2 point frame code,
+    the separation step r2c_bin / c2r_bin, the factors W_n^t x 64th root as the kernels form them): half spectra of real frames against
+    numpy's rfft -- which agrees with the reference's transform of (x, 0) to 3e-16 (tests/test_oracle.py) -- and the way back against
+    irfft, both precisions, at the FFT tolerances."""
+    n = 1 << lg
+    frames = 3
+    rng = np.random.default_rng(lg)
+    for prec, rdt, cdt in ((K.F64, np.float64, np.complex128), (K.F32, np.float32, np.complex64)):
+        x = rng.standard_normal((frames, n)).astype(np.float32).astype(rdt)
+        half = np.zeros((frames, n // 2 + 1), dtype=cdt)
+        K.check(K.lib().sdsp_b200_debug_emulate_r2c(n, prec, 0, x.ctypes.data, half.ctypes.data, frames))
+        ref = np.fft.rfft(x.astype(np.float64), axis=1)
+        assert rel_l2(half, ref) <= FFT_TOL["f64" if prec == K.F64 else "f32"], (n, prec)
+        assert np.all(half[:, n // 2].imag == 0)
+        back = np.zeros((frames, n), dtype=rdt)
+        K.check(K.lib().sdsp_b200_debug_emulate_r2c(n, prec, 1, half.ctypes.data, back.ctypes.data, frames))
+        assert np.linalg.norm(back - x) / np.linalg.norm(x) <= 2 * FFT_TOL["f64" if prec == K.F64 else "f32"], (n, prec)
+        # an arbitrary half spectrum (bins 0 and n/2 real) back to a real frame
+        h2 = (rng.standard_normal((frames, n // 2 + 1)) + 1j * rng.standard_normal((frames, n // 2 + 1))).astype(cdt)
+        h2[:, 0] = h2[:, 0].real
+        h2[:, -1] = h2[:, -1].real
+        K.check(K.lib().sdsp_b200_debug_emulate_r2c(n, prec, 1, h2.ctypes.data, back.ctypes.data, frames))
+        ref2 = np.fft.irfft(h2.astype(np.complex128), n=n, axis=1)
+        assert np.linalg.norm(back - ref2) / np.linalg.norm(ref2) <= FFT_TOL["f64" if prec == K.F64 else "f32"], (n, prec)
+    assert K.lib().sdsp_b200_debug_emulate_r2c(48, K.F32, 0, x.ctypes.data, half.ctypes.data, 1) != 0
+
+
 def test_emulated_iir_kernel_code_matches_golden():
     for name, ftype, fs, f0, q, n, h in golden_impulses():
         g, b, a = S.design(ftype, 4, f0, fs, q)
