@@ -14,3 +14,4 @@ for l in open('gpurun_out/bench_default.log'):
             print('      ', s['plan'][:230])
 PY
 timeout 600 python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/bench_reference.log 2>&1; tail -c 600 gpurun_out/bench_reference.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -1
