@@ -382,6 +382,15 @@ void fft_half_spectrum_device(const S *real_frames, std::complex<S> *half_spectr
 {
     detail::run_real<forward_fft, 2, S, true>(real_frames, half_spectra, static_cast<uint32_t>(n), n_frames, SDSP_B200_PTR_DEVICE, stream);
 }
+// one frame in the reference's container style (std::array, as complex_array<N> is)
+template <size_t N, typename S>
+void fft_half_spectrum(const std::array<S, N> &real_frame, std::array<std::complex<S>, N / 2 + 1> &half_spectrum)
+{
+    static_assert(isPowerOf2(N) && N >= 4, "FFT size must be a power of 2!");
+    fft_half_spectrum(real_frame.data(), half_spectrum.data(), N, 1);
+}
+template <size_t N, typename S>
+void fft_real_from_half_spectrum(const std::array<std::complex<S>, N / 2 + 1> &half_spectrum, std::array<S, N> &real_frame);
 // and back: half spectra in, real frames out, 1/n included (reverse_fft's scaling, reference fft.h:128-132)
 template <typename S>
 void fft_real_from_half_spectrum(const std::complex<S> *half_spectra, S *real_frames, size_t n, size_t n_frames)
@@ -392,5 +401,11 @@ template <typename S>
 void fft_real_from_half_spectrum_device(const std::complex<S> *half_spectra, S *real_frames, size_t n, size_t n_frames, void *stream = nullptr)
 {
     detail::run_c2r<S>(half_spectra, real_frames, static_cast<uint32_t>(n), n_frames, SDSP_B200_PTR_DEVICE, stream);
+}
+template <size_t N, typename S>
+void fft_real_from_half_spectrum(const std::array<std::complex<S>, N / 2 + 1> &half_spectrum, std::array<S, N> &real_frame)
+{
+    static_assert(isPowerOf2(N) && N >= 4, "FFT size must be a power of 2!");
+    fft_real_from_half_spectrum(half_spectrum.data(), real_frame.data(), N, 1);
 }
 } // namespace sdsp

@@ -104,6 +104,25 @@ int main()
             den += reald[i] * reald[i];
         }
         CHECK(std::sqrt(num / den) < 1e-12, "fp64 real_from_half_spectrum(half_spectrum(x)) != x");
+        // one frame in std::array containers, the reference's style
+        std::array<double, 1024> one{};
+        for (size_t i = 0; i < one.size(); i++)
+            one[i] = reald[i];
+        std::array<std::complex<double>, 513> one_half{};
+        sdsp::fft_half_spectrum<1024>(one, one_half);
+        sdsp::complex_array<1024> full{};
+        for (size_t i = 0; i < one.size(); i++)
+            full[i] = { one[i], 0.0 };
+        sdsp::fft_radix2(full);
+        CHECK(rel_l2(one_half.data(), full.data(), 513) < 1e-12, "std::array half spectrum differs from fft_radix2 on (x, 0)");
+        std::array<double, 1024> one_back{};
+        sdsp::fft_real_from_half_spectrum<1024>(one_half, one_back);
+        double e2 = 0, n2 = 0;
+        for (size_t i = 0; i < one.size(); i++) {
+            e2 += (one_back[i] - one[i]) * (one_back[i] - one[i]);
+            n2 += one[i] * one[i];
+        }
+        CHECK(std::sqrt(e2 / n2) < 1e-12, "std::array round trip through the half spectrum");
     }
     // ---- a bank of channels against one filter object per channel (reference signature, casc_2o_iir.h:36-80)
     {
