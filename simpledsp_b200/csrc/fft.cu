@@ -3205,7 +3205,7 @@ int sdsp_b200_fft_exec(sdsp_b200_fft_plan plan, void *data, size_t n_frames, int
         memcpy(data, p.host.bounce, total);
         return SDSP_B200_OK;
     }
-    size_t slab_frames = (64u << 20) / frame_bytes;
+    size_t slab_frames = host_slab_bytes() / frame_bytes;
     if (slab_frames < 1)
         slab_frames = 1;
     if (slab_frames > n_frames)
@@ -3268,7 +3268,7 @@ int sdsp_b200_fft_exec_real(sdsp_b200_fft_plan plan, const void *real_in, void *
     if (rc)
         return rc;
     const size_t in_bytes = (size_t)p.n * es, out_bytes = 2 * in_bytes;
-    size_t slab = (64u << 20) / out_bytes;
+    size_t slab = host_slab_bytes() / out_bytes;
     slab = slab < 1 ? 1 : slab > n_frames ? n_frames : slab;
     const int nbuf = n_frames > slab ? 2 : 1;
     const size_t buf_bytes = slab * (in_bytes + out_bytes);
@@ -3336,7 +3336,7 @@ static int exec_half(sdsp_b200_fft_plan plan, const void *in, void *out, size_t 
         return rc;
     const size_t real_bytes = (size_t)p.n * es, half_bytes = ((size_t)p.n / 2 + 1) * 2 * es;
     const size_t in_bytes = back ? half_bytes : real_bytes, out_bytes = back ? real_bytes : half_bytes;
-    size_t slab = (64u << 20) / (in_bytes + out_bytes);
+    size_t slab = host_slab_bytes() / (in_bytes + out_bytes);
     slab = slab < 1 ? 1 : slab > n_frames ? n_frames : slab;
     const int nbuf = n_frames > slab ? 2 : 1;
     const size_t out_slab = (slab * out_bytes + 255) / 256 * 256, in_slab = (slab * in_bytes + 255) / 256 * 256;

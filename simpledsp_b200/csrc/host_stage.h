@@ -11,6 +11,7 @@
 //     counters (FFT, n >= 32768) or filter history (IIR).
 #pragma once
 #include <cstddef>
+#include <cstdlib>
 #include <cstring>
 
 #include <cuda_runtime.h>
@@ -19,6 +20,9 @@
 
 namespace sdsp_b200
 {
+#ifndef SDSP_HOST_SLAB_MB_DEFAULT
+#define SDSP_HOST_SLAB_MB_DEFAULT 64
+#endif
 struct HostStage {
     static constexpr size_t BOUNCE_BYTES = 1u << 20; // calls up to this size take the pinned bounce buffer
     cudaStream_t stream[2] = { nullptr, nullptr };
@@ -66,6 +70,20 @@ struct HostStage {
 };
 
 // grow-only device staging buffer of a handle
+// bytes of one staging slab of a host-pointer call (two are in flight).  A call's first H2D and last D2H are not overlapped with
+// anything, so a slab costs its own transfer time once per call: 64 MB = 2.8 ms of a 45 ms call on 2 GiB (6 %), 16 MB = 0.7 ms.
+// SDSP_B200_HOST_SLAB_MB overrides (tuning aid; profiles/r02_host_slab_sweep.txt).
+inline size_t host_slab_bytes()
+{
+    static size_t v = 0;
+    if (!v) {
+        const char *e = getenv("SDSP_B200_HOST_SLAB_MB");
+        const int mb = e ? atoi(e) : 0;
+        v = (size_t)(mb >= 1 && mb <= 1024 ? mb : SDSP_HOST_SLAB_MB_DEFAULT) << 20;
+    }
+    return v;
+}
+
 inline int ensure_device_stage(void *&d_stage, size_t &stage_bytes, size_t need, const char *who)
 {
     if (stage_bytes >= need)

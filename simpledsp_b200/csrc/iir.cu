@@ -675,7 +675,7 @@ int sdsp_b200_iir_bank_process(sdsp_b200_iir_bank bank, void *data, size_t n_sam
     // Staging memory is two chunks, whatever the size of the bank (config 3 would need 64 GiB for an uncut copy).
     // Chunk rows are 256-byte multiples so every chunk takes the same kernel (TMA path: 16-byte aligned pitch).
     const size_t row_quantum = 256 / es;
-    size_t chunk = ((size_t)64 << 20) / (b.n_channels * es) / row_quantum * row_quantum;
+    size_t chunk = host_slab_bytes() / (b.n_channels * es) / row_quantum * row_quantum;
     if (chunk < 4 * row_quantum)
         chunk = 4 * row_quantum;
     if (chunk > n_samples)
