@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
 //   X[k] = (Z[k] + conj Z[M - k]) / 2  +  W_N^k (-i) (Z[k] - conj Z[M - k]) / 2,      X[M] = Re Z[0] - Im Z[0].
 // 4 bytes in and 4 bytes out per real sample against 8 + 8 for the reference's calling convention (real part filled, imaginary
 // part zero: test/testFFT.cpp:24, :86) and 4 + 8 for sdsp_b200_fft_exec_real.  W_N^k = W_N^t W_N^(S e) for k = t + S e: the first
-// factor is a per-thread constant (one table look-up per launch), the second is W_(2E)^e, a compile-time index into a 64th-root
+// factor is a per-thread constant (one table look-up per frame), the second is W_(2E)^e, a compile-time index into a 64th-root
 // table in constant memory.  The bins above M are the conjugates of those below (not written).
 __constant__ float2 c_w64_f32[32];
 __constant__ double2 c_w64_f64[32];
